@@ -1,0 +1,153 @@
+// capi.cu -- the extern "C" surface of libupp_geom.so (include/upp_geom.h): argument checks and
+// dispatch only.  No allocation, no host synchronisation, no state besides the launch counter.
+#include <atomic>
+
+#include "common.cuh"
+
+namespace upp {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
+
+int fps_launch(const float*, int, int, int, int32_t*, float*, void*, size_t, cudaStream_t);
+size_t fps_workspace_bytes(int, int);
+int knn_launch(const float*, const float*, int, int, int, int, float*, int64_t*, cudaStream_t);
+int chamfer_fwd_launch(const float*, const float*, int, int, int, float*, float*, int32_t*, int32_t*,
+                       float*, cudaStream_t);
+int chamfer_bwd_launch(const float*, const float*, const int32_t*, const int32_t*, const float*,
+                       const float*, int, int, int, float*, float*, cudaStream_t);
+int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
+int gather_grad_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
+int group_gather_launch(const float*, const float*, const int64_t*, int, int, int, int, float*,
+                        cudaStream_t);
+int group_bwd_launch(const float*, const float*, const int64_t*, const int32_t*, int, int, int, int,
+                     float*, cudaStream_t);
+
+}  // namespace upp
+
+using namespace upp;
+
+#define UPP_REQUIRE(cond) \
+  do {                    \
+    if (!(cond)) return UPP_ERR_INVALID_ARG; \
+  } while (0)
+
+static inline cudaStream_t S(upp_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int upp_version(void) { return UPP_VERSION; }
+
+const char* upp_error_string(int rc) {
+  switch (rc) {
+    case UPP_OK: return "ok";
+    case UPP_ERR_INVALID_ARG: return "upp_geom: invalid argument (null pointer, negative size, or k outside [1, N])";
+    case UPP_ERR_UNSUPPORTED: return "upp_geom: shape not supported by the sm_100a kernels";
+    case UPP_ERR_WORKSPACE: return "upp_geom: workspace missing or too small (see upp_fps_workspace_bytes)";
+    default: return rc > 0 ? cudaGetErrorString(static_cast<cudaError_t>(rc)) : "upp_geom: unknown error";
+  }
+}
+
+unsigned long long upp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t upp_fps_workspace_bytes(int B, int N, int M) {
+  (void)M;
+  if (B <= 0 || N <= 0) return 0;
+  return fps_workspace_bytes(B, N);
+}
+
+int upp_fps_f32(const float* xyz, int B, int N, int M, int32_t* idx_out, float* centers_out,
+                void* workspace, size_t workspace_bytes, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && M >= 0);
+  if (B == 0 || M == 0) return UPP_OK;
+  UPP_REQUIRE(N >= 1 && xyz != nullptr && idx_out != nullptr);
+  return fps_launch(xyz, B, N, M, idx_out, centers_out, workspace, workspace_bytes, S(stream));
+}
+
+int upp_gather_f32(const float* features, const int32_t* idx, int B, int C, int N, int M, float* out,
+                   upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && C >= 0 && N >= 0 && M >= 0);
+  if (static_cast<size_t>(B) * C * M == 0) return UPP_OK;
+  UPP_REQUIRE(N >= 1 && features && idx && out);
+  return gather_launch(features, idx, B, C, N, M, out, S(stream));
+}
+
+int upp_gather_grad_f32(const float* grad_out, const int32_t* idx, int B, int C, int N, int M,
+                        float* grad_features, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && C >= 0 && N >= 0 && M >= 0);
+  if (static_cast<size_t>(B) * C * N == 0) return UPP_OK;
+  UPP_REQUIRE(grad_features != nullptr);
+  UPP_REQUIRE(static_cast<size_t>(B) * C * M == 0 || (grad_out && idx));
+  return gather_grad_launch(grad_out, idx, B, C, N, M, grad_features, S(stream));
+}
+
+int upp_knn_f32(const float* ref, const float* query, int B, int N, int Q, int k, float* dist_out,
+                int64_t* idx_out, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && Q >= 0);
+  UPP_REQUIRE(k >= 1 && k <= N);
+  if (B == 0 || Q == 0) return UPP_OK;
+  UPP_REQUIRE(ref && query && idx_out);
+  return knn_launch(ref, query, B, N, Q, k, dist_out, idx_out, S(stream));
+}
+
+int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
+                        float* dist2, int32_t* idx1, int32_t* idx2, float* partial_sums,
+                        upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && M >= 0);
+  const size_t n1 = static_cast<size_t>(B) * N, n2 = static_cast<size_t>(B) * M;
+  UPP_REQUIRE(n1 == 0 || (dist1 && idx1));
+  UPP_REQUIRE(n2 == 0 || (dist2 && idx2));
+  if (N == 0 || M == 0 || B == 0) {  // reference: outputs stay torch::zeros (chamfer.cu:152-157)
+    cudaError_t e = cudaSuccess;
+    if (n1) { e = cudaMemsetAsync(dist1, 0, n1 * 4, S(stream)); if (e == cudaSuccess) e = cudaMemsetAsync(idx1, 0, n1 * 4, S(stream)); }
+    if (n2 && e == cudaSuccess) { e = cudaMemsetAsync(dist2, 0, n2 * 4, S(stream)); if (e == cudaSuccess) e = cudaMemsetAsync(idx2, 0, n2 * 4, S(stream)); }
+    if (partial_sums && e == cudaSuccess) e = cudaMemsetAsync(partial_sums, 0, 16, S(stream));
+    return static_cast<int>(e);
+  }
+  UPP_REQUIRE(xyz1 && xyz2);
+  return chamfer_fwd_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, partial_sums, S(stream));
+}
+
+int upp_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                        const float* grad_dist1, const float* grad_dist2, int B, int N, int M,
+                        float* grad_xyz1, float* grad_xyz2, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && M >= 0);
+  const size_t n1 = static_cast<size_t>(B) * N, n2 = static_cast<size_t>(B) * M;
+  UPP_REQUIRE(n1 == 0 || grad_xyz1);
+  UPP_REQUIRE(n2 == 0 || grad_xyz2);
+  if (N == 0 || M == 0 || B == 0) {
+    cudaError_t e = cudaSuccess;
+    if (n1) e = cudaMemsetAsync(grad_xyz1, 0, n1 * 12, S(stream));
+    if (n2 && e == cudaSuccess) e = cudaMemsetAsync(grad_xyz2, 0, n2 * 12, S(stream));
+    return static_cast<int>(e);
+  }
+  UPP_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && grad_dist1 && grad_dist2);
+  return chamfer_bwd_launch(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, B, N, M, grad_xyz1,
+                            grad_xyz2, S(stream));
+}
+
+int upp_group_f32(const float* xyz, int B, int N, int G, int k, float* neighborhood, float* center,
+                  int64_t* idx, int32_t* center_idx, void* workspace, size_t workspace_bytes,
+                  upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && G >= 0);
+  UPP_REQUIRE(k >= 1 && k <= N);
+  if (B == 0 || G == 0) return UPP_OK;
+  UPP_REQUIRE(xyz && neighborhood && center && idx && center_idx);
+  int rc = fps_launch(xyz, B, N, G, center_idx, center, workspace, workspace_bytes, S(stream));
+  if (rc != UPP_OK) return rc;
+  rc = knn_launch(xyz, center, B, N, G, k, nullptr, idx, S(stream));
+  if (rc != UPP_OK) return rc;
+  return group_gather_launch(xyz, center, idx, B, N, G, k, neighborhood, S(stream));
+}
+
+int upp_group_bwd_f32(const float* grad_nb, const float* grad_center, const int64_t* idx,
+                      const int32_t* center_idx, int B, int N, int G, int k, float* grad_xyz,
+                      upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && G >= 0 && k >= 0);
+  if (static_cast<size_t>(B) * N == 0) return UPP_OK;
+  UPP_REQUIRE(grad_xyz != nullptr);
+  UPP_REQUIRE(static_cast<size_t>(B) * G == 0 || (grad_nb && idx && center_idx));
+  return group_bwd_launch(grad_nb, grad_center, idx, center_idx, B, N, G, k, grad_xyz, S(stream));
+}
+
+}  // extern "C"

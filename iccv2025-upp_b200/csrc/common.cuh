@@ -1,0 +1,118 @@
+// common.cuh -- shared device helpers for libupp_geom (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "upp_geom.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libupp_geom is written for sm_100a (B200) only"
+#endif
+
+namespace upp {
+
+constexpr int kWarp = 32;
+
+// ---- launch accounting (bench.py's gpu_launches, tests) -------------------------------
+void count_launch(int n = 1);
+
+// ---- distance forms: spelled with explicit roundings, never left to contraction -------
+// chamfer.cu:40-43 / upstream sampling_gpu.cu: nvcc contracts dx*dx + dy*dy + dz*dz to this.
+__device__ __forceinline__ float dist_yxz(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+// KNN_CUDA knn.cu: ssd = 0; ssd += tmp*tmp over x,y,z.  fma(dx,dx,0) == rn(dx*dx).
+__device__ __forceinline__ float dist_xyz_acc(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// ---- warp reductions in one instruction (REDUX) ----------------------------------------
+__device__ __forceinline__ int redux_max_s32(int v) {
+  int r;
+  asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned redux_min_u32(unsigned v) {
+  unsigned r;
+  asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned redux_max_u32(unsigned v) {
+  unsigned r;
+  asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) -----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Stage `npts` xyz triples (AoS, 12 B each) from global into shared memory.
+// The 16-byte-aligned body goes through one TMA bulk copy issued by thread 0; a misaligned
+// source or the (<4 point) tail is copied with plain loads.  All threads of the CTA must
+// call this; `parity` is the caller-tracked phase bit of `bar` (flipped here when used).
+// On return the data is visible to every thread.
+__device__ __forceinline__ void stage_points(float* dst, const float* __restrict__ src, int npts,
+                                             uint64_t* bar, unsigned& parity) {
+  const int nfl = npts * 3;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+  const int body = aligned ? (nfl & ~3) : 0;  // floats moved by TMA (multiple of 16 B)
+  if (body > 0 && threadIdx.x == 0) {
+    mbar_expect_tx(bar, static_cast<unsigned>(body) * 4u);
+    bulk_g2s(dst, src, static_cast<unsigned>(body) * 4u, bar);
+  }
+  for (int i = body + threadIdx.x; i < nfl; i += blockDim.x) dst[i] = __ldg(src + i);
+  if (body > 0) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+  }
+  __syncthreads();
+}
+
+// ---- host-side launch check -----------------------------------------------------------
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UPP_OK : static_cast<int>(e);
+}
+
+}  // namespace upp

@@ -1,0 +1,253 @@
+// fps.cu -- farthest point sampling for sm_100a.
+//
+// Replaces pointnet2_ops furthest_point_sampling_kernel (reference call site utils/misc.py:18).
+// Upstream: one CTA per cloud, running min-distance array in GLOBAL memory (L2 round trip every
+// iteration), ~9 __syncthreads per iteration for a shared-memory tree arg-max.
+//
+// Here (fps_reg_kernel): one cloud per CTA,
+//   * the cloud is staged once into shared memory with a 1-D TMA bulk copy (UBLKCP);
+//   * every thread keeps its P points AND their running min-distance in REGISTERS for the
+//     whole kernel -- HBM traffic is 12N in + 4M(+12M) out per cloud, nothing else;
+//   * the block arg-max is two REDUX stages around ONE __syncthreads per iteration:
+//     warp max of the (order-preserving) float bit pattern, lowest matching point index by
+//     REDUX.MIN, per-warp winners double-buffered in shared memory;
+//   * ties resolve to the lowest point index, deterministically.
+// Semantics kept from upstream: start at index 0, temp = 1e10, d2 = min(d, temp), points with
+// x^2+y^2+z^2 <= 1e-3 (double compare) never selected, d = fma(dz,dz,fma(dx,dx,dy*dy)).
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace upp {
+
+constexpr float kSkipped = -1.0f;      // |p|^2 <= 1e-3 : bits 0xBF800000, s32 -1082130432
+constexpr float kOutOfRange = -0.5f;   // slot >= N     : bits 0xBF000000, s32 -1090519040 (lower)
+constexpr int kFpsMaxRegPoints = 8192; // largest N the register-resident kernel covers
+
+__device__ __forceinline__ float fps_initial_md(float x, float y, float z) {
+  const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+  return (static_cast<double>(mag) <= 1e-3) ? kSkipped : 1e10f;
+}
+
+template <int THREADS, int P>
+__global__ void __launch_bounds__(THREADS, 1)
+    fps_reg_kernel(const float* __restrict__ xyz, int N, int M, int32_t* __restrict__ idx_out,
+                   float* __restrict__ centers_out) {
+  constexpr int NWARPS = THREADS / kWarp;
+  extern __shared__ __align__(16) float s_xyz[];  // 3*N floats (AoS, as in global memory)
+  __shared__ int2 s_slot[2][kWarp];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.x;
+  const float* p = xyz + static_cast<size_t>(b) * N * 3;
+  int32_t* out = idx_out + static_cast<size_t>(b) * M;
+  float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
+
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned parity = 0;
+  stage_points(s_xyz, p, N, &s_bar, parity);
+
+  float x[P], y[P], z[P], md[P];
+#pragma unroll
+  for (int r = 0; r < P; ++r) {
+    const int i = t + r * THREADS;  // ascending in r: lowest-index tie-break inside a thread
+    if (i < N) {
+      x[r] = s_xyz[3 * i];
+      y[r] = s_xyz[3 * i + 1];
+      z[r] = s_xyz[3 * i + 2];
+      md[r] = fps_initial_md(x[r], y[r], z[r]);
+    } else {
+      x[r] = y[r] = z[r] = 0.f;
+      md[r] = kOutOfRange;
+    }
+  }
+
+  float cx = s_xyz[0], cy = s_xyz[1], cz = s_xyz[2];
+  if (t == 0) {
+    out[0] = 0;
+    if (cen) { cen[0] = cx; cen[1] = cy; cen[2] = cz; }
+  }
+
+  for (int j = 1; j < M; ++j) {
+    int best = INT_MIN;
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+      const float d = dist_yxz(x[r] - cx, y[r] - cy, z[r] - cz);
+      md[r] = fminf(md[r], d);
+      best = max(best, __float_as_int(md[r]));
+    }
+    // stage 1: warp winner (value, lowest index)
+    const int wbest = redux_max_s32(best);
+    unsigned cand = 0xffffffffu;
+    if (best == wbest) {
+#pragma unroll
+      for (int r = P - 1; r >= 0; --r)
+        if (__float_as_int(md[r]) == wbest) cand = static_cast<unsigned>(t + r * THREADS);
+    }
+    int sel = static_cast<int>(redux_min_u32(cand));
+    if (NWARPS > 1) {
+      // stage 2: block winner over the per-warp winners (one barrier, double-buffered slots)
+      int2* slot = s_slot[j & 1];
+      if (lane == 0) slot[warp] = make_int2(wbest, sel);
+      __syncthreads();
+      const int2 s = (lane < NWARPS) ? slot[lane] : make_int2(INT_MIN, INT_MAX);
+      const int bbest = redux_max_s32(s.x);
+      sel = static_cast<int>(redux_min_u32(s.x == bbest ? static_cast<unsigned>(s.y) : 0xffffffffu));
+    }
+    cx = s_xyz[3 * sel];
+    cy = s_xyz[3 * sel + 1];
+    cz = s_xyz[3 * sel + 2];
+    if (t == 0) {
+      out[j] = sel;
+      if (cen) { cen[3 * j] = cx; cen[3 * j + 1] = cy; cen[3 * j + 2] = cz; }
+    }
+  }
+}
+
+// Any-N fallback: min-distance array in a global workspace (L2-resident), xyz re-read from
+// global memory every iteration.  Same selection rule, same two-stage arg-max.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+    fps_global_kernel(const float* __restrict__ xyz, int N, int M, int32_t* __restrict__ idx_out,
+                      float* __restrict__ centers_out, float* __restrict__ temp) {
+  constexpr int NWARPS = THREADS / kWarp;
+  __shared__ int2 s_slot[2][kWarp];
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.x;
+  const float* p = xyz + static_cast<size_t>(b) * N * 3;
+  float* md = temp + static_cast<size_t>(b) * N;
+  int32_t* out = idx_out + static_cast<size_t>(b) * M;
+  float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
+
+  for (int i = t; i < N; i += THREADS) md[i] = fps_initial_md(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+  float cx = p[0], cy = p[1], cz = p[2];
+  if (t == 0) {
+    out[0] = 0;
+    if (cen) { cen[0] = cx; cen[1] = cy; cen[2] = cz; }
+  }
+  for (int j = 1; j < M; ++j) {
+    int best = INT_MIN;
+    unsigned besti = 0xffffffffu;
+    for (int i = t; i < N; i += THREADS) {
+      const float d = dist_yxz(p[3 * i] - cx, p[3 * i + 1] - cy, p[3 * i + 2] - cz);
+      const float m = fminf(md[i], d);
+      md[i] = m;
+      const int key = __float_as_int(m);
+      if (key > best) { best = key; besti = static_cast<unsigned>(i); }
+    }
+    const int wbest = redux_max_s32(best);
+    int sel = static_cast<int>(redux_min_u32(best == wbest ? besti : 0xffffffffu));
+    int2* slot = s_slot[j & 1];
+    if (lane == 0) slot[warp] = make_int2(wbest, sel);
+    __syncthreads();
+    const int2 s = (lane < NWARPS) ? slot[lane] : make_int2(INT_MIN, INT_MAX);
+    const int bbest = redux_max_s32(s.x);
+    sel = static_cast<int>(redux_min_u32(s.x == bbest ? static_cast<unsigned>(s.y) : 0xffffffffu));
+    cx = p[3 * sel];
+    cy = p[3 * sel + 1];
+    cz = p[3 * sel + 2];
+    if (t == 0) {
+      out[j] = sel;
+      if (cen) { cen[3 * j] = cx; cen[3 * j + 1] = cy; cen[3 * j + 2] = cz; }
+    }
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------
+
+struct FpsConfig {
+  int threads, p;
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Register-resident configuration for N <= kFpsMaxRegPoints.
+FpsConfig fps_pick_config(int N) {
+  const int want_p = env_int("UPP_FPS_P", 4);  // points per thread the heuristic aims for
+  int threads = pow2_ceil((N + want_p - 1) / want_p);
+  if (threads < 32) threads = 32;
+  if (threads > 1024) threads = 1024;
+  const int forced = env_int("UPP_FPS_THREADS", 0);
+  if (forced >= 32 && forced <= 1024 && (forced & (forced - 1)) == 0) threads = forced;
+  int p = pow2_ceil((N + threads - 1) / threads);
+  const int pmax = threads == 1024 ? 8 : 16;
+  while (p > pmax && threads < 1024) {
+    threads <<= 1;
+    p = pow2_ceil((N + threads - 1) / threads);
+  }
+  return {threads, p};
+}
+
+template <int THREADS, int P>
+static int launch_fps_reg(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
+                          cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(N) * 3 * sizeof(float);
+  auto kern = fps_reg_kernel<THREADS, P>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  kern<<<B, THREADS, smem, st>>>(xyz, N, M, idx, centers);
+  count_launch();
+  return launch_status();
+}
+
+template <int THREADS>
+static int dispatch_fps_p(int P, const float* xyz, int B, int N, int M, int32_t* idx,
+                          float* centers, cudaStream_t st) {
+  switch (P) {
+    case 1: return launch_fps_reg<THREADS, 1>(xyz, B, N, M, idx, centers, st);
+    case 2: return launch_fps_reg<THREADS, 2>(xyz, B, N, M, idx, centers, st);
+    case 4: return launch_fps_reg<THREADS, 4>(xyz, B, N, M, idx, centers, st);
+    case 8: return launch_fps_reg<THREADS, 8>(xyz, B, N, M, idx, centers, st);
+    case 16:
+      if constexpr (THREADS <= 512) return launch_fps_reg<THREADS, 16>(xyz, B, N, M, idx, centers, st);
+      return UPP_ERR_UNSUPPORTED;
+    default: return UPP_ERR_UNSUPPORTED;
+  }
+}
+
+int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
+               void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (N <= kFpsMaxRegPoints) {
+    const FpsConfig c = fps_pick_config(N);
+    switch (c.threads) {
+      case 32: return dispatch_fps_p<32>(c.p, xyz, B, N, M, idx, centers, st);
+      case 64: return dispatch_fps_p<64>(c.p, xyz, B, N, M, idx, centers, st);
+      case 128: return dispatch_fps_p<128>(c.p, xyz, B, N, M, idx, centers, st);
+      case 256: return dispatch_fps_p<256>(c.p, xyz, B, N, M, idx, centers, st);
+      case 512: return dispatch_fps_p<512>(c.p, xyz, B, N, M, idx, centers, st);
+      case 1024: return dispatch_fps_p<1024>(c.p, xyz, B, N, M, idx, centers, st);
+      default: return UPP_ERR_UNSUPPORTED;
+    }
+  }
+  const size_t need = static_cast<size_t>(B) * N * sizeof(float);
+  if (workspace == nullptr || workspace_bytes < need) return UPP_ERR_WORKSPACE;
+  fps_global_kernel<1024><<<B, 1024, 0, st>>>(xyz, N, M, idx, centers, static_cast<float*>(workspace));
+  count_launch();
+  return launch_status();
+}
+
+size_t fps_workspace_bytes(int B, int N) {
+  if (N <= kFpsMaxRegPoints) return 0;
+  return static_cast<size_t>(B) * N * sizeof(float);
+}
+
+}  // namespace upp

@@ -1,0 +1,23 @@
+"""upp_b200 -- B200 (sm_100a) implementation of the UPP point-geometry hot path behind the
+reference's own operator API.
+
+    pointnet2_utils.furthest_point_sample / gather_operation   (pointnet2_ops)
+    KNN                                                        (knn_cuda)
+    chamfer.forward / chamfer.backward                         (extensions/chamfer_dist)
+    fps, Group, ChamferFunction, ChamferDistanceL1/L2/L2_split (reference Python, mirrored)
+    parallel                                                   (batch sharding + NCCL loss all-reduce)
+
+Everything computes in libupp_geom.so (hand-written CUDA); importing this package without the
+built library raises -- there is no CPU or eager fallback.
+"""
+from . import _lib
+
+_lib.load()  # fail loudly, at import, if the CUDA library is missing
+
+from . import chamfer, ops, parallel, pointnet2_utils  # noqa: E402,F401
+from .knn import KNN  # noqa: E402,F401
+from .modules import (ChamferDistanceL1, ChamferDistanceL2, ChamferDistanceL2_split,  # noqa: E402,F401
+                      ChamferFunction, Group, fps)
+
+__version__ = "0.1.0"
+launch_count = _lib.launch_count

@@ -1,0 +1,218 @@
+"""Tensor-level entry points over the C ABI: checks, allocation, stream/device plumbing.
+
+torch is used for device memory, streams and autograd only; every computation below is a
+libupp_geom.so kernel.  Argument rules follow the ops these replace (file:line in each
+docstring): CUDA-only, fp32, contiguous; violations raise instead of printing.
+"""
+import torch
+
+from . import _lib
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(name, t):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (CPU not supported; there is no CPU fallback)")
+
+
+def _need(name, t, dtype, ndim):
+    _need_cuda(name, t)
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def _xyz(name, t):
+    _need(name, t, torch.float32, 3)
+    if t.shape[2] != 3:
+        raise ValueError(f"{name} must be (B, N, 3), got {tuple(t.shape)}")
+
+
+class _on:
+    """Make t's device current for the duration of the call (only when it is not already)."""
+    __slots__ = ("prev", "dev")
+
+    def __init__(self, t):
+        self.dev = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.dev:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def fps(xyz, npoint, want_centers=False):
+    """Farthest point sampling; replaces pointnet2_utils.furthest_point_sample (utils/misc.py:18)
+    and, with want_centers, also the gather of utils/misc.py:19.
+    xyz (B,N,3) f32 CUDA -> idx (B,npoint) int32 [, centers (B,npoint,3) f32]."""
+    _xyz("xyz", xyz)
+    npoint = int(npoint)
+    if npoint < 0:
+        raise ValueError("npoint must be >= 0")
+    B, N, _ = xyz.shape
+    if N == 0 and npoint > 0 and B > 0:
+        raise ValueError("cannot sample from an empty cloud")
+    lib = _lib.load()
+    idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+    centers = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device) if want_centers else None
+    wbytes = int(lib.upp_fps_workspace_bytes(B, N, npoint))
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=xyz.device) if wbytes else None
+    with _on(xyz):
+        rc = lib.upp_fps_f32(_ptr(xyz), B, N, npoint, _ptr(idx), _ptr(centers), _ptr(ws), wbytes, _stream(xyz))
+    _lib.check(rc, "upp_fps_f32")
+    return (idx, centers) if want_centers else idx
+
+
+def gather(features, idx):
+    """features (B,C,N) f32, idx (B,M) int32 -> (B,C,M); replaces gather_operation fwd (utils/misc.py:19)."""
+    _need("features", features, torch.float32, 3)
+    _need("idx", idx, torch.int32, 2)
+    B, C, N = features.shape
+    if idx.shape[0] != B:
+        raise ValueError(f"idx batch {idx.shape[0]} != features batch {B}")
+    M = idx.shape[1]
+    out = torch.empty((B, C, M), dtype=torch.float32, device=features.device)
+    with _on(features):
+        rc = _lib.load().upp_gather_f32(_ptr(features), _ptr(idx), B, C, N, M, _ptr(out), _stream(features))
+    _lib.check(rc, "upp_gather_f32")
+    return out
+
+
+def gather_grad(grad_out, idx, N):
+    """grad_out (B,C,M), idx (B,M) int32 -> grad_features (B,C,N) (scatter-add)."""
+    _need("grad_out", grad_out, torch.float32, 3)
+    _need("idx", idx, torch.int32, 2)
+    B, C, M = grad_out.shape
+    g = torch.empty((B, C, int(N)), dtype=torch.float32, device=grad_out.device)
+    with _on(grad_out):
+        rc = _lib.load().upp_gather_grad_f32(_ptr(grad_out), _ptr(idx), B, C, int(N), M, _ptr(g), _stream(grad_out))
+    _lib.check(rc, "upp_gather_grad_f32")
+    return g
+
+
+def knn(ref, query, k, want_dist=True):
+    """ref (B,N,3), query (B,Q,3) -> D (B,Q,k) f32 Euclidean ascending, I (B,Q,k) int64;
+    replaces KNN(k, transpose_mode=True).forward (models/Point_MAE_unify.py:69)."""
+    _xyz("ref", ref)
+    _xyz("query", query)
+    if ref.shape[0] != query.shape[0]:
+        raise ValueError(f"ref.shape={tuple(ref.shape)} != query.shape={tuple(query.shape)}")
+    if ref.device != query.device:
+        raise RuntimeError("ref and query must be on the same device")
+    B, N, _ = ref.shape
+    Q = query.shape[1]
+    k = int(k)
+    if not 1 <= k <= N:
+        raise ValueError(f"k={k} must be in [1, N={N}]")
+    D = torch.empty((B, Q, k), dtype=torch.float32, device=ref.device) if want_dist else None
+    I = torch.empty((B, Q, k), dtype=torch.int64, device=ref.device)
+    with _on(ref):
+        rc = _lib.load().upp_knn_f32(_ptr(ref), _ptr(query), B, N, Q, k, _ptr(D), _ptr(I), _stream(ref))
+    _lib.check(rc, "upp_knn_f32")
+    return D, I
+
+
+def chamfer_forward(xyz1, xyz2, want_sums=False):
+    """chamfer.forward (extensions/chamfer_dist/chamfer.cu:147-171):
+    -> [dist1 (B,N), dist2 (B,M) f32 squared, idx1, idx2 int32] (+ 4-float partial sums)."""
+    _xyz("xyz1", xyz1)
+    _xyz("xyz2", xyz2)
+    if xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError("xyz1 and xyz2 must have the same batch size")
+    if xyz1.device != xyz2.device:
+        raise RuntimeError("xyz1 and xyz2 must be on the same device")
+    B, N, _ = xyz1.shape
+    M = xyz2.shape[1]
+    dev = xyz1.device
+    d1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+    d2 = torch.empty((B, M), dtype=torch.float32, device=dev)
+    i1 = torch.empty((B, N), dtype=torch.int32, device=dev)
+    i2 = torch.empty((B, M), dtype=torch.int32, device=dev)
+    sums = torch.empty(4, dtype=torch.float32, device=dev) if want_sums else None
+    with _on(xyz1):
+        rc = _lib.load().upp_chamfer_fwd_f32(_ptr(xyz1), _ptr(xyz2), B, N, M, _ptr(d1), _ptr(d2),
+                                             _ptr(i1), _ptr(i2), _ptr(sums), _stream(xyz1))
+    _lib.check(rc, "upp_chamfer_fwd_f32")
+    return [d1, d2, i1, i2] + ([sums] if want_sums else [])
+
+
+def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
+    """chamfer.backward (extensions/chamfer_dist/chamfer.cu:203-229) -> [grad_xyz1, grad_xyz2].
+    grad_dist* may arrive non-contiguous (expanded scalars from mean/sqrt backward); they are
+    densified here -- the reference silently assumes dense (chamfer.cu:217)."""
+    _xyz("xyz1", xyz1)
+    _xyz("xyz2", xyz2)
+    _need("idx1", idx1, torch.int32, 2)
+    _need("idx2", idx2, torch.int32, 2)
+    _need_cuda("grad_dist1", grad_dist1)
+    _need_cuda("grad_dist2", grad_dist2)
+    B, N, _ = xyz1.shape
+    M = xyz2.shape[1]
+    if tuple(grad_dist1.shape) != (B, N) or tuple(grad_dist2.shape) != (B, M):
+        raise ValueError("grad_dist shapes must be (B,N) and (B,M)")
+    g1 = grad_dist1.to(torch.float32).contiguous()
+    g2 = grad_dist2.to(torch.float32).contiguous()
+    gx1 = torch.empty_like(xyz1)
+    gx2 = torch.empty_like(xyz2)
+    with _on(xyz1):
+        rc = _lib.load().upp_chamfer_bwd_f32(_ptr(xyz1), _ptr(xyz2), _ptr(idx1), _ptr(idx2), _ptr(g1),
+                                             _ptr(g2), B, N, M, _ptr(gx1), _ptr(gx2), _stream(xyz1))
+    _lib.check(rc, "upp_chamfer_bwd_f32")
+    return [gx1, gx2]
+
+
+def group(xyz, num_group, group_size):
+    """Fused Group divider (models/Point_MAE_unify.py:58-92):
+    -> neighborhood (B,G,k,3), center (B,G,3), idx (B,G,k) int64 local, center_idx (B,G) int32."""
+    _xyz("xyz", xyz)
+    B, N, _ = xyz.shape
+    G, k = int(num_group), int(group_size)
+    if not 1 <= k <= N:
+        raise ValueError(f"group_size={k} must be in [1, N={N}]")
+    dev = xyz.device
+    lib = _lib.load()
+    nb = torch.empty((B, G, k, 3), dtype=torch.float32, device=dev)
+    ce = torch.empty((B, G, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, G, k), dtype=torch.int64, device=dev)
+    cidx = torch.empty((B, G), dtype=torch.int32, device=dev)
+    wbytes = int(lib.upp_fps_workspace_bytes(B, N, G))
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev) if wbytes else None
+    with _on(xyz):
+        rc = lib.upp_group_f32(_ptr(xyz), B, N, G, k, _ptr(nb), _ptr(ce), _ptr(idx), _ptr(cidx),
+                               _ptr(ws), wbytes, _stream(xyz))
+    _lib.check(rc, "upp_group_f32")
+    return nb, ce, idx, cidx
+
+
+def group_backward(grad_nb, grad_center, idx, center_idx, N):
+    """Gradient of the fused Group w.r.t. xyz -> (B,N,3)."""
+    _need("grad_nb", grad_nb, torch.float32, 4)
+    _need("idx", idx, torch.int64, 3)
+    _need("center_idx", center_idx, torch.int32, 2)
+    B, G, k, _ = grad_nb.shape
+    if grad_center is not None:
+        _need("grad_center", grad_center, torch.float32, 3)
+    gx = torch.empty((B, int(N), 3), dtype=torch.float32, device=grad_nb.device)
+    with _on(grad_nb):
+        rc = _lib.load().upp_group_bwd_f32(_ptr(grad_nb), _ptr(grad_center), _ptr(idx), _ptr(center_idx),
+                                           B, int(N), G, k, _ptr(gx), _stream(grad_nb))
+    _lib.check(rc, "upp_group_bwd_f32")
+    return gx

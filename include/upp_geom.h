@@ -1,0 +1,157 @@
+/*
+ * upp_geom.h -- C ABI of libupp_geom.so: the B200 (sm_100a) implementation of the UPP
+ * point-geometry hot path (farthest-point sampling, kNN patch grouping, Chamfer fwd/bwd).
+ *
+ * This is the drop-in boundary.  Every entry point
+ *   - is extern "C", takes raw DEVICE pointers + sizes + an explicit stream
+ *     (upp_stream_t == cudaStream_t), no torch types;
+ *   - never allocates, never synchronises the host, never keeps state between calls
+ *     (safe to capture in a CUDA graph); scratch, where needed, is passed in;
+ *   - returns 0 (UPP_OK), a negative UPP_ERR_* for argument errors, or the positive
+ *     cudaError_t the launch produced.  Nothing is printed, nothing calls exit()
+ *     (the reference prints and carries on: extensions/chamfer_dist/chamfer.cu:166-169,224-227);
+ *   - all tensors are dense row-major ("contiguous") fp32 unless stated.
+ *
+ * Each prototype cites the reference interface it replaces (paths relative to the
+ * reference repo root, zhoujiahuan1991/ICCV2025-UPP).  INTEGRATION.md shows the Python
+ * (ctypes) binding a maintainer adds on the reference side.
+ */
+#ifndef UPP_GEOM_H_
+#define UPP_GEOM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* upp_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define UPP_API __attribute__((visibility("default")))
+#else
+#define UPP_API
+#endif
+
+#define UPP_OK 0
+#define UPP_ERR_INVALID_ARG (-1) /* null pointer, negative size, k > N, ... */
+#define UPP_ERR_UNSUPPORTED (-2) /* shape outside what the kernels cover (see each call) */
+#define UPP_ERR_WORKSPACE (-3)   /* workspace too small / missing */
+
+#define UPP_VERSION 100 /* 0.1.0 */
+
+/* Library version (UPP_VERSION of the build). */
+UPP_API int upp_version(void);
+
+/* Human-readable text for a return code of any function below (static storage). */
+UPP_API const char* upp_error_string(int rc);
+
+/* ---------------------------------------------------------------------------------------
+ * Farthest point sampling.
+ * Replaces pointnet2_ops.pointnet2_utils.furthest_point_sample(xyz, npoint)
+ *   call sites: utils/misc.py:18, tools/runner_module.py:151,450 (third-party CUDA op;
+ *   upstream pointnet2_ops/_ext-src/src/sampling_gpu.cu furthest_point_sampling_kernel).
+ * xyz (B,N,3) f32 -> idx_out (B,M) int32.  First sample is index 0; points with
+ * x^2+y^2+z^2 <= 1e-3 are never selected (upstream quirk, kept); ties resolve to the LOWEST
+ * point index (BASELINE.json north_star; upstream resolves exact ties thread-major).
+ * M > N is allowed (as upstream): once every point has been taken the arg-max keeps
+ * returning already-selected points.
+ * centers_out: optional (nullable) (B,M,3) f32 receiving xyz[b, idx[b,j], :] -- fuses the
+ *   gather_operation + two transposes of utils/misc.py:19.
+ * workspace: only needed when upp_fps_workspace_bytes(B,N,M) > 0 (N beyond the
+ *   register-resident limit); may be NULL otherwise.
+ */
+UPP_API size_t upp_fps_workspace_bytes(int B, int N, int M);
+UPP_API int upp_fps_f32(const float* xyz, int B, int N, int M, int32_t* idx_out, float* centers_out,
+                void* workspace, size_t workspace_bytes, upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Channel-first gather and its gradient.
+ * Replaces pointnet2_ops.pointnet2_utils.gather_operation(features, idx) fwd / bwd
+ *   call sites: utils/misc.py:19, tools/runner_module.py:153,455
+ *   (upstream sampling_gpu.cu gather_points_kernel / gather_points_grad_kernel).
+ * features (B,C,N) f32, idx (B,M) int32 in [0,N) -> out (B,C,M): out[b,c,j] = features[b,c,idx[b,j]].
+ * Gradient: grad_features (B,C,N) is OVERWRITTEN with the scatter-add of grad_out (B,C,M)
+ *   (the callee zero-fills; duplicate indices accumulate).
+ */
+UPP_API int upp_gather_f32(const float* features, const int32_t* idx, int B, int C, int N, int M,
+                   float* out, upp_stream_t stream);
+UPP_API int upp_gather_grad_f32(const float* grad_out, const int32_t* idx, int B, int C, int N, int M,
+                        float* grad_features, upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Exact brute-force k nearest neighbours.
+ * Replaces knn_cuda.KNN(k, transpose_mode=True).forward(ref, query)
+ *   constructed models/Point_MAE_unify.py:56, called :69 (third-party KNN_CUDA 0.2,
+ *   knn.cu cuComputeDistanceGlobal / cuInsertionSort / cuParallelSqrt, one cloud per
+ *   Python-loop iteration; here one launch for the batch).
+ * ref (B,N,3), query (B,Q,3) -> dist_out (B,Q,k) f32 EUCLIDEAN (sqrt applied), ascending;
+ * idx_out (B,Q,k) int64, 0-based; equal distances keep the lower ref index first.
+ * dist_out may be NULL (Group discards it).  Requires 1 <= k <= N (upstream reads out of
+ * bounds when k > N; rejected here with UPP_ERR_INVALID_ARG).
+ */
+UPP_API int upp_knn_f32(const float* ref, const float* query, int B, int N, int Q, int k,
+                float* dist_out, int64_t* idx_out, upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Chamfer distance forward.
+ * Replaces chamfer.forward(xyz1, xyz2) = chamfer_cuda_forward
+ *   extensions/chamfer_dist/chamfer_cuda.cpp:36-39, chamfer.cu:147-171 (kernel :15-145);
+ *   consumed by extensions/chamfer_dist/__init__.py:16.
+ * xyz1 (B,N,3), xyz2 (B,M,3) -> dist1 (B,N), dist2 (B,M) f32 SQUARED nearest distances and
+ * idx1 (B,N), idx2 (B,M) int32 arg-mins (lowest index on ties).  N == 0 or M == 0 yields
+ * zero-filled outputs, as the reference's torch::zeros does.
+ * partial_sums: optional (nullable) 4 floats, OVERWRITTEN with
+ *   { sum dist1, sum dist2, sum sqrt(dist1), sum sqrt(dist2) } over the whole call -- the
+ *   send buffer of the one NCCL all-reduce the batch-sharded loss needs (utils/dist_utils.py:41-48).
+ */
+UPP_API int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
+                        float* dist2, int32_t* idx1, int32_t* idx2, float* partial_sums,
+                        upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Chamfer distance backward.
+ * Replaces chamfer.backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2) = chamfer_cuda_backward
+ *   extensions/chamfer_dist/chamfer_cuda.cpp:36-39, chamfer.cu:203-229 (kernel :173-201);
+ *   consumed by extensions/chamfer_dist/__init__.py:24.
+ * grad_xyz1 (B,N,3), grad_xyz2 (B,M,3) are OVERWRITTEN with
+ *   grad_xyz1[b,j] = 2 g1[b,j] (x1_j - x2_idx1[j]) - sum_{k: idx2[k]==j} 2 g2[b,k] (x2_k - x1_j)
+ * and symmetrically for grad_xyz2; inf*0 = NaN appears exactly where the reference produces it.
+ * grad_dist1 (B,N), grad_dist2 (B,M) must be dense (the binding makes them so; the reference
+ * silently assumes it, chamfer.cu:217).
+ */
+UPP_API int upp_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* idx1,
+                        const int32_t* idx2, const float* grad_dist1, const float* grad_dist2,
+                        int B, int N, int M, float* grad_xyz1, float* grad_xyz2,
+                        upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused Group divider (opt-in fast path; the unchanged call site composes the ops above).
+ * Replaces the body of Group.forward  models/Point_MAE_unify.py:58-92:
+ *   misc.fps -> KNN -> index gather -> subtract centre.
+ * xyz (B,N,3) -> neighborhood (B,G,k,3) (already centre-subtracted), center (B,G,3),
+ * idx (B,G,k) int64 LOCAL ref indices (the gather_idx=True convention; the binding adds b*N
+ * for the flat convention), center_idx (B,G) int32.  idx / center_idx may be NULL.
+ * Same workspace rule as upp_fps_f32 (query with upp_fps_workspace_bytes(B,N,G)).
+ */
+UPP_API int upp_group_f32(const float* xyz, int B, int N, int G, int k, float* neighborhood,
+                  float* center, int64_t* idx, int32_t* center_idx, void* workspace,
+                  size_t workspace_bytes, upp_stream_t stream);
+
+/* Backward of the fused Group w.r.t. xyz:
+ *   grad_xyz[b, idx[b,g,j]] += grad_nb[b,g,j];  grad_xyz[b, center_idx[b,g]] += grad_center[b,g] - sum_j grad_nb[b,g,j]
+ * grad_xyz (B,N,3) is OVERWRITTEN.  grad_center may be NULL (treated as zero). */
+UPP_API int upp_group_bwd_f32(const float* grad_nb, const float* grad_center, const int64_t* idx,
+                      const int32_t* center_idx, int B, int N, int G, int k, float* grad_xyz,
+                      upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Introspection used by bench.py / tests: number of kernel launches the library has issued
+ * since load (monotonic, process-wide, relaxed atomic). */
+UPP_API unsigned long long upp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPP_GEOM_H_ */

@@ -1,0 +1,158 @@
+"""numpy/ctypes front-end to oracle/upp_oracle.c (TEST INFRASTRUCTURE ONLY).
+
+Each wrapper names the reference file:line its C function follows; see the C
+file for the restatement itself.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libupp_oracle.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(force=False):
+    """Compile upp_oracle.c with gcc (seconds)."""
+    src = os.path.join(_HERE, "upp_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.upp_oracle_knn.restype = ctypes.c_int
+        _lib.upp_oracle_group.restype = ctypes.c_int
+        _lib.upp_oracle_fps_upstream_block.restype = ctypes.c_int
+        _lib.upp_oracle_get_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def set_threads(n):
+    lib().upp_oracle_set_threads(ctypes.c_int(int(n)))
+
+
+def get_threads():
+    return int(lib().upp_oracle_get_threads())
+
+
+def upstream_block(N):
+    """upstream opt_n_threads(N) (pointnet2_ops sampling_gpu.cu)."""
+    return int(lib().upp_oracle_fps_upstream_block(ctypes.c_int(int(N))))
+
+
+def fps(xyz, M, block_size=0):
+    """pointnet2_utils.furthest_point_sample (reference utils/misc.py:18).
+    xyz (B,N,3) f32 -> (B,M) int32.  block_size=0: lowest-index ties."""
+    xyz = _f32(xyz)
+    B, N, _ = xyz.shape
+    out = np.zeros((B, M), dtype=np.int32)
+    lib().upp_oracle_fps(_p(xyz, _f32p), B, N, int(M), _p(out, _i32p), int(block_size))
+    return out
+
+
+def gather(feat, idx):
+    """pointnet2_utils.gather_operation fwd (reference utils/misc.py:19).
+    feat (B,C,N) f32, idx (B,M) int32 -> (B,C,M)."""
+    feat = _f32(feat)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    B, C, N = feat.shape
+    M = idx.shape[1]
+    out = np.empty((B, C, M), dtype=np.float32)
+    lib().upp_oracle_gather(_p(feat, _f32p), _p(idx, _i32p), B, C, N, M, _p(out, _f32p))
+    return out
+
+
+def gather_grad(gout, idx, N):
+    """gather_operation backward: scatter-add (B,C,M) -> (B,C,N)."""
+    gout = _f32(gout)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    B, C, M = gout.shape
+    out = np.empty((B, C, N), dtype=np.float32)
+    lib().upp_oracle_gather_grad(_p(gout, _f32p), _p(idx, _i32p), B, C, int(N), M, _p(out, _f32p))
+    return out
+
+
+def knn(ref, query, k):
+    """knn_cuda.KNN(k, transpose_mode=True)(ref, query)
+    (reference models/Point_MAE_unify.py:56,69).
+    ref (B,N,3), query (B,Q,3) -> D (B,Q,k) f32 Euclidean ascending, I (B,Q,k) int64."""
+    ref = _f32(ref)
+    query = _f32(query)
+    B, N, _ = ref.shape
+    Q = query.shape[1]
+    D = np.empty((B, Q, k), dtype=np.float32)
+    I = np.empty((B, Q, k), dtype=np.int64)
+    rc = lib().upp_oracle_knn(_p(ref, _f32p), _p(query, _f32p), B, N, Q, int(k),
+                              _p(D, _f32p), _p(I, _i64p))
+    if rc != 0:
+        raise ValueError(f"knn: k={k} must be in [1, N={N}]")
+    return D, I
+
+
+def chamfer_fwd(xyz1, xyz2):
+    """chamfer.forward (reference extensions/chamfer_dist/chamfer.cu:147-171).
+    -> dist1 (B,N), dist2 (B,M) squared f32; idx1, idx2 int32."""
+    xyz1 = _f32(xyz1)
+    xyz2 = _f32(xyz2)
+    B, N, _ = xyz1.shape
+    M = xyz2.shape[1]
+    d1 = np.empty((B, N), dtype=np.float32)
+    d2 = np.empty((B, M), dtype=np.float32)
+    i1 = np.empty((B, N), dtype=np.int32)
+    i2 = np.empty((B, M), dtype=np.int32)
+    lib().upp_oracle_chamfer_fwd(_p(xyz1, _f32p), _p(xyz2, _f32p), B, N, M,
+                                 _p(d1, _f32p), _p(d2, _f32p), _p(i1, _i32p), _p(i2, _i32p))
+    return d1, d2, i1, i2
+
+
+def chamfer_bwd(xyz1, xyz2, idx1, idx2, g1, g2):
+    """chamfer.backward (reference extensions/chamfer_dist/chamfer.cu:203-229)."""
+    xyz1 = _f32(xyz1)
+    xyz2 = _f32(xyz2)
+    idx1 = np.ascontiguousarray(idx1, dtype=np.int32)
+    idx2 = np.ascontiguousarray(idx2, dtype=np.int32)
+    g1 = _f32(g1)
+    g2 = _f32(g2)
+    B, N, _ = xyz1.shape
+    M = xyz2.shape[1]
+    gx1 = np.empty((B, N, 3), dtype=np.float32)
+    gx2 = np.empty((B, M, 3), dtype=np.float32)
+    lib().upp_oracle_chamfer_bwd(_p(xyz1, _f32p), _p(xyz2, _f32p), _p(idx1, _i32p),
+                                 _p(idx2, _i32p), _p(g1, _f32p), _p(g2, _f32p), B, N, M,
+                                 _p(gx1, _f32p), _p(gx2, _f32p))
+    return gx1, gx2
+
+
+def group(xyz, G, k):
+    """Group.forward (reference models/Point_MAE_unify.py:58-92), gather_idx=True
+    index convention: idx (B,G,k) int64 local, center_idx (B,G) int32."""
+    xyz = _f32(xyz)
+    B, N, _ = xyz.shape
+    nb = np.empty((B, G, k, 3), dtype=np.float32)
+    ce = np.empty((B, G, 3), dtype=np.float32)
+    idx = np.empty((B, G, k), dtype=np.int64)
+    cidx = np.empty((B, G), dtype=np.int32)
+    rc = lib().upp_oracle_group(_p(xyz, _f32p), B, N, int(G), int(k), _p(nb, _f32p),
+                                _p(ce, _f32p), _p(idx, _i64p), _p(cidx, _i32p))
+    if rc != 0:
+        raise ValueError(f"group: k={k} must be in [1, N={N}]")
+    return nb, ce, idx, cidx

@@ -1,0 +1,81 @@
+"""Per-op device timings at the BASELINE shapes (CUDA events, L2 flushed between iterations).
+Tuning aid; the numbers of record come from bench.py."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "iccv2025-upp_b200"), ROOT):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+import upp_b200  # noqa: E402
+from upp_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=20, warm=5, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator().manual_seed(0)
+    rows = []
+
+    def rec(name, fn, work=None):
+        if args.only and args.only not in name:
+            return
+        med, best = timeit(fn, flush=flush)
+        r = {"op": name, "us_median": round(med, 2), "us_min": round(best, 2)}
+        if work:
+            r.update(work(med))
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+
+    for (B, N, M) in [(32, 1024, 64), (32, 1096, 32), (32, 32, 32), (32, 972, 32), (32, 1024, 256), (32, 1228, 1024),
+                      (32, 64, 32), (128, 8192, 1024), (128, 1024, 64), (32, 2048, 128), (32, 1843, 1536),
+                      (1, 6144, 1024), (1, 2048, 1024), (16, 8192, 1024)]:
+        x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+        rec(f"fps B{B} N{N} M{M}", lambda: ops.fps(x, M),
+            lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "gflops": round(8.0 * N * (M - 1) * B / us / 1e3, 1)})
+    for (B, N, Q, k) in [(32, 1024, 64, 32), (32, 1096, 32, 16), (32, 32, 32, 16), (32, 64, 32, 8), (128, 1024, 64, 32),
+                         (32, 2048, 128, 32), (32, 1536, 128, 32)]:
+        r = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+        q = r[:, :Q].contiguous()
+        rec(f"knn B{B} N{N} Q{Q} k{k}", lambda: ops.knn(r, q, k), lambda us: {"gflops": round(8.0 * N * Q * B / us / 1e3, 1)})
+    for (B, N, G, k) in [(32, 1024, 64, 32), (128, 1024, 64, 32), (32, 2048, 128, 32)]:
+        x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+        rec(f"group B{B} N{N} G{G} k{k}", lambda: ops.group(x, G, k))
+    for (B, N, M) in [(64, 2048, 2048), (64, 1024, 1024), (64, 32, 1024), (64, 2048, 8192), (32, 1024, 1024)]:
+        a = torch.rand(B, N, 3, generator=g).to(dev)
+        b = torch.rand(B, M, 3, generator=g).to(dev)
+        rec(f"chamfer_fwd B{B} N{N} M{M}", lambda: ops.chamfer_forward(a, b),
+            lambda us: {"tflops_8NM": round(8.0 * N * M * B / us / 1e6, 2), "tflops_16NM": round(16.0 * N * M * B / us / 1e6, 2)})
+        d1, d2, i1, i2 = ops.chamfer_forward(a, b)
+        g1, g2 = torch.rand_like(d1), torch.rand_like(d2)
+        rec(f"chamfer_bwd B{B} N{N} M{M}", lambda: ops.chamfer_backward(a, b, i1, i2, g1, g2),
+            lambda us: {"gbs": round(56.0 * (N + M) * B / us / 1e3, 1)})
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "time_ops.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "iccv2025-upp_b200")
+for p in (PKG, os.path.join(PKG, "dropin"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def dev():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+def unit_sphere(x):
+    """Dataset-style normalisation (reference datasets/ModelNetDataset.py:20-26): centroid to the
+    origin, scale so the farthest point has radius 1 -- leaves a few points inside the FPS
+    skip radius sqrt(1e-3)."""
+    import torch
+    x = x - x.mean(dim=1, keepdim=True)
+    return x / x.norm(dim=2).max(dim=1)[0].view(-1, 1, 1)

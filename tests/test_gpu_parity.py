@@ -1,0 +1,343 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via upp_b200.ops) against the CPU
+oracle on the same seeded inputs.  Bar: indices bit-exact, values within 1e-5 relative (fp32),
+Chamfer distances bit-exact (same fma spelling as the reference kernel)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import unit_sphere
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # BASELINE.json north_star: "within 1e-5 relative in fp32"
+
+
+@pytest.fixture(scope="module")
+def U():
+    import upp_b200
+    return upp_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import c_oracle
+    return c_oracle
+
+
+def cube(B, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, N, 3, generator=g) * 2 - 1
+
+
+# ------------------------------------------------------------------ FPS ----------------------
+
+FPS_SHAPES = [  # (B, N, M)  -- SURVEY.md Appendix A census + edges
+    (3, 1, 1), (2, 5, 5), (2, 31, 7), (4, 32, 32), (4, 33, 16), (4, 64, 32), (3, 511, 64), (3, 513, 64),
+    (3, 972, 32), (4, 1024, 64), (2, 1023, 256), (2, 1025, 64), (3, 1096, 32), (2, 1228, 1024),
+    (2, 1459, 32), (2, 1536, 128), (2, 1624, 32), (2, 1843, 1536), (2, 2048, 128), (1, 6144, 1024),
+    (2, 8192, 1024),
+]
+
+
+@pytest.mark.parametrize("B,N,M", FPS_SHAPES)
+def test_fps_matches_oracle_cube(U, O, dev, B, N, M):
+    xyz = cube(B, N, 100 + N + M)
+    got = U.ops.fps(xyz.to(dev), M).cpu().numpy()
+    assert got.dtype == np.int32 and got.shape == (B, M)
+    assert np.array_equal(got, O.fps(xyz.numpy(), M))
+
+
+@pytest.mark.parametrize("B,N,M", [(4, 1024, 64), (2, 2048, 128), (2, 8192, 1024), (3, 1096, 32)])
+def test_fps_unit_sphere_skip_quirk(U, O, dev, B, N, M):
+    """Dataset-normalised clouds have points with |p|^2 <= 1e-3: never selected (upstream quirk)."""
+    xyz = unit_sphere(torch.randn(B, N, 3, generator=torch.Generator().manual_seed(7)) * 0.3)
+    near = (xyz.pow(2).sum(-1) <= 1e-3)
+    assert near.any(), "test input must exercise the skip rule"
+    got = U.ops.fps(xyz.to(dev), M).cpu().numpy()
+    assert np.array_equal(got, O.fps(xyz.numpy(), M))
+    sel = torch.from_numpy(got).long()
+    picked_near = torch.gather(near, 1, sel)[:, 1:]
+    assert not picked_near.any()
+
+
+def test_fps_exact_ties_lowest_index(U, O, dev):
+    """Integer lattice => many exactly equal distances; tie-break must be the lowest index."""
+    ax = torch.arange(8, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3) + 1.0
+    xyz = torch.cat([grid, grid.flip(1)], 0).contiguous()
+    got = U.ops.fps(xyz.to(dev), 100).cpu().numpy()
+    assert np.array_equal(got, O.fps(xyz.numpy(), 100))
+
+
+def test_fps_duplicates_all_skipped_and_m_gt_n(U, O, dev):
+    xyz = cube(2, 40, 3)
+    xyz[:, 20:] = xyz[:, :20]  # duplicated points
+    assert np.array_equal(U.ops.fps(xyz.to(dev), 40).cpu().numpy(), O.fps(xyz.numpy(), 40))
+    tiny = cube(2, 64, 4) * 0.01  # every point inside the skip radius -> index 0 forever
+    got = U.ops.fps(tiny.to(dev), 8).cpu().numpy()
+    assert np.array_equal(got, np.zeros((2, 8), np.int32))
+    assert np.array_equal(got, O.fps(tiny.numpy(), 8))
+    small = cube(2, 10, 5)
+    assert np.array_equal(U.ops.fps(small.to(dev), 25).cpu().numpy(), O.fps(small.numpy(), 25))
+
+
+def test_fps_large_n_workspace_path(U, O, dev):
+    xyz = cube(2, 10000, 11)
+    assert np.array_equal(U.ops.fps(xyz.to(dev), 48).cpu().numpy(), O.fps(xyz.numpy(), 48))
+
+
+def test_fps_centers_and_misc_fps_grad(U, O, dev):
+    xyz = cube(3, 500, 12)
+    x = xyz.to(dev).requires_grad_(True)
+    centers, idx = U.fps(x, 20)
+    o_idx = O.fps(xyz.numpy(), 20)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    want = np.take_along_axis(xyz.numpy(), o_idx[:, :, None].astype(np.int64), 1)
+    assert np.array_equal(centers.detach().cpu().numpy(), want)
+    w = torch.randn(3, 20, 3, generator=torch.Generator().manual_seed(1)).to(dev)
+    (centers * w).sum().backward()
+    g = np.zeros((3, 500, 3), np.float32)
+    for b in range(3):
+        for j in range(20):
+            g[b, o_idx[b, j]] += w[b, j].cpu().numpy()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g, rtol=RTOL, atol=0)
+
+
+def test_fps_empty(U, dev):
+    assert U.ops.fps(torch.zeros(0, 16, 3, device=dev), 4).shape == (0, 4)
+    assert U.ops.fps(torch.zeros(2, 16, 3, device=dev), 0).shape == (2, 0)
+
+
+# ------------------------------------------------------------------ gather -------------------
+
+
+def test_gather_fwd_bwd(U, O, dev):
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(3, 7, 50, generator=g)
+    idx = torch.randint(0, 50, (3, 20), generator=g, dtype=torch.int32)
+    idx[0, :5] = 3  # duplicates accumulate in the gradient
+    f = feat.to(dev).requires_grad_(True)
+    out = U.pointnet2_utils.gather_operation(f, idx.to(dev))
+    assert np.array_equal(out.detach().cpu().numpy(), O.gather(feat.numpy(), idx.numpy()))
+    go = torch.randn(3, 7, 20, generator=g)
+    out.backward(go.to(dev))
+    np.testing.assert_allclose(f.grad.cpu().numpy(), O.gather_grad(go.numpy(), idx.numpy(), 50),
+                               rtol=RTOL, atol=1e-7)
+
+
+# ------------------------------------------------------------------ kNN ----------------------
+
+KNN_SHAPES = [  # (B, N, Q, k)
+    (2, 32, 32, 16), (2, 32, 32, 32), (3, 64, 32, 8), (2, 972, 32, 16), (4, 1024, 64, 32),
+    (2, 1096, 32, 16), (2, 1536, 128, 32), (2, 2048, 128, 32), (2, 1624, 32, 16), (1, 5000, 70, 32),
+    (2, 33, 5, 1), (2, 100, 9, 31), (2, 3, 4, 3), (1, 300, 10, 48), (1, 200, 3, 200),
+]
+
+
+@pytest.mark.parametrize("B,N,Q,k", KNN_SHAPES)
+def test_knn_matches_oracle(U, O, dev, B, N, Q, k):
+    ref = cube(B, N, 200 + N)
+    qry = torch.cat([ref[:, : Q // 2], cube(B, Q - Q // 2, 300 + Q)], 1).contiguous()  # half are ref points
+    D, I = U.ops.knn(ref.to(dev), qry.to(dev), k)
+    oD, oI = O.knn(ref.numpy(), qry.numpy(), k)
+    assert I.dtype == torch.int64 and tuple(I.shape) == (B, Q, k)
+    assert np.array_equal(I.cpu().numpy(), oI)
+    assert np.array_equal(D.cpu().numpy(), oD)  # same fma order + IEEE sqrt -> bit-exact
+
+
+def test_knn_ties_keep_lower_index(U, O, dev):
+    ax = torch.arange(6, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3).contiguous()
+    qry = grid[:, ::7].contiguous()
+    D, I = U.ops.knn(grid.to(dev), qry.to(dev), 32)
+    oD, oI = O.knn(grid.numpy(), qry.numpy(), 32)
+    assert np.array_equal(I.cpu().numpy(), oI)
+    assert np.array_equal(D.cpu().numpy(), oD)
+
+
+def test_knn_module_modes_and_errors(U, O, dev):
+    ref, qry = cube(2, 128, 1), cube(2, 16, 2)
+    oD, oI = O.knn(ref.numpy(), qry.numpy(), 8)
+    D, I = U.KNN(k=8, transpose_mode=True)(ref.to(dev), qry.to(dev))
+    assert np.array_equal(I.cpu().numpy(), oI)
+    D2, I2 = U.KNN(k=8, transpose_mode=False)(ref.transpose(1, 2).to(dev), qry.transpose(1, 2).to(dev))
+    assert tuple(I2.shape) == (2, 8, 16)
+    assert np.array_equal(I2.transpose(1, 2).cpu().numpy(), oI)
+    assert np.array_equal(D2.transpose(1, 2).cpu().numpy(), oD)
+    with pytest.raises(ValueError):
+        U.ops.knn(ref.to(dev), qry.to(dev), 129)  # k > N: upstream UB, rejected here
+    with pytest.raises(RuntimeError):
+        U.ops.knn(ref, qry, 4)  # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------ Chamfer ------------------
+
+CH_SHAPES = [  # (B, N, M)
+    (4, 64, 128), (2, 1, 1), (3, 5, 3), (2, 32, 1024), (2, 1024, 1024), (2, 2048, 2048), (1, 2048, 8192),
+    (2, 513, 2049), (2, 1000, 4099), (3, 300, 200),
+]
+
+
+@pytest.mark.parametrize("B,N,M", CH_SHAPES)
+def test_chamfer_forward_bit_exact(U, O, dev, B, N, M):
+    g = torch.Generator().manual_seed(N * 7 + M)
+    a, b = torch.rand(B, N, 3, generator=g), torch.rand(B, M, 3, generator=g)
+    d1, d2, i1, i2 = [t.cpu().numpy() for t in U.chamfer.forward(a.to(dev), b.to(dev))]
+    o1, o2, j1, j2 = O.chamfer_fwd(a.numpy(), b.numpy())
+    assert i1.dtype == np.int32 and i2.dtype == np.int32
+    assert np.array_equal(i1, j1) and np.array_equal(i2, j2)
+    assert np.array_equal(d1, o1) and np.array_equal(d2, o2)
+
+
+def test_chamfer_against_reference_cuda_extension(U, dev):
+    """The reference's own chamfer.cu, compiled unmodified into oracle/_ref (when it travelled)."""
+    from oracle import ref_gpu
+    ref = ref_gpu.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/chamfer_ref*.so not built")
+    torch.cuda.set_device(0)  # the reference allocates on the current device, default stream
+    for (B, N, M, seed) in [(4, 64, 128, 0), (8, 1024, 1024, 1), (4, 2048, 2048, 2), (2, 2048, 8192, 3),
+                            (3, 777, 1301, 4)]:
+        g = torch.Generator().manual_seed(seed)
+        a, b = torch.rand(B, N, 3, generator=g).to(dev), torch.rand(B, M, 3, generator=g).to(dev)
+        mine = U.chamfer.forward(a, b)
+        torch.cuda.synchronize()
+        theirs = ref.forward(a, b)
+        torch.cuda.synchronize()
+        for x, y in zip(mine, theirs):
+            assert torch.equal(x, y)
+        g1, g2 = torch.rand(B, N, generator=g).to(dev), torch.rand(B, M, generator=g).to(dev)
+        mg = U.chamfer.backward(a, b, mine[2], mine[3], g1, g2)
+        torch.cuda.synchronize()
+        tg = ref.backward(a, b, theirs[2], theirs[3], g1, g2)
+        torch.cuda.synchronize()
+        for x, y in zip(mg, tg):  # both sides sum with float atomics in unspecified order
+            torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-6)
+
+
+def test_chamfer_backward_matches_oracle(U, O, dev):
+    g = torch.Generator().manual_seed(9)
+    a, b = torch.rand(3, 400, 3, generator=g), torch.rand(3, 250, 3, generator=g)
+    g1, g2 = torch.randn(3, 400, generator=g), torch.randn(3, 250, generator=g)
+    _, _, i1, i2 = U.chamfer.forward(a.to(dev), b.to(dev))
+    gx1, gx2 = U.chamfer.backward(a.to(dev), b.to(dev), i1, i2, g1.to(dev), g2.to(dev))
+    o1, o2 = O.chamfer_bwd(a.numpy(), b.numpy(), i1.cpu().numpy(), i2.cpu().numpy(), g1.numpy(), g2.numpy())
+    np.testing.assert_allclose(gx1.cpu().numpy(), o1, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gx2.cpu().numpy(), o2, rtol=1e-4, atol=1e-6)
+
+
+def test_chamfer_modules_l1_l2_and_autograd(U, O, dev):
+    g = torch.Generator().manual_seed(10)
+    a, b = torch.rand(4, 256, 3, generator=g), torch.rand(4, 300, 3, generator=g)
+    o1, o2, _, _ = O.chamfer_fwd(a.numpy(), b.numpy())
+    l2 = U.ChamferDistanceL2()(a.to(dev), b.to(dev)).item()
+    l1 = U.ChamferDistanceL1()(a.to(dev), b.to(dev)).item()
+    s1, s2 = U.ChamferDistanceL2_split()(a.to(dev), b.to(dev))
+    assert abs(l2 - (o1.mean() + o2.mean())) <= RTOL * abs(l2)
+    assert abs(l1 - (np.sqrt(o1).mean() + np.sqrt(o2).mean()) / 2) <= RTOL * abs(l1)
+    assert abs(s1.item() - o1.mean()) <= RTOL * abs(o1.mean()) and abs(s2.item() - o2.mean()) <= RTOL * abs(o2.mean())
+    # gradient through the non-contiguous expanded grad of mean(): compare with float64 autograd
+    ad = a.to(dev).requires_grad_(True)
+    bd = b.to(dev).requires_grad_(True)
+    U.ChamferDistanceL2()(ad, bd).backward()
+    a64 = a.double().requires_grad_(True)
+    b64 = b.double().requires_grad_(True)
+    dm = (a64[:, :, None, :] - b64[:, None, :, :]).pow(2).sum(-1)
+    (dm.min(2)[0].mean() + dm.min(1)[0].mean()).backward()
+    torch.testing.assert_close(ad.grad.cpu().double(), a64.grad, rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(bd.grad.cpu().double(), b64.grad, rtol=1e-4, atol=1e-9)
+
+
+def test_chamfer_l1_exact_zero_nan_rows(U, dev):
+    """partial subset of gt (runner_pretask.py:223): d == 0 -> sqrt' = inf -> inf*0 = NaN in exactly
+    the rows the reference poisons, nowhere else."""
+    g = torch.Generator().manual_seed(11)
+    gt = torch.rand(2, 128, 3, generator=g)
+    pred = torch.cat([gt[:, :32], torch.rand(2, 32, 3, generator=g)], 1).contiguous()
+    p = pred.to(dev).requires_grad_(True)
+    U.ChamferDistanceL1()(p, gt.to(dev)).backward()
+    nan_rows = torch.isnan(p.grad).any(-1).cpu()
+    assert nan_rows[:, :32].all()
+    assert not nan_rows[:, 32:].any()
+
+
+def test_chamfer_ignore_zeros_b1(U, O, dev):
+    g = torch.Generator().manual_seed(12)
+    a, b = torch.rand(1, 100, 3, generator=g), torch.rand(1, 120, 3, generator=g)
+    a[0, 60:] = 0  # zero-padded rows as produced by misc.random_dropping (utils/misc.py:313-314)
+    got = U.ChamferDistanceL2(ignore_zeros=True)(a.to(dev), b.to(dev)).item()
+    o1, o2, _, _ = O.chamfer_fwd(a[:, :60].numpy(), b.numpy())
+    assert abs(got - (o1.mean() + o2.mean())) <= RTOL * abs(got)
+
+
+def test_chamfer_empty_and_sums(U, O, dev):
+    out = U.chamfer.forward(torch.zeros(2, 0, 3, device=dev), torch.rand(2, 5, 3, device=dev))
+    assert out[0].shape == (2, 0) and torch.count_nonzero(out[1]) == 0 and torch.count_nonzero(out[3]) == 0
+    g = torch.Generator().manual_seed(13)
+    a, b = torch.rand(5, 700, 3, generator=g), torch.rand(5, 900, 3, generator=g)
+    d1, d2, _, _, sums = U.ops.chamfer_forward(a.to(dev), b.to(dev), want_sums=True)
+    want = np.array([d1.double().sum().item(), d2.double().sum().item(),
+                     d1.double().sqrt().sum().item(), d2.double().sqrt().sum().item()])
+    np.testing.assert_allclose(sums.cpu().numpy(), want, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ Group --------------------
+
+
+@pytest.mark.parametrize("B,N,G,k", [(4, 1024, 64, 32), (3, 1096, 32, 16), (3, 32, 32, 16), (3, 64, 32, 8),
+                                     (2, 2048, 128, 32), (2, 972, 32, 16)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_group_matches_oracle(U, O, dev, B, N, G, k, fused):
+    xyz = unit_sphere(cube(B, N, 400 + N))
+    o_nb, o_ce, o_idx, o_cidx = O.group(xyz.numpy(), G, k)
+    grp = U.Group(G, k, fused=fused)
+    nb, ce, idx, cidx = grp(xyz.to(dev), require_index=True, gather_idx=True)
+    assert np.array_equal(cidx.cpu().numpy(), o_cidx.astype(np.int64))
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    assert np.array_equal(ce.cpu().numpy(), o_ce)
+    assert np.array_equal(nb.cpu().numpy(), o_nb)
+    # flat index convention (gather_idx=False): + b*N base
+    nb2, ce2, fidx, fcidx = grp(xyz.to(dev), require_index=True, gather_idx=False)
+    base = (np.arange(B) * N)
+    assert np.array_equal(fidx.cpu().numpy(), (o_idx + base[:, None, None]).reshape(-1))
+    assert np.array_equal(fcidx.cpu().numpy(), (o_cidx.astype(np.int64) + base[:, None]).reshape(-1))
+    assert torch.equal(nb2, nb) and torch.equal(ce2, ce)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_group_backward(U, O, dev, fused):
+    xyz = cube(2, 200, 21)
+    _, _, o_idx, o_cidx = O.group(xyz.numpy(), 8, 4)
+    x = xyz.to(dev).requires_grad_(True)
+    nb, ce = U.Group(8, 4, fused=fused)(x)
+    g = torch.Generator().manual_seed(3)
+    wn, wc = torch.randn(2, 8, 4, 3, generator=g), torch.randn(2, 8, 3, generator=g)
+    ((nb * wn.to(dev)).sum() + (ce * wc.to(dev)).sum()).backward()
+    want = np.zeros((2, 200, 3), np.float64)
+    for b in range(2):
+        for gg in range(8):
+            want[b, o_cidx[b, gg]] += wc[b, gg].numpy() - wn[b, gg].numpy().sum(0)
+            for j in range(4):
+                want[b, o_idx[b, gg, j]] += wn[b, gg, j].numpy()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ drop-in imports ----------
+
+
+def test_dropin_modules_resolve_reference_imports(U, O, dev):
+    import chamfer  # reference extensions/chamfer_dist/__init__.py:10
+    from knn_cuda import KNN  # reference models/Point_MAE_unify.py:16
+    from pointnet2_ops import pointnet2_utils  # reference utils/misc.py:10
+    xyz = cube(2, 256, 31)
+    x = xyz.to(dev)
+    idx = pointnet2_utils.furthest_point_sample(x, 16)
+    data = pointnet2_utils.gather_operation(x.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    o_idx = O.fps(xyz.numpy(), 16)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    assert np.array_equal(data.cpu().numpy(), np.take_along_axis(xyz.numpy(), o_idx[:, :, None].astype(np.int64), 1))
+    _, I = KNN(k=8, transpose_mode=True)(x, data)
+    assert np.array_equal(I.cpu().numpy(), O.knn(xyz.numpy(), data.cpu().numpy(), 8)[1])
+    d1, d2, i1, i2 = chamfer.forward(x, data)
+    assert torch.count_nonzero(d2) == 0  # sampled points are cloud points: exact zeros
+    assert U.launch_count() > 0
