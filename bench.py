@@ -1,0 +1,524 @@
+#!/usr/bin/env python
+"""bench.py -- clouds/s for the UPP point-geometry hot path (FPS + kNN Group + Chamfer fwd/bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic clouds.  Default workload
+`upp_cls_geometry+chamfer` = every FPS / Group call of one UPP ModelNet40 classification
+forward+backward (BASELINE.json configs[1]; shape census SURVEY.md 3.1 / Appendix A, B=32,
+1024 points + 72 noise points) followed by the Completion-Prompter Chamfer-L1 fwd+bwd on the
+rebuilt 1024 points (tools/runner_pretask.py:222).  Other BASELINE configs: --workload c1|c3|c4|c5.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs in HBM, CUDA events,
+L2 flushed between steps, max over ranks); `e2e` = same metric through the public module API with
+pinned-host inputs copied H2D and the loss read back D2H every step; `roofline` = the dominant
+kernel measured live with CUDA events; `cpu_baseline` = the reference's pure-torch formulation
+(oracle/torch_formulation.py) timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "iccv2025-upp_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "point clouds/sec for FPS+kNN group+Chamfer fwd/bwd"
+UNIT = "clouds/s"
+N_SM, FP32_LANES = 148, 128
+
+
+# ----------------------------------------------------------------------------- inputs --------
+
+def unit_sphere(x):
+    x = x - x.mean(dim=1, keepdim=True)
+    return x / x.norm(dim=2).max(dim=1)[0].view(-1, 1, 1)
+
+
+def make_inputs(workload, B, seed):
+    """Synthetic host tensors of the workload's shapes (float32, CPU)."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=g)  # noqa: E731
+    if workload == "upp_cls_geometry+chamfer":
+        clean = unit_sphere(torch.randn(B, 1024, 3, generator=g) * 0.35)
+        lidar = clean[:, torch.randint(0, 1024, (48,), generator=g)] * (1.02 + 0.28 * r(1, 48, 1))
+        gn = torch.randn(B, 24, 3, generator=g) * 0.2
+        gn = gn + gn / gn.norm(dim=-1, keepdim=True) * 0.9
+        return {"pts": torch.cat([clean, lidar, gn], 1).contiguous(),          # (B,1096,3) misc.py:28-46
+                "rebuild": (clean[:, torch.randperm(1024, generator=g)] + 0.02 * torch.randn(B, 1024, 3, generator=g)).contiguous(),
+                "target": clean.contiguous(),
+                "w_nb": torch.randn(B, 64, 32, 3, generator=g), "w_c5": torch.randn(B, 32, 3, generator=g)}
+    if workload == "c1":
+        return {"pts": (r(B, 1024, 3) * 2 - 1).contiguous()}
+    if workload == "c3":
+        return {"xyz1": r(B, 2048, 3).contiguous(), "xyz2": r(B, 2048, 3).contiguous()}
+    if workload == "c4":
+        return {"pts": unit_sphere(torch.randn(B, 8192, 3, generator=g) * 0.35).contiguous()}
+    if workload == "c5":
+        return {"pts": unit_sphere(torch.randn(B, 2048, 3, generator=g) * 0.35).contiguous()}
+    raise SystemExit(f"unknown workload {workload}")
+
+
+DEFAULT_B = {"upp_cls_geometry+chamfer": 32, "c1": 32, "c3": 64, "c4": 128, "c5": 32}
+DESCR = {
+    "upp_cls_geometry+chamfer": "all FPS/Group calls of one UPP ModelNet40 cls fwd+bwd (BASELINE configs[1] census: "
+                                "Group(32,16)x3, Group(64,32), Group(32,8), fps 1024->256, fps 1228->1024) + "
+                                "Chamfer-L1 fwd+bwd 1024 vs 1024, B=32 per GPU",
+    "c1": "Point-MAE Group divider FPS 64 + kNN k=32, B=32, N=1024 (BASELINE configs[0])",
+    "c3": "Chamfer L1 fwd+bwd B=64, 2048 vs 2048 (BASELINE configs[2])",
+    "c4": "ShapeNet55-scale grouping FPS 8192->1024 then Group(64,32), B=128 (BASELINE configs[3])",
+    "c5": "ShapeNetPart Group(128,32) on 2048 points, B=32 (BASELINE configs[4], grouping part)",
+}
+
+
+# ----------------------------------------------------------------------------- GPU steps -----
+
+class GpuWorkload:
+    """The step expressed twice: `run_ops` on the C-ABI-level ops (static, CUDA-graph friendly) and
+    `run_modules` on the public module API with autograd (what a user of the reference calls)."""
+
+    def __init__(self, name, host, dev, world):
+        import upp_b200
+        self.U, self.ops, self.par = upp_b200, upp_b200.ops, upp_b200.parallel
+        self.name, self.dev, self.world = name, dev, world
+        self.host = {k: v.pin_memory() for k, v in host.items()}
+        self.d = {k: v.to(dev) for k, v in host.items()}
+        self.B = next(iter(host.values())).shape[0]
+        self.timers = None  # when set: list collecting (label, start_event, stop_event)
+        U = upp_b200
+        self.g32_16, self.g64_32, self.g32_8 = U.Group(32, 16), U.Group(64, 32), U.Group(32, 8)
+        self.g128_32 = U.Group(128, 32)
+        self.cd_l1 = U.ChamferDistanceL1()
+
+    # -- per-op event timing (roofline pass) --
+    def _t(self, label, fn, *a, **k):
+        if self.timers is None:
+            return fn(*a, **k)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn(*a, **k)
+        e.record()
+        self.timers.append((label, s, e))
+        return out
+
+    def h2d_bytes(self):
+        keys = {"upp_cls_geometry+chamfer": ("pts", "rebuild", "target")}.get(self.name, tuple(self.host))
+        return sum(self.host[k].numel() * 4 for k in keys), keys
+
+    # -- ops-level step --
+    def run_ops(self, d):
+        o, t = self.ops, self._t
+        n = self.name
+        if n == "upp_cls_geometry+chamfer":
+            B = self.B
+            g1 = t("group N1096 G32 k16", o.group, d["pts"], 32, 16)
+            t("group N32 G32 k16", o.group, g1[1], 32, 16)
+            keep = d["pts"][:, :972].contiguous()
+            t("group N972 G32 k16", o.group, keep, 32, 16)
+            i1, c1 = t("fps N1024 M256", o.fps, d["rebuild"], 256, True)
+            cat = torch.cat([keep, c1], 1)
+            i2, c2 = t("fps N1228 M1024", o.fps, cat, 1024, True)
+            g4 = t("group N1024 G64 k32", o.group, c2, 64, 32)
+            g5 = t("group N64 G32 k8", o.group, g4[1], 32, 8)
+            d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward, d["rebuild"], d["target"], True)
+            if self.world > 1:
+                self.par.reduce_sums(sums)
+            nglob = float(B * self.world * 1024)
+            loss = (sums[2] + sums[3]) / (2.0 * nglob)
+            # backward chain: G5 -> G4 -> fps(1228->1024) gather -> fps(1024->256) gather, + Chamfer
+            gc4 = t("group_bwd N64", o.group_backward, torch.zeros_like(g5[0]), d["w_c5"], g5[2], g5[3], 64)
+            gx = t("group_bwd N1024", o.group_backward, d["w_nb"], gc4, g4[2], g4[3], 1024)
+            gcat = t("gather_grad N1228", o.gather_grad, gx.transpose(1, 2).contiguous(), i2, 1228)
+            gc1 = gcat[:, :, 972:].contiguous()
+            greb = t("gather_grad N1024", o.gather_grad, gc1, i1, 1024).transpose(1, 2)
+            gd1 = (0.25 / nglob) / torch.sqrt(d1)
+            gd2 = (0.25 / nglob) / torch.sqrt(d2)
+            ga, _ = t("chamfer_bwd N1024 M1024", o.chamfer_backward, d["rebuild"], d["target"], j1, j2, gd1, gd2)
+            self.grad = ga + greb
+            return loss
+        if n == "c1":
+            nb, ce, _, _ = t("group N1024 G64 k32", o.group, d["pts"], 64, 32)
+            return ce[0, 0, 0]
+        if n == "c3":
+            nglob = float(self.B * self.world * 2048)
+            d1, d2, j1, j2, sums = t("chamfer_fwd N2048 M2048", o.chamfer_forward, d["xyz1"], d["xyz2"], True)
+            if self.world > 1:
+                self.par.reduce_sums(sums)
+            gd1, gd2 = (0.25 / nglob) / torch.sqrt(d1), (0.25 / nglob) / torch.sqrt(d2)
+            self.grad = t("chamfer_bwd N2048 M2048", o.chamfer_backward, d["xyz1"], d["xyz2"], j1, j2, gd1, gd2)
+            return (sums[2] + sums[3]) / (2.0 * nglob)
+        if n == "c4":
+            _, c = t("fps N8192 M1024", o.fps, d["pts"], 1024, True)
+            nb, ce, _, _ = t("group N1024 G64 k32", o.group, c, 64, 32)
+            return ce[0, 0, 0]
+        if n == "c5":
+            nb, ce, _, _ = t("group N2048 G128 k32", o.group, d["pts"], 128, 32)
+            return ce[0, 0, 0]
+        raise SystemExit(n)
+
+    # -- module-level step (public API + autograd), used for e2e --
+    def run_modules(self, d):
+        U, n = self.U, self.name
+        if n == "upp_cls_geometry+chamfer":
+            _, ce1 = self.g32_16(d["pts"])
+            self.g32_16(ce1)
+            keep = d["pts"][:, :972].contiguous()
+            self.g32_16(keep)
+            reb = d["rebuild"].detach().requires_grad_(True)
+            c1, _ = U.fps(reb, 256)
+            c2, _ = U.fps(torch.cat([keep, c1], 1), 1024)
+            nb4, ce4 = self.g64_32(c2)
+            _, ce5 = self.g32_8(ce4)
+            if self.world > 1:
+                cd = self.par.sharded_chamfer(reb, d["target"], "l1", n_global_clouds=self.B * self.world)
+            else:
+                cd = self.cd_l1(reb, d["target"])
+            loss = cd + 1e-9 * ((nb4 * d["w_nb"]).sum() + (ce5 * d["w_c5"]).sum())
+            loss.backward()
+            self.grad = reb.grad
+            return cd.detach()
+        if n == "c3":
+            a = d["xyz1"].detach().requires_grad_(True)
+            b = d["xyz2"].detach().requires_grad_(True)
+            if self.world > 1:
+                loss = self.par.sharded_chamfer(a, b, "l1", n_global_clouds=self.B * self.world)
+            else:
+                loss = self.cd_l1(a, b)
+            loss.backward()
+            return loss.detach()
+        if n == "c1":
+            nb, ce = self.g64_32(d["pts"])
+            return ce[0, 0, 0]
+        if n == "c4":
+            c, _ = U.fps(d["pts"], 1024)
+            nb, ce = self.g64_32(c)
+            return ce[0, 0, 0]
+        if n == "c5":
+            nb, ce = self.g128_32(d["pts"])
+            return ce[0, 0, 0]
+        raise SystemExit(n)
+
+
+# algorithmic work per launch (SURVEY.md 8d / DESIGN.md "Kernels"): label -> (flops, bytes) per cloud
+def op_work(label):
+    f = label.split()
+    kind = f[0]
+    v = {x[0]: int(x[1:]) for x in f[1:] if x[1:].isdigit()}
+    if kind == "fps":
+        N, M = v["N"], v["M"]
+        return 8.0 * N * (M - 1), 12.0 * N + 16.0 * M
+    if kind == "group":
+        N, G, k = v["N"], v["G"], v["k"]
+        return 8.0 * N * (G - 1) + 8.0 * G * N, 12.0 * N + 12.0 * G * k + 12.0 * G + 8.0 * G * k + 4.0 * G
+    if kind == "chamfer_fwd":
+        N, M = v["N"], v["M"]
+        return 8.0 * N * M, 20.0 * (N + M)
+    if kind == "chamfer_bwd":
+        N, M = v["N"], v["M"]
+        return 0.0, 56.0 * (N + M)
+    if kind == "group_bwd":
+        return 0.0, 0.0
+    if kind == "gather_grad":
+        return 0.0, 0.0
+    return 0.0, 0.0
+
+
+# ----------------------------------------------------------------------------- clocks --------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arms ------
+
+def cpu_step(workload, host):
+    """The reference's pure-torch formulation of the same step, on host cores."""
+    from oracle import torch_formulation as T
+    if workload == "upp_cls_geometry+chamfer":
+        _, ce1 = T.group(host["pts"], 32, 16)
+        T.group(ce1, 32, 16)
+        keep = host["pts"][:, :972]
+        T.group(keep, 32, 16)
+        reb = host["rebuild"].clone().requires_grad_(True)
+        c1, _ = T.fps(reb, 256)
+        c2, _ = T.fps(torch.cat([keep, c1], 1), 1024)
+        nb4, ce4 = T.group(c2, 64, 32)
+        _, ce5 = T.group(ce4, 32, 8)
+        loss = T.chamfer_l1(reb, host["target"]) + ((nb4 * host["w_nb"]).sum() + (ce5 * host["w_c5"]).sum()) * 1e-9
+        loss.backward()
+        return float(loss.detach())
+    if workload == "c1":
+        return float(T.group(host["pts"], 64, 32)[1][0, 0, 0])
+    if workload == "c3":
+        a = host["xyz1"].clone().requires_grad_(True)
+        b = host["xyz2"].clone().requires_grad_(True)
+        loss = T.chamfer_l1(a, b)
+        loss.backward()
+        return float(loss.detach())
+    if workload == "c4":
+        c, _ = T.fps(host["pts"], 1024)
+        return float(T.group(c, 64, 32)[1][0, 0, 0])
+    if workload == "c5":
+        return float(T.group(host["pts"], 128, 32)[1][0, 0, 0])
+    raise SystemExit(workload)
+
+
+def cpu_sample_batch(workload, B):
+    """Bounded sample: the CPU arm processes this many clouds per step (same shapes per cloud)."""
+    cap = {"upp_cls_geometry+chamfer": 32, "c1": 32, "c3": 8, "c4": 4, "c5": 32}[workload]
+    return min(B, cap)
+
+
+def time_cpu(workload, B, seed, steps, warmup, budget_s=25.0):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    bs = cpu_sample_batch(workload, B)
+    host = make_inputs(workload, bs, seed)
+    for _ in range(warmup):
+        cpu_step(workload, host)
+    ts, t_all = [], time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(workload, host)
+        ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    sec = statistics.median(ts)
+    return {"value": bs / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{bs} clouds/step x {len(ts)} steps of the same per-cloud shapes, pure-torch formulation "
+                      f"(oracle/torch_formulation.py), median step {sec * 1e3:.1f} ms"}, sec, bs
+
+
+# ----------------------------------------------------------------------------- main ----------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="upp_cls_geometry+chamfer", choices=sorted(DEFAULT_B))
+    ap.add_argument("--batch", type=int, default=0, help="clouds per GPU (default: the config's B)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = args.batch or DEFAULT_B[args.workload]
+    config = {"workload": args.workload, "description": DESCR[args.workload], "clouds_per_gpu": B,
+              "l2": "flushed between timed steps (256 MiB memset outside the event pair); inputs are << L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, sec, bs = time_cpu(args.workload, B, 0, args.steps, args.warmup, budget_s=120.0)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, clouds_per_step=bs), "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import upp_b200
+
+    host = make_inputs(args.workload, B, seed=rank)
+    W = GpuWorkload(args.workload, host, dev, world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: CUDA-graph replay of the ops-level step ----
+    for _ in range(2):
+        W.run_ops(W.d)
+    torch.cuda.synchronize()
+    graph, use_graph = None, not args.no_graph and world == 1
+    launches_per_step = None
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            c0 = upp_b200.launch_count()
+            with torch.cuda.graph(graph):
+                static_loss = W.run_ops(W.d)
+            launches_per_step = upp_b200.launch_count() - c0
+        except Exception as ex:  # capture unsupported: fall back to eager launches, and say so
+            graph, use_graph = None, False
+            config["graph_error"] = str(ex)[:120]
+            torch.cuda.synchronize()
+    if launches_per_step is None:
+        c0 = upp_b200.launch_count()
+        W.run_ops(W.d)
+        launches_per_step = upp_b200.launch_count() - c0
+    config["launch_mode"] = "cuda_graph_replay" if use_graph else "eager"
+
+    def one_step():
+        if use_graph:
+            graph.replay()
+            return static_loss
+        return W.run_ops(W.d)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        one_step()
+        e.record()
+        evs.append((s, e))
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end arm: module API, pinned host -> device every step, loss read back ----
+    h2d_bytes, h2d_keys = W.h2d_bytes()
+    dd = dict(W.d)
+
+    def e2e_step():
+        for k in h2d_keys:
+            dd[k] = W.host[k].to(dev, non_blocking=True)
+        return W.run_modules(dd).item()  # D2H of the step's result
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        e2e_step()
+        e.record()
+        evs.append((s, e))
+    barrier()
+    e2e_ms = sum(s.elapsed_time(e) for s, e in evs)
+
+    # ---- per-kernel pass (roofline): eager ops with CUDA events around every op ----
+    per_op = {}
+    for it in range(args.warmup + args.steps):
+        W.timers = []
+        flush.zero_()
+        W.run_ops(W.d)
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            for label, s, e in W.timers:
+                per_op.setdefault(label, []).append(s.elapsed_time(e))
+        W.timers = None
+    op_ms = {k: sum(v) / len(v) for k, v in per_op.items()}
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    clouds = B * world * args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    fp32_peak = N_SM * FP32_LANES * 2 * sm_max * 1e6 / 1e12  # TFLOP/s
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    kernels = []
+    for label, ms in sorted(op_ms.items(), key=lambda kv: -kv[1]):
+        fl, by = op_work(label)
+        kernels.append({"op": label, "ms": round(ms, 5), "share": round(ms / sum(op_ms.values()), 4),
+                        "tflops": round(fl * B / (ms * 1e-3) / 1e12, 4), "gbs": round(by * B / (ms * 1e-3) / 1e9, 2)})
+    top = kernels[0]
+    fl, by = op_work(top["op"])
+    fp32_bound = fl > 0
+    roofline = {"kernel": top["op"], "bound": "fp32" if fp32_bound else "hbm",
+                "achieved": top["tflops"] if fp32_bound else top["gbs"],
+                "peak": round(fp32_peak, 2) if fp32_bound else hbm_peak,
+                "unit": "TFLOP/s" if fp32_bound else "GB/s",
+                "frac": round((top["tflops"] / fp32_peak) if fp32_bound else (top["gbs"] / hbm_peak), 5),
+                "traffic": None,
+                "peak_source": (f"computed 148 SM x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no fp32 figure; "
+                                "K=3 distances are not a tensor-core contraction)") if fp32_bound
+                else ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"),
+                "hbm_gbs": top["gbs"], "hbm_frac": round(top["gbs"] / hbm_peak, 5),
+                "note": "FPS is a serial chain of M-1 block arg-max rounds: latency-bound, see DESIGN.md" if top["op"].startswith(("fps", "group")) else ""}
+
+    line = {"metric": METRIC, "value": clouds / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": clouds / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps, "api": "upp_b200 modules + autograd, eager"},
+            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+            "roofline": roofline, "kernels": kernels}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"], _, _ = time_cpu(args.workload, B, 0, 5, 1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

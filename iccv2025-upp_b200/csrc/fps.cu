@@ -177,12 +177,15 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-// Register-resident configuration for N <= kFpsMaxRegPoints.
+// Register-resident configuration for N <= kFpsMaxRegPoints.  Measured on B200 (scripts/
+// time_ops.py --sweep-fps): the per-iteration cost is dominated by fixed latencies (4 REDUX,
+// 3 LDS, 1 BAR ~ 270 cycles), so up to 512 threads with 2 points each is fastest for N ~ 1k;
+// 1024 threads lose to 512 (BAR.SYNC: 45 -> 77 cycles, more per-warp reduction overhead).
 FpsConfig fps_pick_config(int N) {
-  const int want_p = env_int("UPP_FPS_P", 4);  // points per thread the heuristic aims for
+  const int want_p = env_int("UPP_FPS_P", 2);  // points per thread the heuristic aims for
   int threads = pow2_ceil((N + want_p - 1) / want_p);
   if (threads < 32) threads = 32;
-  if (threads > 1024) threads = 1024;
+  if (threads > 512) threads = 512;
   const int forced = env_int("UPP_FPS_THREADS", 0);
   if (forced >= 32 && forced <= 1024 && (forced & (forced - 1)) == 0) threads = forced;
   int p = pow2_ceil((N + threads - 1) / threads);

@@ -34,6 +34,7 @@ def timeit(fn, iters=20, warm=5, flush=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
+    ap.add_argument("--sweep-fps", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -50,6 +51,20 @@ def main():
         rows.append(r)
         print(json.dumps(r), flush=True)
 
+    if args.sweep_fps:
+        for (B, N, M) in [(32, 1228, 1024), (32, 1024, 256), (128, 8192, 1024), (32, 2048, 128)]:
+            x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+            for threads in (32, 64, 128, 256, 512, 1024):
+                p = 1
+                while p * threads < N:
+                    p *= 2
+                if p > (8 if threads == 1024 else 16):
+                    continue
+                os.environ["UPP_FPS_THREADS"] = str(threads)
+                rec(f"fps-sweep B{B} N{N} M{M} T{threads} P{p}", lambda: ops.fps(x, M),
+                    lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
+            os.environ.pop("UPP_FPS_THREADS", None)
+        return
     for (B, N, M) in [(32, 1024, 64), (32, 1096, 32), (32, 32, 32), (32, 972, 32), (32, 1024, 256), (32, 1228, 1024),
                       (32, 64, 32), (128, 8192, 1024), (128, 1024, 64), (32, 2048, 128), (32, 1843, 1536),
                       (1, 6144, 1024), (1, 2048, 1024), (16, 8192, 1024)]:

@@ -341,3 +341,50 @@ def test_dropin_modules_resolve_reference_imports(U, O, dev):
     d1, d2, i1, i2 = chamfer.forward(x, data)
     assert torch.count_nonzero(d2) == 0  # sampled points are cloud points: exact zeros
     assert U.launch_count() > 0
+
+
+# ------------------------------------------------------------------ golden fixtures ----------
+# generated from the reference's own Python in the build container (tests/golden/make_golden.py)
+
+def _gold(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+def test_golden_reference_knn_point_and_numpy_fps(U, dev):
+    g = _gold("golden_knn_point.npz")
+    _, I = U.ops.knn(torch.from_numpy(g["ref"]).to(dev), torch.from_numpy(g["query"]).to(dev), int(g["k"]))
+    assert np.array_equal(np.sort(I.cpu().numpy(), -1), g["idx_sorted_by_index"])
+    g = _gold("golden_fps_numpy.npz")
+    centers, _ = U.fps(torch.from_numpy(g["xyz"]).to(dev), int(g["npoint"]))
+    assert np.array_equal(centers.cpu().numpy(), g["picked"])
+
+
+def test_golden_reference_chamfer_modules(U, dev):
+    g = _gold("golden_chamfer_modules.npz")
+    for name, mod in (("l1", U.ChamferDistanceL1()), ("l2", U.ChamferDistanceL2())):
+        a = torch.from_numpy(g["xyz1"]).to(dev).requires_grad_(True)
+        b = torch.from_numpy(g["xyz2"]).to(dev).requires_grad_(True)
+        loss = mod(a, b)
+        loss.backward()
+        assert abs(loss.item() - g[f"{name}_loss"]) <= RTOL * abs(g[f"{name}_loss"])
+        np.testing.assert_allclose(a.grad.cpu().numpy(), g[f"{name}_g1"], rtol=2e-4, atol=1e-8)
+        np.testing.assert_allclose(b.grad.cpu().numpy(), g[f"{name}_g2"], rtol=2e-4, atol=1e-8)
+    s1, s2 = U.ChamferDistanceL2_split()(torch.from_numpy(g["xyz1"]).to(dev), torch.from_numpy(g["xyz2"]).to(dev))
+    np.testing.assert_allclose([s1.item(), s2.item()], g["l2_split"], rtol=RTOL)
+    z1, z2 = torch.from_numpy(g["z1"]).to(dev), torch.from_numpy(g["z2"]).to(dev)
+    assert abs(U.ChamferDistanceL2(ignore_zeros=True)(z1, z2).item() - g["l2_ignore_zeros"]) <= RTOL * g["l2_ignore_zeros"]
+    assert abs(U.ChamferDistanceL1(ignore_zeros=True)(z1, z2).item() - g["l1_ignore_zeros"]) <= RTOL * g["l1_ignore_zeros"]
+    assert abs(U.ChamferDistanceL2(ignore_zeros=False)(z1, z2).item() - g["l2_keep_zeros"]) <= RTOL * g["l2_keep_zeros"]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_golden_reference_group_forward(U, dev, fused):
+    g = _gold("golden_group.npz")
+    grp = U.Group(int(g["G"]), int(g["k"]), fused=fused)
+    x = torch.from_numpy(g["xyz"]).to(dev)
+    nb, ce, idx, cidx = grp(x, require_index=True, gather_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), g["idx"]) and np.array_equal(cidx.cpu().numpy(), g["center_idx"])
+    assert np.array_equal(nb.cpu().numpy(), g["neighborhood"]) and np.array_equal(ce.cpu().numpy(), g["center"])
+    _, _, fidx, fcidx = grp(x, require_index=True, gather_idx=False)
+    assert np.array_equal(fidx.cpu().numpy(), g["flat_idx"]) and np.array_equal(fcidx.cpu().numpy(), g["flat_center_idx"])

@@ -1,0 +1,160 @@
+"""CPU (`-m "not gpu"`) tests of the host side: the C-ABI library loads and exports every symbol
+include/upp_geom.h declares, argument validation that returns before any CUDA call, the Python
+mirror's error behaviour, the batch-sharding logic under a 2-rank gloo group, and bench.py's
+reference arm contract."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(ROOT, "iccv2025-upp_b200", "lib", "libupp_geom.so")):
+        g.build()
+    from upp_b200 import _lib
+    return _lib.load()
+
+
+def test_cabi_exports_every_declared_symbol(lib):
+    from upp_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "upp_geom.h")).read()
+    declared = set(re.findall(r"UPP_API[^;(]*?\b(upp_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 12
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/upp_geom.h but not exported"
+    assert declared == set(_lib.EXPORTS), "ctypes binding and header disagree"
+    assert lib.upp_version() == 100
+    assert _lib.error_string(0) == "ok"
+    assert "invalid argument" in _lib.error_string(-1)
+    assert "workspace" in _lib.error_string(-3)
+
+
+def test_cabi_argument_validation_without_gpu(lib):
+    # every call below must return before touching the device
+    assert lib.upp_knn_f32(None, None, 2, 10, 4, 11, None, None, None) == -1  # k > N
+    assert lib.upp_knn_f32(None, None, 2, 10, 4, 0, None, None, None) == -1   # k < 1
+    assert lib.upp_knn_f32(None, None, 2, 10, 4, 3, None, None, None) == -1   # null pointers
+    assert lib.upp_knn_f32(None, None, 0, 10, 4, 3, None, None, None) == 0    # empty batch: no-op
+    assert lib.upp_fps_f32(None, 2, 16, 4, None, None, None, 0, None) == -1
+    assert lib.upp_fps_f32(None, -1, 16, 4, None, None, None, 0, None) == -1
+    assert lib.upp_fps_f32(None, 0, 16, 4, None, None, None, 0, None) == 0
+    assert lib.upp_chamfer_fwd_f32(None, None, 2, 8, 8, None, None, None, None, None, None) == -1
+    assert lib.upp_chamfer_bwd_f32(None, None, None, None, None, None, 2, 8, 8, None, None, None) == -1
+    assert lib.upp_group_f32(None, 2, 8, 4, 9, None, None, None, None, None, 0, None) == -1  # k > N
+    assert lib.upp_gather_f32(None, None, 2, 3, 8, 4, None, None) == -1
+    assert lib.upp_fps_workspace_bytes(32, 1024, 64) == 0          # register-resident: no scratch
+    assert lib.upp_fps_workspace_bytes(4, 10000, 64) == 4 * 10000 * 4
+    assert lib.upp_launch_count() == 0 or lib.upp_launch_count() > 0
+
+
+def test_python_api_rejects_cpu_and_bad_inputs(lib):
+    import upp_b200 as U
+    x = torch.rand(2, 16, 3)
+    for call in (lambda: U.ops.fps(x, 4), lambda: U.ops.knn(x, x, 2), lambda: U.chamfer.forward(x, x),
+                 lambda: U.pointnet2_utils.furthest_point_sample(x, 4), lambda: U.fps(x, 4),
+                 lambda: U.Group(4, 2)(x), lambda: U.ChamferDistanceL1()(x, x),
+                 lambda: U.KNN(2, transpose_mode=True)(x, x)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+    with pytest.raises(TypeError):
+        U.ops.fps("nope", 4)
+    with pytest.raises(AssertionError):
+        U.KNN(2, transpose_mode=True)(torch.rand(2, 8, 3), torch.rand(3, 8, 3))
+
+
+def test_dropin_packages_resolve(lib):
+    import chamfer
+    import knn_cuda
+    from pointnet2_ops import pointnet2_utils
+    import upp_b200 as U
+    assert chamfer.forward is U.chamfer.forward and chamfer.backward is U.chamfer.backward
+    assert knn_cuda.KNN is U.KNN
+    assert pointnet2_utils.furthest_point_sample is U.pointnet2_utils.furthest_point_sample
+    assert pointnet2_utils.gather_operation is U.pointnet2_utils.gather_operation
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "iccv2025-upp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower().replace("no cpu or eager fallback", ""), os.path.join(dirpath, f)
+
+
+def test_shard_bounds():
+    from upp_b200.parallel import shard_bounds
+    for B in (1, 7, 32, 128, 130):
+        for W in (1, 2, 4, 8):
+            spans = [shard_bounds(B, r, W) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [os.path.join(ROOT, "iccv2025-upp_b200"), ROOT]
+    import torch.distributed as dist
+    from oracle import c_oracle as O
+    from upp_b200 import parallel as P
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.rand(6, 50, 3, generator=g), torch.rand(6, 70, 3, generator=g)
+    la, lb = P.shard_batch(a), P.shard_batch(b)
+    d1, d2, _, _ = O.chamfer_fwd(la.numpy(), lb.numpy())  # the CUDA kernel's role, played by the checker
+    sums = torch.tensor([d1.sum(), d2.sum(), np.sqrt(d1).sum(), np.sqrt(d2).sum()], dtype=torch.float32)
+    P.reduce_sums(sums)
+    l1 = P.chamfer_loss_from_sums(sums, 6 * 50, 6 * 70, "l1")
+    l2 = P.chamfer_loss_from_sums(sums, 6 * 50, 6 * 70, "l2")
+    q.put((rank, float(l1), float(l2), tuple(la.shape)))
+    dist.destroy_process_group()
+
+
+def test_sharded_chamfer_loss_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    from oracle import c_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.rand(6, 50, 3, generator=g), torch.rand(6, 70, 3, generator=g)
+    d1, d2, _, _ = O.chamfer_fwd(a.numpy(), b.numpy())
+    want_l1 = (np.sqrt(d1).mean() + np.sqrt(d2).mean()) / 2
+    want_l2 = d1.mean() + d2.mean()
+    assert res[0][3] == (3, 50, 3) and res[1][3] == (3, 50, 3)
+    for _, l1, l2, _ in res:  # every rank holds the GLOBAL loss
+        assert abs(l1 - want_l1) <= 1e-5 * want_l1 and abs(l2 - want_l2) <= 1e-5 * want_l2
+
+
+def test_bench_reference_arm_contract():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "clouds/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"] == "c1"
