@@ -8,12 +8,13 @@
 // Forward here: ONE launch covers both directions (blockIdx.z) and the whole batch (blockIdx.y).
 // The reference cloud is staged in 2048-point tiles by TMA bulk copy; each thread owns R queries
 // in registers and reads the tile as broadcast LDS.128 (3 loads feed 4 refs x R queries), so the
-// inner loop is FP32-pipe bound: 3 FADD + FMUL + 2 FFMA + compare/select per pair.
+// inner loop is issue bound on the distance itself: 3 FADD + FMUL + 2 FFMA + 0.5 FMNMX3 per pair.
 // d = fma(dz,dz,fma(dx,dx,dy*dy)), d* = ref - query; strict '<' in ascending ref order gives the
 // lowest index on ties (== reference).  The grid is sized from the problem, not fixed.
 //
 // Backward here: pass 1 WRITES each point's own term (no atomics, no memset), pass 2 scatters the
 // partner term with float RED.ADD -- half the reference's atomics, all B*(N+M) points in flight.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -22,6 +23,12 @@ namespace upp {
 
 constexpr int kChTile = 2048;  // reference points per shared-memory tile (24 KB)
 
+// Min-tracking costs as much as the distance itself if done per pair (FSETP+FSEL+SEL ~ 4.4 issue
+// cycles vs 6 for the distance, scripts/microbench.cu), so the inner loop tracks per GROUP of 8
+// refs: two FMNMX3 chains fold 8 distances into one min (0.5 instr/pair), ONE compare/select pair
+// per group keeps (best value, group base).  The arg-min inside the winning group is recovered once
+// per query in the epilogue by recomputing its 8 distances (first one equal to the best value).
+// Strict '<' across groups in ascending order + first match inside => lowest index on ties.
 template <int R, int THREADS>
 __global__ void __launch_bounds__(THREADS)
     chamfer_fwd_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2, int N, int M,
@@ -49,7 +56,7 @@ __global__ void __launch_bounds__(THREADS)
   unsigned parity = 0;
 
   float qx[R], qy[R], qz[R], best[R];
-  int bi[R];
+  int bg[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int j = q0 + r * THREADS + t;
@@ -58,73 +65,119 @@ __global__ void __launch_bounds__(THREADS)
     qy[r] = __ldg(qp + 3 * jj + 1);
     qz[r] = __ldg(qp + 3 * jj + 2);
     best[r] = __int_as_float(0x7f800000);
-    bi[r] = 0;
+    bg[r] = 0;
   }
 
   for (int base = 0; base < nr; base += kChTile) {
     const int tile = min(kChTile, nr - base);
-    const int tile4 = (tile + 3) & ~3;
+    const int tile8 = (tile + 7) & ~7;
     if (base > 0) __syncthreads();
-    // pad the last group of four with NaN: (NaN - q)^2 = NaN never compares '<'
-    for (int i = tile * 3 + t; i < tile4 * 3; i += THREADS) s_ref[i] = __int_as_float(0x7fc00000);
+    // pad the last group of eight with NaN: (NaN - q)^2 = NaN, and fminf() drops NaN operands
+    for (int i = tile * 3 + t; i < tile8 * 3; i += THREADS) s_ref[i] = __int_as_float(0x7fc00000);
     stage_points(s_ref, rp + static_cast<size_t>(base) * 3, tile, &s_bar, parity);
 
     const float4* s4 = reinterpret_cast<const float4*>(s_ref);
-#pragma unroll 2
-    for (int k = 0; k < tile4; k += 4) {
-      const float4 a = s4[(k >> 2) * 3 + 0];  // x0 y0 z0 x1
-      const float4 c = s4[(k >> 2) * 3 + 1];  // y1 z1 x2 y2
-      const float4 e = s4[(k >> 2) * 3 + 2];  // z2 x3 y3 z3
+    for (int k = 0; k < tile8; k += 8) {
+      float m[R];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 a = s4[(k >> 2) * 3 + h * 3 + 0];  // x0 y0 z0 x1
+        const float4 c = s4[(k >> 2) * 3 + h * 3 + 1];  // y1 z1 x2 y2
+        const float4 e = s4[(k >> 2) * 3 + h * 3 + 2];  // z2 x3 y3 z3
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float d0 = dist_yxz(a.x - qx[r], a.y - qy[r], a.z - qz[r]);
+          const float d1 = dist_yxz(a.w - qx[r], c.x - qy[r], c.y - qz[r]);
+          const float d2 = dist_yxz(c.z - qx[r], c.w - qy[r], e.x - qz[r]);
+          const float d3 = dist_yxz(e.y - qx[r], e.z - qy[r], e.w - qz[r]);
+          if (h == 0) m[r] = fminf(fminf(fminf(d0, d1), d2), d3);
+          else m[r] = fminf(fminf(fminf(fminf(m[r], d0), d1), d2), d3);
+        }
+      }
       const int kk = base + k;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float d;
-        d = dist_yxz(a.x - qx[r], a.y - qy[r], a.z - qz[r]);
-        if (d < best[r]) { best[r] = d; bi[r] = kk; }
-        d = dist_yxz(a.w - qx[r], c.x - qy[r], c.y - qz[r]);
-        if (d < best[r]) { best[r] = d; bi[r] = kk + 1; }
-        d = dist_yxz(c.z - qx[r], c.w - qy[r], e.x - qz[r]);
-        if (d < best[r]) { best[r] = d; bi[r] = kk + 2; }
-        d = dist_yxz(e.y - qx[r], e.z - qy[r], e.w - qz[r]);
-        if (d < best[r]) { best[r] = d; bi[r] = kk + 3; }
-      }
+      for (int r = 0; r < R; ++r)
+        if (m[r] < best[r]) { best[r] = m[r]; bg[r] = kk; }
     }
   }
+  // epilogue: arg-min inside the winning group of 8 (refs re-read from global / L2)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int j = q0 + r * THREADS + t;
     if (j < nq) {
+      int bi = bg[r];
+      const int lim = min(8, nr - bg[r]);
+      for (int u = lim - 1; u >= 0; --u) {
+        const float* p = rp + static_cast<size_t>(bg[r] + u) * 3;
+        const float d = dist_yxz(__ldg(p) - qx[r], __ldg(p + 1) - qy[r], __ldg(p + 2) - qz[r]);
+        if (d == best[r]) bi = bg[r] + u;
+      }
       dout[j] = best[r];
-      iout[j] = bi[r];
+      iout[j] = bi;
     }
   }
 }
 
-// Deterministic whole-call sums { sum d1, sum d2, sum sqrt d1, sum sqrt d2 }: one CTA, fixed
-// strided order + fixed tree, so the value fed to the NCCL all-reduce is run-to-run identical.
-__global__ void __launch_bounds__(1024)
+// Deterministic whole-call sums { sum d1, sum d2, sum sqrt d1, sum sqrt d2 } -- the send buffer of
+// the one NCCL all-reduce the batch-sharded loss needs.  One thread-block CLUSTER of 8 CTAs: each
+// CTA reduces a fixed interleaved slice (4 independent accumulators per quantity keep loads in
+// flight), leaves 4 floats in its shared memory, and after one cluster barrier CTA 0 adds the 8
+// partials in rank order through distributed shared memory.  Fixed partition + fixed order =>
+// run-to-run identical value, no scratch buffer, no atomics.
+constexpr int kSumCluster = 8;
+constexpr int kSumThreads = 512;
+
+__global__ void __cluster_dims__(kSumCluster, 1, 1) __launch_bounds__(kSumThreads)
     chamfer_sums_kernel(const float* __restrict__ dist1, size_t n1, const float* __restrict__ dist2,
                         size_t n2, float* __restrict__ sums) {
-  __shared__ float s_part[4][32];
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (size_t i = threadIdx.x; i < n1; i += 1024) {
-    const float d = dist1[i];
-    a0 += d;
-    a2 += __fsqrt_rn(d);
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float s_part[4][kSumThreads / 32];
+  __shared__ float s_out[4];
+  const unsigned rank = cluster.block_rank();
+  const size_t stride = static_cast<size_t>(kSumCluster) * kSumThreads;
+  const size_t first = static_cast<size_t>(rank) * kSumThreads + threadIdx.x;
+  float acc[2][2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[a][q][u] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const float* d = a == 0 ? dist1 : dist2;
+    const size_t n = a == 0 ? n1 : n2;
+    for (size_t i = first; i < n; i += 4 * stride) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t j = i + u * stride;
+        const float v = j < n ? __ldg(d + j) : 0.f;
+        acc[a][0][u] += v;
+        acc[a][1][u] += __fsqrt_rn(v);
+      }
+    }
   }
-  for (size_t i = threadIdx.x; i < n2; i += 1024) {
-    const float d = dist2[i];
-    a1 += d;
-    a3 += __fsqrt_rn(d);
-  }
-  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_part[0][warp] = a0; s_part[1][warp] = a1; s_part[2][warp] = a2; s_part[3][warp] = a3; }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float v = warp_sum((acc[a][q][0] + acc[a][q][1]) + (acc[a][q][2] + acc[a][q][3]));
+      if (lane == 0) s_part[q * 2 + a][warp] = v;
+    }
   __syncthreads();
   if (warp < 4) {
-    const float v = warp_sum(s_part[warp][lane]);
-    if (lane == 0) sums[warp] = v;
+    const float v = warp_sum(lane < kSumThreads / 32 ? s_part[warp][lane] : 0.f);
+    if (lane == 0) s_out[warp] = v;
   }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x < 4) {
+    float tot = 0.f;
+    for (unsigned r = 0; r < kSumCluster; ++r) tot += *cluster.map_shared_rank(&s_out[threadIdx.x], r);
+    sums[threadIdx.x] = tot;
+  }
+  cluster.sync();  // keep every CTA's shared memory alive until CTA 0 has read it
 }
 
 // Backward pass 1: own term, plain stores.  grad_a[j] = 2 g[j] (a_j - b_idx[j]) for both clouds.
@@ -176,18 +229,36 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+template <int R, int THREADS>
+static void launch_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
+                               float* dist2, int32_t* idx1, int32_t* idx2, cudaStream_t st) {
+  const int per = R * THREADS;
+  dim3 grid((max(N, M) + per - 1) / per, B, 2);
+  chamfer_fwd_kernel<R, THREADS><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, dist1, dist2, idx1, idx2);
+}
+
 int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                        float* dist2, int32_t* idx1, int32_t* idx2, float* sums, cudaStream_t st) {
-  constexpr int R = 4, THREADS = 128;
-  const int per = R * THREADS;
-  const int tiles = (max(N, M) + per - 1) / per;
-  dim3 grid(tiles, B, 2);
-  chamfer_fwd_kernel<R, THREADS><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, dist1, dist2, idx1, idx2);
+  const char* v = getenv("UPP_CH_VARIANT");  // tuning aid: "R,T"
+  const int variant = v ? atoi(v) : 0;
+  switch (variant) {
+    case 1: launch_chamfer_fwd<4, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    case 2: launch_chamfer_fwd<8, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    case 3: launch_chamfer_fwd<8, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    case 4: launch_chamfer_fwd<4, 256>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    case 5: launch_chamfer_fwd<4, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    case 6: launch_chamfer_fwd<2, 256>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    case 7: launch_chamfer_fwd<2, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    case 8: launch_chamfer_fwd<1, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    case 9: launch_chamfer_fwd<1, 256>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    // measured best on B200 (scripts/time_ops.py --sweep-chamfer): more warps beat more queries per thread
+    default: launch_chamfer_fwd<2, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+  }
   count_launch();
   int rc = launch_status();
   if (rc != UPP_OK || sums == nullptr) return rc;
-  chamfer_sums_kernel<<<1, 1024, 0, st>>>(dist1, static_cast<size_t>(B) * N, dist2,
-                                          static_cast<size_t>(B) * M, sums);
+  chamfer_sums_kernel<<<kSumCluster, kSumThreads, 0, st>>>(dist1, static_cast<size_t>(B) * N, dist2,
+                                                          static_cast<size_t>(B) * M, sums);
   count_launch();
   return launch_status();
 }

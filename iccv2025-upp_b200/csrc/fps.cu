@@ -8,7 +8,8 @@
 //   * the cloud is staged once into shared memory with a 1-D TMA bulk copy (UBLKCP);
 //   * every thread keeps its P points AND their running min-distance in REGISTERS for the
 //     whole kernel -- HBM traffic is 12N in + 4M(+12M) out per cloud, nothing else;
-//   * the block arg-max is two REDUX stages around ONE __syncthreads per iteration:
+//   * the block arg-max is two REDUX stages around ONE __syncthreads per iteration (a single
+//     warp needs neither the barrier nor the second stage):
 //     warp max of the (order-preserving) float bit pattern, lowest matching point index by
 //     REDUX.MIN, per-warp winners double-buffered in shared memory;
 //   * ties resolve to the lowest point index, deterministically.
@@ -29,11 +30,14 @@ __device__ __forceinline__ float fps_initial_md(float x, float y, float z) {
   return (static_cast<double>(mag) <= 1e-3) ? kSkipped : 1e10f;
 }
 
-template <int THREADS, int P>
-__global__ void __launch_bounds__(THREADS, 1)
+// THREADS is any multiple of 32; one warp means no barrier and no second stage at all.
+// TT == 0 is the tuning variant: thread count taken from blockDim.x at run time.
+template <int TT, int P>
+__global__ void __launch_bounds__(TT ? TT : (P > 8 ? 512 : 1024), 1)
     fps_reg_kernel(const float* __restrict__ xyz, int N, int M, int32_t* __restrict__ idx_out,
                    float* __restrict__ centers_out) {
-  constexpr int NWARPS = THREADS / kWarp;
+  const int THREADS = TT ? TT : static_cast<int>(blockDim.x);
+  const int NWARPS = THREADS / kWarp;
   extern __shared__ __align__(16) float s_xyz[];  // 3*N floats (AoS, as in global memory)
   __shared__ int2 s_slot[2][kWarp];
   __shared__ __align__(8) uint64_t s_bar;
@@ -171,29 +175,34 @@ static int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-static int pow2_ceil(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
+static const int kPs[] = {1, 2, 3, 4, 6, 8, 12, 16};
+
+static int round_p(int p) {
+  for (int v : kPs)
+    if (v >= p) return v;
+  return 0;
 }
 
-// Register-resident configuration for N <= kFpsMaxRegPoints.  Measured on B200 (scripts/
-// time_ops.py --sweep-fps): the per-iteration cost is dominated by fixed latencies (4 REDUX,
-// 3 LDS, 1 BAR ~ 270 cycles), so up to 512 threads with 2 points each is fastest for N ~ 1k;
-// 1024 threads lose to 512 (BAR.SYNC: 45 -> 77 cycles, more per-warp reduction overhead).
+// Register-resident configuration for N <= kFpsMaxRegPoints, from B200 measurements
+// (scripts/time_ops.py --sweep-fps, scripts/microbench.cu).  One iteration is a latency chain:
+//   LDS centroid 34 -> distance/min/max ~30 -> REDUX 23 -> REDUX 23 -> STS/BAR.SYNC 21..50 ->
+//   LDS 34 -> REDUX 23 -> REDUX 23 -> LDS ...   ~ 350-400 cycles (0.18-0.20 us) for any N <= 1280,
+// plus ~8 issue slots per point per warp.  Measured best everywhere: TWO points per thread
+// (more per thread lengthens the in-thread max/select chains; one per thread doubles the warps
+// and the barrier cost), i.e. N/2 threads up to 640; beyond that 512 threads x ceil(N/512) points.
 FpsConfig fps_pick_config(int N) {
-  const int want_p = env_int("UPP_FPS_P", 2);  // points per thread the heuristic aims for
-  int threads = pow2_ceil((N + want_p - 1) / want_p);
-  if (threads < 32) threads = 32;
-  if (threads > 512) threads = 512;
-  const int forced = env_int("UPP_FPS_THREADS", 0);
-  if (forced >= 32 && forced <= 1024 && (forced & (forced - 1)) == 0) threads = forced;
-  int p = pow2_ceil((N + threads - 1) / threads);
-  const int pmax = threads == 1024 ? 8 : 16;
-  while (p > pmax && threads < 1024) {
-    threads <<= 1;
-    p = pow2_ceil((N + threads - 1) / threads);
+  int threads, p;
+  if (N <= 32) {
+    threads = 32;
+    p = 1;
+  } else if (N <= 1280) {
+    p = 2;
+    threads = ((N + 1) / 2 + 31) / 32 * 32;
+  } else {
+    threads = 512;
+    p = round_p((N + 511) / 512);
   }
+  if (p == 0 || static_cast<long>(threads) * p < N) return {0, 0};
   return {threads, p};
 }
 
@@ -212,34 +221,64 @@ static int launch_fps_reg(const float* xyz, int B, int N, int M, int32_t* idx, f
   return launch_status();
 }
 
-template <int THREADS>
-static int dispatch_fps_p(int P, const float* xyz, int B, int N, int M, int32_t* idx,
-                          float* centers, cudaStream_t st) {
-  switch (P) {
-    case 1: return launch_fps_reg<THREADS, 1>(xyz, B, N, M, idx, centers, st);
-    case 2: return launch_fps_reg<THREADS, 2>(xyz, B, N, M, idx, centers, st);
-    case 4: return launch_fps_reg<THREADS, 4>(xyz, B, N, M, idx, centers, st);
-    case 8: return launch_fps_reg<THREADS, 8>(xyz, B, N, M, idx, centers, st);
-    case 16:
-      if constexpr (THREADS <= 512) return launch_fps_reg<THREADS, 16>(xyz, B, N, M, idx, centers, st);
-      return UPP_ERR_UNSUPPORTED;
-    default: return UPP_ERR_UNSUPPORTED;
+// tuning variant (UPP_FPS_THREADS + UPP_FPS_P both set): any thread count, run-time stride
+template <int P>
+static int launch_fps_rt(int threads, const float* xyz, int B, int N, int M, int32_t* idx,
+                         float* centers, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(N) * 3 * sizeof(float);
+  auto kern = fps_reg_kernel<0, P>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
   }
+  kern<<<B, threads, smem, st>>>(xyz, N, M, idx, centers);
+  count_launch();
+  return launch_status();
 }
+
+#define UPP_FPS_CASE_P(T, PP) \
+  case PP: return launch_fps_reg<T, PP>(xyz, B, N, M, idx, centers, st);
+#define UPP_FPS_CASE_T(T) \
+  case T: return launch_fps_reg<T, 2>(xyz, B, N, M, idx, centers, st);
 
 int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (N <= kFpsMaxRegPoints) {
-    const FpsConfig c = fps_pick_config(N);
-    switch (c.threads) {
-      case 32: return dispatch_fps_p<32>(c.p, xyz, B, N, M, idx, centers, st);
-      case 64: return dispatch_fps_p<64>(c.p, xyz, B, N, M, idx, centers, st);
-      case 128: return dispatch_fps_p<128>(c.p, xyz, B, N, M, idx, centers, st);
-      case 256: return dispatch_fps_p<256>(c.p, xyz, B, N, M, idx, centers, st);
-      case 512: return dispatch_fps_p<512>(c.p, xyz, B, N, M, idx, centers, st);
-      case 1024: return dispatch_fps_p<1024>(c.p, xyz, B, N, M, idx, centers, st);
-      default: return UPP_ERR_UNSUPPORTED;
+    const int ft = env_int("UPP_FPS_THREADS", 0), fp = env_int("UPP_FPS_P", 0);
+    if (ft >= 32 && ft <= 1024 && ft % 32 == 0 && fp > 0 && round_p(fp) == fp &&
+        static_cast<long>(ft) * fp >= N && ft <= (fp > 8 ? 512 : 1024)) {
+      switch (fp) {
+        case 1: return launch_fps_rt<1>(ft, xyz, B, N, M, idx, centers, st);
+        case 2: return launch_fps_rt<2>(ft, xyz, B, N, M, idx, centers, st);
+        case 3: return launch_fps_rt<3>(ft, xyz, B, N, M, idx, centers, st);
+        case 4: return launch_fps_rt<4>(ft, xyz, B, N, M, idx, centers, st);
+        case 6: return launch_fps_rt<6>(ft, xyz, B, N, M, idx, centers, st);
+        case 8: return launch_fps_rt<8>(ft, xyz, B, N, M, idx, centers, st);
+        case 12: return launch_fps_rt<12>(ft, xyz, B, N, M, idx, centers, st);
+        default: return launch_fps_rt<16>(ft, xyz, B, N, M, idx, centers, st);
+      }
     }
+    const FpsConfig c = fps_pick_config(N);
+    if (c.p == 1 && c.threads == 32) return launch_fps_reg<32, 1>(xyz, B, N, M, idx, centers, st);
+    if (c.p == 2) {
+      switch (c.threads) {
+        UPP_FPS_CASE_T(32) UPP_FPS_CASE_T(64) UPP_FPS_CASE_T(96) UPP_FPS_CASE_T(128)
+        UPP_FPS_CASE_T(160) UPP_FPS_CASE_T(192) UPP_FPS_CASE_T(224) UPP_FPS_CASE_T(256)
+        UPP_FPS_CASE_T(288) UPP_FPS_CASE_T(320) UPP_FPS_CASE_T(352) UPP_FPS_CASE_T(384)
+        UPP_FPS_CASE_T(416) UPP_FPS_CASE_T(448) UPP_FPS_CASE_T(480) UPP_FPS_CASE_T(512)
+        UPP_FPS_CASE_T(544) UPP_FPS_CASE_T(576) UPP_FPS_CASE_T(608) UPP_FPS_CASE_T(640)
+        default: return UPP_ERR_UNSUPPORTED;
+      }
+    }
+    if (c.threads == 512) {
+      switch (c.p) {
+        UPP_FPS_CASE_P(512, 3) UPP_FPS_CASE_P(512, 4) UPP_FPS_CASE_P(512, 6)
+        UPP_FPS_CASE_P(512, 8) UPP_FPS_CASE_P(512, 12) UPP_FPS_CASE_P(512, 16)
+        default: return UPP_ERR_UNSUPPORTED;
+      }
+    }
+    return UPP_ERR_UNSUPPORTED;
   }
   const size_t need = static_cast<size_t>(B) * N * sizeof(float);
   if (workspace == nullptr || workspace_bytes < need) return UPP_ERR_WORKSPACE;

@@ -7,10 +7,12 @@
 //
 // Here: the cloud's reference points are staged once per CTA into shared memory by a TMA bulk
 // copy; one WARP owns one query.  Lanes stride over the references (conflict-free LDS), the
-// running top-k lives in registers as a lane-distributed sorted list (lane i holds the i-th
-// best).  A candidate is admitted by one ballot (position = popcount of entries <= it) and one
-// shuffle-up; candidates arrive in ascending index order so "entries <= candidate stay in
-// front" reproduces upstream's stable insertion (equal distances keep the lower index first).
+// running top-32 lives in registers as a lane-distributed sorted list (lane i holds the i-th
+// best; the first k are the answer).  A chunk of 32 distances is filtered against the current
+// k-th best with one ballot; each survivor is admitted with one shuffle-up (every lane decides
+// from its own and its left neighbour's entry).  Candidates arrive in ascending index order, so
+// "entries <= candidate stay in front" reproduces upstream's stable insertion (equal distances
+// keep the lower index first).
 // No distance matrix, no global scratch.  d = fma(dz,dz,fma(dy,dy,dx*dx)) with d* = ref-query,
 // sorted on the squared value, sqrt (IEEE rn) applied to the k survivors, int64 0-based indices.
 #include <float.h>
@@ -66,15 +68,18 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
+        // Admit candidate (cd, ci).  Candidates arrive in ascending index order, so it goes behind
+        // every entry with distance <= cd.  Each lane decides from its own entry and its left
+        // neighbour's (one shuffle-up, no ballot/popc on the dependent chain): entries > cd shift
+        // right by one, the first of them is replaced by the candidate, lane 31's entry falls off.
         const float cd = __shfl_sync(0xffffffffu, d, src);
         const int ci = base + c0 + src;
-        const int pos = __popc(__ballot_sync(0xffffffffu, ld <= cd));
         const float ud = __shfl_up_sync(0xffffffffu, ld, 1);
         const int ui = __shfl_up_sync(0xffffffffu, li, 1);
-        if (pos < k) {
-          if (lane == pos) { ld = cd; li = ci; }
-          else if (lane > pos) { ld = ud; li = ui; }
-        }
+        const bool mine_gt = ld > cd;
+        const bool left_gt = (lane > 0) && (ud > cd);
+        li = mine_gt ? (left_gt ? ui : ci) : li;
+        ld = mine_gt ? (left_gt ? ud : cd) : ld;
       }
       thr = __shfl_sync(0xffffffffu, ld, k - 1);
     }

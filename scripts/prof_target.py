@@ -1,0 +1,26 @@
+"""Runs one op a few times so that `ncu -k regex:<kernel>` can capture it (see profiles/README.md)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "iccv2025-upp_b200"), ROOT):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+from upp_b200 import ops  # noqa: E402
+
+what = sys.argv[1]
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+for _ in range(4):
+    if what == "chamfer":
+        a, b = torch.rand(64, 2048, 3, generator=g).to(dev), torch.rand(64, 2048, 3, generator=g).to(dev)
+        out = ops.chamfer_forward(a, b)
+        ops.chamfer_backward(a, b, out[2], out[3], torch.rand_like(out[0]), torch.rand_like(out[1]))
+    elif what == "fps":
+        ops.fps((torch.rand(32, 1228, 3, generator=g) * 2 - 1).to(dev), 1024)
+    elif what == "fps8k":
+        ops.fps((torch.rand(128, 8192, 3, generator=g) * 2 - 1).to(dev), 1024)
+    elif what == "knn":
+        r = (torch.rand(32, 1024, 3, generator=g) * 2 - 1).to(dev)
+        ops.knn(r, r[:, :64].contiguous(), 32)
+    torch.cuda.synchronize()

@@ -14,6 +14,14 @@ from upp_b200 import ops  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=5, flush=None):
+    """Kernel-only time: the op is captured into a CUDA graph and replayed (no Python / launch gaps)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    fn = g.replay
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -35,6 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--sweep-fps", action="store_true")
+    ap.add_argument("--sweep-chamfer", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -51,19 +60,29 @@ def main():
         rows.append(r)
         print(json.dumps(r), flush=True)
 
+    if args.sweep_chamfer:
+        for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192)]:
+            a = torch.rand(B, N, 3, generator=g).to(dev)
+            b = torch.rand(B, M, 3, generator=g).to(dev)
+            for v, name in enumerate(["R2T128", "R4T64", "R8T64", "R8T128", "R4T256", "R4T128", "R2T256", "R2T64", "R1T128", "R1T256"]):
+                os.environ["UPP_CH_VARIANT"] = str(v)
+                rec(f"chamfer-sweep {name} B{B} N{N} M{M}", lambda: ops.chamfer_forward(a, b),
+                    lambda us: {"tflops_16NM": round(16.0 * N * M * B / us / 1e6, 2)})
+            os.environ.pop("UPP_CH_VARIANT", None)
+        return
     if args.sweep_fps:
-        for (B, N, M) in [(32, 1228, 1024), (32, 1024, 256), (128, 8192, 1024), (32, 2048, 128)]:
+        for (B, N, M) in [(32, 1228, 1024), (32, 1024, 256), (32, 2048, 256), (128, 8192, 256), (32, 512, 256), (32, 256, 128)]:
             x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
-            for threads in (32, 64, 128, 256, 512, 1024):
-                p = 1
-                while p * threads < N:
-                    p *= 2
-                if p > (8 if threads == 1024 else 16):
+            rec(f"fps-sweep B{B} N{N} M{M} default", lambda: ops.fps(x, M), lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
+            for p in (1, 2, 3, 4, 6, 8, 12, 16):
+                threads = ((N + p - 1) // p + 31) // 32 * 32
+                if threads > (512 if p > 8 else 1024) or threads < 32:
                     continue
-                os.environ["UPP_FPS_THREADS"] = str(threads)
-                rec(f"fps-sweep B{B} N{N} M{M} T{threads} P{p}", lambda: ops.fps(x, M),
+                os.environ["UPP_FPS_THREADS"], os.environ["UPP_FPS_P"] = str(threads), str(p)
+                rec(f"fps-sweep B{B} N{N} M{M} T{threads} P{p} (runtime-T)", lambda: ops.fps(x, M),
                     lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
             os.environ.pop("UPP_FPS_THREADS", None)
+            os.environ.pop("UPP_FPS_P", None)
         return
     for (B, N, M) in [(32, 1024, 64), (32, 1096, 32), (32, 32, 32), (32, 972, 32), (32, 1024, 256), (32, 1228, 1024),
                       (32, 64, 32), (128, 8192, 1024), (128, 1024, 64), (32, 2048, 128), (32, 1843, 1536),
