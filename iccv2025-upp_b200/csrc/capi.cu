@@ -13,7 +13,8 @@ int fps_launch(const float*, int, int, int, int32_t*, float*, void*, size_t, cud
 size_t fps_workspace_bytes(int, int);
 int knn_launch(const float*, const float*, int, int, int, int, float*, int64_t*, cudaStream_t);
 int chamfer_fwd_launch(const float*, const float*, int, int, int, float*, float*, int32_t*, int32_t*,
-                       float*, cudaStream_t);
+                       float*, void*, size_t, cudaStream_t);
+size_t chamfer_fwd_workspace_bytes(int, int, int);
 int chamfer_bwd_launch(const float*, const float*, const int32_t*, const int32_t*, const float*,
                        const float*, int, int, int, float*, float*, cudaStream_t);
 int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
@@ -90,9 +91,11 @@ int upp_knn_f32(const float* ref, const float* query, int B, int N, int Q, int k
   return knn_launch(ref, query, B, N, Q, k, dist_out, idx_out, S(stream));
 }
 
+size_t upp_chamfer_fwd_workspace_bytes(int B, int N, int M) { return chamfer_fwd_workspace_bytes(B, N, M); }
+
 int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                         float* dist2, int32_t* idx1, int32_t* idx2, float* partial_sums,
-                        upp_stream_t stream) {
+                        void* workspace, size_t workspace_bytes, upp_stream_t stream) {
   UPP_REQUIRE(B >= 0 && N >= 0 && M >= 0);
   const size_t n1 = static_cast<size_t>(B) * N, n2 = static_cast<size_t>(B) * M;
   UPP_REQUIRE(n1 == 0 || (dist1 && idx1));
@@ -105,7 +108,8 @@ int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int N, int 
     return static_cast<int>(e);
   }
   UPP_REQUIRE(xyz1 && xyz2);
-  return chamfer_fwd_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, partial_sums, S(stream));
+  return chamfer_fwd_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, partial_sums, workspace,
+                            workspace_bytes, S(stream));
 }
 
 int upp_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,

@@ -106,16 +106,194 @@ __global__ void __launch_bounds__(THREADS)
     const int j = q0 + r * THREADS + t;
     if (j < nq) {
       int bi = bg[r];
-      const int lim = min(8, nr - bg[r]);
-      for (int u = lim - 1; u >= 0; --u) {
-        const float* p = rp + static_cast<size_t>(bg[r] + u) * 3;
+#pragma unroll
+      for (int u = 7; u >= 0; --u) {  // independent (clamped) loads, lowest match wins
+        const float* p = rp + static_cast<size_t>(min(bg[r] + u, nr - 1)) * 3;
         const float d = dist_yxz(__ldg(p) - qx[r], __ldg(p + 1) - qy[r], __ldg(p + 2) - qz[r]);
-        if (d == best[r]) bi = bg[r] + u;
+        if (d == best[r] && bg[r] + u < nr) bi = bg[r] + u;
       }
       dout[j] = best[r];
       iout[j] = bi;
     }
   }
+}
+
+// Predicated (branch-free) RED.MIN.U64 of the key (bits << 32 | code), issued only by lanes whose
+// value equals the warp minimum.
+__device__ __forceinline__ void red_min_key_if_equal(unsigned long long* addr, unsigned mine,
+                                                     unsigned warp_min, unsigned code) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 key;\n\t"
+      "setp.eq.u32 p, %1, %2;\n\t"
+      "mov.b64 key, {%3, %2};\n\t"
+      "@p red.global.min.u64 [%0], key;\n\t"
+      "}" ::"l"(addr),
+      "r"(mine), "r"(warp_min), "r"(code)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass forward: every pairwise distance is computed ONCE and serves both directions
+// (the matrix is bitwise symmetric: (-a)^2 == a^2), halving the FP32 work of the reference's two
+// directed launches.  Rows (cloud A) live in registers, R per thread, lane-major so that a lower
+// lane owns lower row indices; columns (cloud B) stream through shared memory in TMA-staged tiles,
+// the CTA's WC warps taking interleaved groups of 8 columns.
+//   row side : as chamfer_fwd_kernel -- FMNMX3 folds pairs of columns into a per-group min, one
+//              compare/select per 8 columns; the WC partial results per row are combined through
+//              shared memory and the arg-min inside the winning group is recomputed once per row.
+//   col side : per column, an FMNMX3 tree over the thread's R rows, REDUX.MIN over the warp on the
+//              (non-negative) float bits, and the lane(s) holding the minimum issue one
+//              RED.MIN.U64 of (distance bits << 32 | row-block id) into a (B, M8) workspace.
+//              64-bit min == smallest distance, then lowest row block.  chamfer_cols_finalize_kernel
+//              then turns the keys into dist/idx by recomputing the R distances of the winning
+//              row block -- first row equal to the minimum => lowest index on ties.
+// The workspace is preset to 0xFF bytes (keys = +max) by a memset node in front of the kernel.
+template <int R, int WC>
+__global__ void __launch_bounds__(WC * 32)
+    chamfer_fwd_both_kernel(const float* __restrict__ xyzA, const float* __restrict__ xyzB, int NA,
+                            int NB, int NB8, float* __restrict__ distA, int32_t* __restrict__ idxA,
+                            float* __restrict__ distB, int32_t* __restrict__ idxB,
+                            unsigned long long* __restrict__ colbest) {
+  constexpr int ROWS = 32 * R;
+  constexpr int THREADS = WC * 32;
+  static_assert(WC * ROWS * 8 <= kChTile * 12, "row-combine scratch must fit in the tile buffer");
+  __shared__ __align__(16) float s_ref[kChTile * 3];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int t = threadIdx.x, lane = t & 31;
+  // warp index through a shuffle: lets the compiler treat it (and the column loop) as warp-uniform,
+  // so the REDUX in the loop needs no divergence guard (BSSY / BRA.DIV / BSYNC)
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int b = blockIdx.y;
+  const float* ap = xyzA + static_cast<size_t>(b) * NA * 3;
+  const float* bp = xyzB + static_cast<size_t>(b) * NB * 3;
+  unsigned long long* cb = colbest + static_cast<size_t>(b) * NB8;
+  const int row0 = blockIdx.x * ROWS + lane * R;
+  const unsigned code = static_cast<unsigned>(blockIdx.x * 32 + lane);  // row block id = row0 / R
+
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned parity = 0;
+
+  float qx[R], qy[R], qz[R], best[R];
+  int bg[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int j = row0 + r;
+    const bool ok = j < NA;  // rows past the end are NaN: they never win a min
+    qx[r] = ok ? __ldg(ap + 3 * j) : __int_as_float(0x7fc00000);
+    qy[r] = ok ? __ldg(ap + 3 * j + 1) : __int_as_float(0x7fc00000);
+    qz[r] = ok ? __ldg(ap + 3 * j + 2) : __int_as_float(0x7fc00000);
+    best[r] = __int_as_float(0x7f800000);
+    bg[r] = 0;
+  }
+
+  for (int base = 0; base < NB; base += kChTile) {
+    const int tile = min(kChTile, NB - base);
+    const int tile8 = (tile + 7) & ~7;
+    if (base > 0) __syncthreads();
+    for (int i = tile * 3 + t; i < tile8 * 3; i += THREADS) s_ref[i] = __int_as_float(0x7fc00000);
+    stage_points(s_ref, bp + static_cast<size_t>(base) * 3, tile, &s_bar, parity);
+
+    const int ngroups = tile8 >> 3;
+    for (int g = warp; g < ngroups; g += WC) {
+      const float4* s4 = reinterpret_cast<const float4*>(s_ref) + g * 6;
+      unsigned long long* cbk = cb + base + g * 8;
+      float m[R];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {  // four column pairs per group of 8
+        // refs 2h and 2h+1 of the group: 6 consecutive floats starting at float 6h
+        const float4 v0 = s4[(6 * h) >> 2];
+        const float4 v1 = s4[((6 * h) >> 2) + 1];
+        float ax, ay, az, bx, by, bz;
+        if ((h & 1) == 0) { ax = v0.x; ay = v0.y; az = v0.z; bx = v0.w; by = v1.x; bz = v1.y; }
+        else              { ax = v0.z; ay = v0.w; az = v1.x; bx = v1.y; by = v1.z; bz = v1.w; }
+        float ca = 0.f, cbm = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float da = dist_yxz(ax - qx[r], ay - qy[r], az - qz[r]);
+          const float db = dist_yxz(bx - qx[r], by - qy[r], bz - qz[r]);
+          m[r] = h == 0 ? fminf(da, db) : fminf(fminf(m[r], da), db);
+          ca = r == 0 ? da : fminf(ca, da);
+          cbm = r == 0 ? db : fminf(cbm, db);
+        }
+        const unsigned ua = __float_as_uint(ca), ub = __float_as_uint(cbm);
+        const unsigned wa = redux_min_u32(ua), wb = redux_min_u32(ub);
+        red_min_key_if_equal(cbk + 2 * h, ua, wa, code);
+        red_min_key_if_equal(cbk + 2 * h + 1, ub, wb, code);
+      }
+      const int kk = base + g * 8;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (m[r] < best[r]) { best[r] = m[r]; bg[r] = kk; }
+    }
+  }
+
+  // ---- row side: combine the WC column-chunk partials, resolve the arg-min inside the group ----
+  __syncthreads();  // every warp is done reading the tile
+  float* s_best = s_ref;
+  int* s_bg = reinterpret_cast<int*>(s_ref + WC * ROWS);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    s_best[warp * ROWS + lane * R + r] = best[r];
+    s_bg[warp * ROWS + lane * R + r] = bg[r];
+  }
+  __syncthreads();
+  for (int rho = t; rho < ROWS; rho += THREADS) {
+    const int j = blockIdx.x * ROWS + rho;
+    if (j >= NA) continue;
+    float bb = __int_as_float(0x7f800000);
+    int gg = 0;
+#pragma unroll
+    for (int w = 0; w < WC; ++w) {
+      const float v = s_best[w * ROWS + rho];
+      const int g = s_bg[w * ROWS + rho];
+      if (v < bb || (v == bb && g < gg)) { bb = v; gg = g; }
+    }
+    const float px = __ldg(ap + 3 * j), py = __ldg(ap + 3 * j + 1), pz = __ldg(ap + 3 * j + 2);
+    int bi = gg;
+#pragma unroll
+    for (int u = 7; u >= 0; --u) {  // 8 independent (clamped) loads in flight, lowest match wins
+      const int kcol = min(gg + u, NB - 1);
+      const float* p = bp + static_cast<size_t>(kcol) * 3;
+      const float d = dist_yxz(__ldg(p) - px, __ldg(p + 1) - py, __ldg(p + 2) - pz);
+      if (d == bb && gg + u < NB) bi = gg + u;
+    }
+    distA[static_cast<size_t>(b) * NA + j] = bb;
+    idxA[static_cast<size_t>(b) * NA + j] = bi;
+  }
+}
+
+// Column side, second half: turn each packed key into (distance, lowest matching row index) by
+// recomputing the R distances of the winning row block.  One thread per column, all loads independent.
+template <int R>
+__global__ void __launch_bounds__(256)
+    chamfer_cols_finalize_kernel(const float* __restrict__ xyzA, const float* __restrict__ xyzB, int NA,
+                                 int NB, int NB8, const unsigned long long* __restrict__ colbest,
+                                 float* __restrict__ distB, int32_t* __restrict__ idxB) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= NB) return;
+  const float* ap = xyzA + static_cast<size_t>(b) * NA * 3;
+  const float* bp = xyzB + (static_cast<size_t>(b) * NB + k) * 3;
+  const unsigned long long key = colbest[static_cast<size_t>(b) * NB8 + k];
+  const unsigned bits = static_cast<unsigned>(key >> 32);
+  const int j0 = static_cast<int>(static_cast<unsigned>(key)) * R;
+  const float rx = __ldg(bp), ry = __ldg(bp + 1), rz = __ldg(bp + 2);
+  int bi = j0;
+#pragma unroll
+  for (int u = R - 1; u >= 0; --u) {
+    const int j = min(j0 + u, NA - 1);
+    const float* p = ap + static_cast<size_t>(j) * 3;
+    const float d = dist_yxz(rx - __ldg(p), ry - __ldg(p + 1), rz - __ldg(p + 2));
+    if (__float_as_uint(d) == bits && j0 + u < NA) bi = j0 + u;
+  }
+  distB[static_cast<size_t>(b) * NB + k] = __uint_as_float(bits);
+  idxB[static_cast<size_t>(b) * NB + k] = bi;
 }
 
 // Deterministic whole-call sums { sum d1, sum d2, sum sqrt d1, sum sqrt d2 } -- the send buffer of
@@ -237,22 +415,68 @@ static void launch_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int 
   chamfer_fwd_kernel<R, THREADS><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, dist1, dist2, idx1, idx2);
 }
 
+size_t chamfer_fwd_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  const size_t nb8 = (static_cast<size_t>(min(N, M)) + 7) & ~static_cast<size_t>(7);
+  return static_cast<size_t>(B) * nb8 * 8;
+}
+
+template <int R, int WC>
+static int launch_chamfer_both(const float* a, const float* bpts, int B, int NA, int NB, float* dA,
+                               int32_t* iA, float* dB, int32_t* iB, void* ws, cudaStream_t st) {
+  const int nb8 = (NB + 7) & ~7;
+  const size_t keys = static_cast<size_t>(B) * nb8 * 8;
+  cudaError_t e = cudaMemsetAsync(ws, 0xFF, keys, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  dim3 grid((NA + 32 * R - 1) / (32 * R), B);
+  chamfer_fwd_both_kernel<R, WC><<<grid, WC * 32, 0, st>>>(a, bpts, NA, NB, nb8, dA, iA, dB, iB,
+                                                          static_cast<unsigned long long*>(ws));
+  count_launch();
+  int rc = launch_status();
+  if (rc != UPP_OK) return rc;
+  chamfer_cols_finalize_kernel<R><<<dim3((NB + 255) / 256, B), 256, 0, st>>>(
+      a, bpts, NA, NB, nb8, static_cast<const unsigned long long*>(ws), dB, iB);
+  return UPP_OK;
+}
+
 int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
-                       float* dist2, int32_t* idx1, int32_t* idx2, float* sums, cudaStream_t st) {
-  const char* v = getenv("UPP_CH_VARIANT");  // tuning aid: "R,T"
-  const int variant = v ? atoi(v) : 0;
-  switch (variant) {
-    case 1: launch_chamfer_fwd<4, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    case 2: launch_chamfer_fwd<8, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    case 3: launch_chamfer_fwd<8, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    case 4: launch_chamfer_fwd<4, 256>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    case 5: launch_chamfer_fwd<4, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    case 6: launch_chamfer_fwd<2, 256>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    case 7: launch_chamfer_fwd<2, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    case 8: launch_chamfer_fwd<1, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    case 9: launch_chamfer_fwd<1, 256>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
-    // measured best on B200 (scripts/time_ops.py --sweep-chamfer): more warps beat more queries per thread
-    default: launch_chamfer_fwd<2, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+                       float* dist2, int32_t* idx1, int32_t* idx2, float* sums, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  const char* v = getenv("UPP_CH_VARIANT");  // tuning aid
+  const int variant = v ? atoi(v) : -1;
+  const bool have_ws = workspace != nullptr && workspace_bytes >= chamfer_fwd_workspace_bytes(B, N, M);
+  // single pass pays off once both clouds fill the 32*R-row tiles; tiny clouds stay on the directed kernel
+  const bool single = have_ws && min(N, M) >= 128 && (variant < 0 || variant >= 20);
+  if (single) {
+    // rows = the larger cloud (more CTAs), columns = the smaller one (fewer keys)
+    const bool swap = M > N;
+    const float* a = swap ? xyz2 : xyz1;
+    const float* c = swap ? xyz1 : xyz2;
+    const int na = swap ? M : N, nb = swap ? N : M;
+    float* dA = swap ? dist2 : dist1; float* dB = swap ? dist1 : dist2;
+    int32_t* iA = swap ? idx2 : idx1; int32_t* iB = swap ? idx1 : idx2;
+    const long ctas8 = static_cast<long>(B) * ((na + 255) / 256);
+    int rc;
+    int pick = variant >= 20 ? variant : (ctas8 >= 2 * 148 ? 20 : 21);
+    switch (pick) {
+      case 21: rc = launch_chamfer_both<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
+      case 22: rc = launch_chamfer_both<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
+      case 23: rc = launch_chamfer_both<4, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
+      case 24: rc = launch_chamfer_both<2, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
+      default: rc = launch_chamfer_both<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
+    }
+    if (rc != UPP_OK) return rc;
+  } else {
+    switch (variant) {
+      case 1: launch_chamfer_fwd<4, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+      case 5: launch_chamfer_fwd<4, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+      case 6: launch_chamfer_fwd<2, 256>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+      case 7: launch_chamfer_fwd<2, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+      case 8: launch_chamfer_fwd<1, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+      case 9: launch_chamfer_fwd<1, 256>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+      // measured best on B200 (scripts/time_ops.py --sweep-chamfer): more warps beat more queries per thread
+      default: launch_chamfer_fwd<2, 128>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;
+    }
   }
   count_launch();
   int rc = launch_status();

@@ -23,7 +23,8 @@ _SIGNATURES = {
     "upp_gather_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "upp_gather_grad_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "upp_knn_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
-    "upp_chamfer_fwd_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "upp_chamfer_fwd_workspace_bytes": [_i, _i, _i],
+    "upp_chamfer_fwd_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "upp_chamfer_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "upp_group_f32": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "upp_group_bwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
@@ -32,6 +33,7 @@ _RESTYPES = {
     "upp_error_string": ctypes.c_char_p,
     "upp_launch_count": ctypes.c_ulonglong,
     "upp_fps_workspace_bytes": _sz,
+    "upp_chamfer_fwd_workspace_bytes": _sz,
 }
 
 EXPORTS = tuple(_SIGNATURES)

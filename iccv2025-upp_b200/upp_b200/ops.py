@@ -147,9 +147,12 @@ def chamfer_forward(xyz1, xyz2, want_sums=False):
     i1 = torch.empty((B, N), dtype=torch.int32, device=dev)
     i2 = torch.empty((B, M), dtype=torch.int32, device=dev)
     sums = torch.empty(4, dtype=torch.float32, device=dev) if want_sums else None
+    lib = _lib.load()
+    wbytes = int(lib.upp_chamfer_fwd_workspace_bytes(B, N, M))
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev) if wbytes else None
     with _on(xyz1):
-        rc = _lib.load().upp_chamfer_fwd_f32(_ptr(xyz1), _ptr(xyz2), B, N, M, _ptr(d1), _ptr(d2),
-                                             _ptr(i1), _ptr(i2), _ptr(sums), _stream(xyz1))
+        rc = lib.upp_chamfer_fwd_f32(_ptr(xyz1), _ptr(xyz2), B, N, M, _ptr(d1), _ptr(d2), _ptr(i1), _ptr(i2),
+                                     _ptr(sums), _ptr(ws), wbytes, _stream(xyz1))
     _lib.check(rc, "upp_chamfer_fwd_f32")
     return [d1, d2, i1, i2] + ([sums] if want_sums else [])
 

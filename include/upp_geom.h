@@ -105,10 +105,15 @@ UPP_API int upp_knn_f32(const float* ref, const float* query, int B, int N, int 
  * partial_sums: optional (nullable) 4 floats, OVERWRITTEN with
  *   { sum dist1, sum dist2, sum sqrt(dist1), sum sqrt(dist2) } over the whole call -- the
  *   send buffer of the one NCCL all-reduce the batch-sharded loss needs (utils/dist_utils.py:41-48).
+ * workspace: optional scratch of upp_chamfer_fwd_workspace_bytes(B,N,M) bytes (contents irrelevant
+ *   on entry, clobbered on exit).  With it the single-pass kernel runs (each pairwise distance
+ *   computed once for both directions); with NULL the two-direction kernel runs.  Results are
+ *   identical either way.
  */
+UPP_API size_t upp_chamfer_fwd_workspace_bytes(int B, int N, int M);
 UPP_API int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                         float* dist2, int32_t* idx1, int32_t* idx2, float* partial_sums,
-                        upp_stream_t stream);
+                        void* workspace, size_t workspace_bytes, upp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Chamfer distance backward.

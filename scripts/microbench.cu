@@ -63,6 +63,7 @@ __global__ void bar_only_kernel(long long* out, int iters) {
 // ---- throughput: NW warps per CTA, 1 CTA per SM, unrolled independent ops ----
 // MIX: 0 = FFMA 3 distinct regs; 1 = FFMA a*a+c; 2 = FADD; 3 = chamfer pair (3 FADD, FMUL, 2 FFMA);
 //      4 = chamfer pair + FSETP/FSEL/SEL tracking; 5 = chamfer pair + FMNMX only; 6 = FMNMX only; 7 = pair + 0.5 FMNMX3
+//      8 = independent REDUX.MIN (throughput); 9 = independent SHFL.bfly; 10 = independent ballot
 template <int MIX>
 __global__ void __launch_bounds__(1024) tput_kernel(long long* out, float* sink, int iters, float a0) {
   float acc[8];
@@ -94,6 +95,9 @@ __global__ void __launch_bounds__(1024) tput_kernel(long long* out, float* sink,
         if (MIX == 7) { if (j & 1) acc[j] = fminf(fminf(acc[j], acc[j - 1]), d); else acc[j] = d; }
       }
       if (MIX == 6) asm volatile("min.f32 %0, %0, %1;" : "+f"(acc[j]) : "f"(qx));
+      if (MIX == 8) { unsigned r; asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(__float_as_uint(acc[j]) + i)); bi[j] += r; }
+      if (MIX == 9) { bi[j] += __shfl_xor_sync(0xffffffffu, bi[j] + i, 1); }
+      if (MIX == 10) { bi[j] += __ballot_sync(0xffffffffu, (bi[j] + i) & 1); }
     }
   }
   long long t1 = clock64();
@@ -173,5 +177,8 @@ int main() {
   run_tput<5>("pair + FMNMX", d_out, d_sink, 7);
   run_tput<4>("pair + FSETP/FSEL/SEL", d_out, d_sink, 9);
   run_tput<7>("pair + 0.5 FMNMX3", d_out, d_sink, 6);
+  run_tput<8>("REDUX.MIN independent (+IADD x2)", d_out, d_sink, 3);
+  run_tput<9>("SHFL.bfly independent (+IADD x2)", d_out, d_sink, 3);
+  run_tput<10>("ballot independent (+LOP,IADD x2)", d_out, d_sink, 4);
   return 0;
 }

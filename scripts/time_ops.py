@@ -61,10 +61,11 @@ def main():
         print(json.dumps(r), flush=True)
 
     if args.sweep_chamfer:
-        for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192)]:
+        for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 1024, 1024), (32, 256, 256), (8, 2048, 2048)]:
             a = torch.rand(B, N, 3, generator=g).to(dev)
             b = torch.rand(B, M, 3, generator=g).to(dev)
-            for v, name in enumerate(["R2T128", "R4T64", "R8T64", "R8T128", "R4T256", "R4T128", "R2T256", "R2T64", "R1T128", "R1T256"]):
+            for v, name in [(0, "2pass R2T128"), (6, "2pass R2T256"), (8, "2pass R1T128"), (9, "2pass R1T256"), (20, "1pass R8W8"),
+                            (21, "1pass R4W8"), (22, "1pass R8W4"), (23, "1pass R4W4"), (-1, "default")]:
                 os.environ["UPP_CH_VARIANT"] = str(v)
                 rec(f"chamfer-sweep {name} B{B} N{N} M{M}", lambda: ops.chamfer_forward(a, b),
                     lambda us: {"tflops_16NM": round(16.0 * N * M * B / us / 1e6, 2)})
@@ -98,9 +99,36 @@ def main():
     for (B, N, G, k) in [(32, 1024, 64, 32), (128, 1024, 64, 32), (32, 2048, 128, 32)]:
         x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
         rec(f"group B{B} N{N} G{G} k{k}", lambda: ops.group(x, G, k))
+    try:
+        from oracle import ref_gpu
+        ref = ref_gpu.load()   # the reference's own chamfer.cu, compiled unmodified (legacy default stream)
+    except Exception:
+        ref = None
     for (B, N, M) in [(64, 2048, 2048), (64, 1024, 1024), (64, 32, 1024), (64, 2048, 8192), (32, 1024, 1024)]:
         a = torch.rand(B, N, 3, generator=g).to(dev)
         b = torch.rand(B, M, 3, generator=g).to(dev)
+        if ref is not None and not args.only:
+            o = ref.forward(a, b)
+            g1r, g2r = torch.rand_like(o[0]), torch.rand_like(o[1])
+            for name, fn in (("REFERENCE chamfer_fwd", lambda: ref.forward(a, b)),
+                             ("REFERENCE chamfer_bwd", lambda: ref.backward(a, b, o[2], o[3], g1r, g2r))):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(10):
+                    flush.zero_()
+                    torch.cuda.synchronize()
+                    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s0.record()
+                    fn()
+                    e0.record()
+                    torch.cuda.synchronize()
+                    ts.append(s0.elapsed_time(e0) * 1e3)
+                ts.sort()
+                r = {"op": f"{name} B{B} N{N} M{M} (eager, incl. torch::zeros)", "us_median": round(ts[len(ts) // 2], 2)}
+                rows.append(r)
+                print(json.dumps(r), flush=True)
         rec(f"chamfer_fwd B{B} N{N} M{M}", lambda: ops.chamfer_forward(a, b),
             lambda us: {"tflops_8NM": round(8.0 * N * M * B / us / 1e6, 2), "tflops_16NM": round(16.0 * N * M * B / us / 1e6, 2)})
         d1, d2, i1, i2 = ops.chamfer_forward(a, b)

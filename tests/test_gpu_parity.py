@@ -174,12 +174,21 @@ def test_knn_module_modes_and_errors(U, O, dev):
 
 CH_SHAPES = [  # (B, N, M)
     (4, 64, 128), (2, 1, 1), (3, 5, 3), (2, 32, 1024), (2, 1024, 1024), (2, 2048, 2048), (1, 2048, 8192),
-    (2, 513, 2049), (2, 1000, 4099), (3, 300, 200),
+    (2, 513, 2049), (2, 1000, 4099), (3, 300, 200), (2, 128, 128), (2, 129, 255), (3, 257, 131), (70, 256, 300),
 ]
 
 
+@pytest.fixture(params=["single_pass", "two_pass"])
+def chamfer_path(request, monkeypatch):
+    """Both forward kernels must give identical results: the single-pass kernel (default when the
+    binding passes a workspace) and the directed two-pass kernel (UPP_CH_VARIANT=0 forces it)."""
+    if request.param == "two_pass":
+        monkeypatch.setenv("UPP_CH_VARIANT", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("B,N,M", CH_SHAPES)
-def test_chamfer_forward_bit_exact(U, O, dev, B, N, M):
+def test_chamfer_forward_bit_exact(U, O, dev, chamfer_path, B, N, M):
     g = torch.Generator().manual_seed(N * 7 + M)
     a, b = torch.rand(B, N, 3, generator=g), torch.rand(B, M, 3, generator=g)
     d1, d2, i1, i2 = [t.cpu().numpy() for t in U.chamfer.forward(a.to(dev), b.to(dev))]
@@ -189,7 +198,22 @@ def test_chamfer_forward_bit_exact(U, O, dev, B, N, M):
     assert np.array_equal(d1, o1) and np.array_equal(d2, o2)
 
 
-def test_chamfer_against_reference_cuda_extension(U, dev):
+def test_chamfer_ties_and_duplicates_both_kernels(U, O, dev, chamfer_path):
+    """Lattice points + duplicated points: many exactly equal distances in both directions."""
+    ax = torch.arange(7, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3)
+    a = torch.cat([grid, grid[:, :57]], 1).repeat(3, 1, 1).contiguous()          # 400 points, 57 duplicates
+    b = (grid[:, torch.randperm(343, generator=torch.Generator().manual_seed(1))] + 0.5).repeat(3, 1, 1).contiguous()
+    d1, d2, i1, i2 = [t.cpu().numpy() for t in U.chamfer.forward(a.to(dev), b.to(dev))]
+    o1, o2, j1, j2 = O.chamfer_fwd(a.numpy(), b.numpy())
+    assert np.array_equal(i1, j1) and np.array_equal(i2, j2)
+    assert np.array_equal(d1, o1) and np.array_equal(d2, o2)
+    d1, d2, i1, i2 = [t.cpu().numpy() for t in U.chamfer.forward(a.to(dev), a.flip(1).contiguous().to(dev))]
+    o1, o2, j1, j2 = O.chamfer_fwd(a.numpy(), a.flip(1).contiguous().numpy())
+    assert np.array_equal(i1, j1) and np.array_equal(i2, j2) and np.array_equal(d1, o1) and np.array_equal(d2, o2)
+
+
+def test_chamfer_against_reference_cuda_extension(U, dev, chamfer_path):
     """The reference's own chamfer.cu, compiled unmodified into oracle/_ref (when it travelled)."""
     from oracle import ref_gpu
     ref = ref_gpu.load()

@@ -49,7 +49,7 @@ def test_cabi_argument_validation_without_gpu(lib):
     assert lib.upp_fps_f32(None, 2, 16, 4, None, None, None, 0, None) == -1
     assert lib.upp_fps_f32(None, -1, 16, 4, None, None, None, 0, None) == -1
     assert lib.upp_fps_f32(None, 0, 16, 4, None, None, None, 0, None) == 0
-    assert lib.upp_chamfer_fwd_f32(None, None, 2, 8, 8, None, None, None, None, None, None) == -1
+    assert lib.upp_chamfer_fwd_f32(None, None, 2, 8, 8, None, None, None, None, None, None, 0, None) == -1
     assert lib.upp_chamfer_bwd_f32(None, None, None, None, None, None, 2, 8, 8, None, None, None) == -1
     assert lib.upp_group_f32(None, 2, 8, 4, 9, None, None, None, None, None, 0, None) == -1  # k > N
     assert lib.upp_gather_f32(None, None, 2, 3, 8, 4, None, None) == -1
