@@ -11,7 +11,7 @@ void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(
 
 int fps_launch(const float*, int, int, int, int32_t*, float*, void*, size_t, cudaStream_t);
 size_t fps_workspace_bytes(int, int);
-int knn_launch(const float*, const float*, int, int, int, int, float*, int64_t*, cudaStream_t);
+int knn_launch(const float*, const float*, int, int, int, int, float*, int64_t*, float*, cudaStream_t);
 int chamfer_fwd_launch(const float*, const float*, int, int, int, float*, float*, int32_t*, int32_t*,
                        float*, void*, size_t, cudaStream_t);
 size_t chamfer_fwd_workspace_bytes(int, int, int);
@@ -88,7 +88,7 @@ int upp_knn_f32(const float* ref, const float* query, int B, int N, int Q, int k
   UPP_REQUIRE(k >= 1 && k <= N);
   if (B == 0 || Q == 0) return UPP_OK;
   UPP_REQUIRE(ref && query && idx_out);
-  return knn_launch(ref, query, B, N, Q, k, dist_out, idx_out, S(stream));
+  return knn_launch(ref, query, B, N, Q, k, dist_out, idx_out, nullptr, S(stream));
 }
 
 size_t upp_chamfer_fwd_workspace_bytes(int B, int N, int M) { return chamfer_fwd_workspace_bytes(B, N, M); }
@@ -139,9 +139,8 @@ int upp_group_f32(const float* xyz, int B, int N, int G, int k, float* neighborh
   UPP_REQUIRE(xyz && neighborhood && center && idx && center_idx);
   int rc = fps_launch(xyz, B, N, G, center_idx, center, workspace, workspace_bytes, S(stream));
   if (rc != UPP_OK) return rc;
-  rc = knn_launch(xyz, center, B, N, G, k, nullptr, idx, S(stream));
-  if (rc != UPP_OK) return rc;
-  return group_gather_launch(xyz, center, idx, B, N, G, k, neighborhood, S(stream));
+  // kNN with the fused epilogue: neighbourhood = xyz[idx] - center, no separate gather launch
+  return knn_launch(xyz, center, B, N, G, k, nullptr, idx, neighborhood, S(stream));
 }
 
 int upp_group_bwd_f32(const float* grad_nb, const float* grad_center, const int64_t* idx,

@@ -114,6 +114,115 @@ __global__ void __launch_bounds__(TT ? TT : (P > 8 ? 512 : 1024), 1)
   }
 }
 
+// Variant for small / medium clouds: FOUR warps per cloud, one per SM sub-partition, so the P
+// points of a thread issue back to back with no contention, BAR.SYNC is at its cheapest (21 cycles
+// at 4 warps vs 45 at 16) and the second stage is a register scan of the four per-warp winners
+// (two LDS.128 + three compare/selects) instead of two more REDUX.  In-thread max and lowest-index
+// resolution are balanced trees (VIMNMX3), not serial chains.  128-thread CTAs also let up to 16
+// clouds share an SM when the batch is large.
+template <int P>
+__global__ void __launch_bounds__(128, 1)
+    fps_w4_kernel(const float* __restrict__ xyz, int N, int M, int32_t* __restrict__ idx_out,
+                  float* __restrict__ centers_out) {
+  constexpr int THREADS = 128;
+  extern __shared__ __align__(16) float s_xyz[];
+  __shared__ __align__(16) int2 s_slot[2][4];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.x;
+  const float* p = xyz + static_cast<size_t>(b) * N * 3;
+  int32_t* out = idx_out + static_cast<size_t>(b) * M;
+  float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
+
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned parity = 0;
+  stage_points(s_xyz, p, N, &s_bar, parity);
+
+  float x[P], y[P], z[P], md[P];
+#pragma unroll
+  for (int r = 0; r < P; ++r) {
+    const int i = t + r * THREADS;
+    if (i < N) {
+      x[r] = s_xyz[3 * i];
+      y[r] = s_xyz[3 * i + 1];
+      z[r] = s_xyz[3 * i + 2];
+      md[r] = fps_initial_md(x[r], y[r], z[r]);
+    } else {
+      x[r] = y[r] = z[r] = 0.f;
+      md[r] = kOutOfRange;
+    }
+  }
+  float cx = s_xyz[0], cy = s_xyz[1], cz = s_xyz[2];
+  if (t == 0) {
+    out[0] = 0;
+    if (cen) { cen[0] = cx; cen[1] = cy; cen[2] = cz; }
+  }
+
+  for (int j = 1; j < M; ++j) {
+    int key[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+      const float d = dist_yxz(x[r] - cx, y[r] - cy, z[r] - cz);
+      md[r] = fminf(md[r], d);
+      key[r] = __float_as_int(md[r]);
+    }
+    // balanced max tree over the thread's keys
+    int red[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) red[r] = key[r];
+#pragma unroll
+    for (int n = P; n > 1; n = (n + 2) / 3) {
+#pragma unroll
+      for (int q = 0; q < (n + 2) / 3; ++q) {
+        int v = red[3 * q];
+        if (3 * q + 1 < n) v = max(v, red[3 * q + 1]);
+        if (3 * q + 2 < n) v = max(v, red[3 * q + 2]);
+        red[q] = v;
+      }
+    }
+    const int wbest = redux_max_s32(red[0]);
+    // lowest point index among this thread's points equal to the warp maximum (balanced min tree)
+    unsigned cnd[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) cnd[r] = key[r] == wbest ? static_cast<unsigned>(t + r * THREADS) : 0xffffffffu;
+#pragma unroll
+    for (int n = P; n > 1; n = (n + 2) / 3) {
+#pragma unroll
+      for (int q = 0; q < (n + 2) / 3; ++q) {
+        unsigned v = cnd[3 * q];
+        if (3 * q + 1 < n) v = min(v, cnd[3 * q + 1]);
+        if (3 * q + 2 < n) v = min(v, cnd[3 * q + 2]);
+        cnd[q] = v;
+      }
+    }
+    const int widx = static_cast<int>(redux_min_u32(cnd[0]));
+    int2* slot = s_slot[j & 1];
+    if (lane == 0) slot[warp] = make_int2(wbest, widx);
+    __syncthreads();
+    // stage 2 in registers: scan the four per-warp winners (value desc, index asc)
+    const int4 s01 = *reinterpret_cast<const int4*>(&slot[0]);
+    const int4 s23 = *reinterpret_cast<const int4*>(&slot[2]);
+    int bv = s01.x, bi = s01.y;
+    if (s01.z > bv || (s01.z == bv && s01.w < bi)) { bv = s01.z; bi = s01.w; }
+    int cv = s23.x, ci = s23.y;
+    if (s23.z > cv || (s23.z == cv && s23.w < ci)) { cv = s23.z; ci = s23.w; }
+    if (cv > bv || (cv == bv && ci < bi)) { bv = cv; bi = ci; }
+    const int sel = bi;
+    cx = s_xyz[3 * sel];
+    cy = s_xyz[3 * sel + 1];
+    cz = s_xyz[3 * sel + 2];
+    if (t == 0) {
+      out[j] = sel;
+      if (cen) { cen[3 * j] = cx; cen[3 * j + 1] = cy; cen[3 * j + 2] = cz; }
+    }
+  }
+}
+
 // Any-N fallback: min-distance array in a global workspace (L2-resident), xyz re-read from
 // global memory every iteration.  Same selection rule, same two-stage arg-max.
 template <int THREADS>
@@ -237,6 +346,36 @@ static int launch_fps_rt(int threads, const float* xyz, int B, int N, int M, int
   return launch_status();
 }
 
+template <int P>
+static int launch_fps_w4(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
+                         cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(N) * 3 * sizeof(float);
+  auto kern = fps_w4_kernel<P>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  kern<<<B, 128, smem, st>>>(xyz, N, M, idx, centers);
+  count_launch();
+  return launch_status();
+}
+
+static int dispatch_fps_w4(int p, const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
+                           cudaStream_t st) {
+  switch (p) {
+    case 1: return launch_fps_w4<1>(xyz, B, N, M, idx, centers, st);
+    case 2: return launch_fps_w4<2>(xyz, B, N, M, idx, centers, st);
+    case 3: return launch_fps_w4<3>(xyz, B, N, M, idx, centers, st);
+    case 4: return launch_fps_w4<4>(xyz, B, N, M, idx, centers, st);
+    case 6: return launch_fps_w4<6>(xyz, B, N, M, idx, centers, st);
+    case 8: return launch_fps_w4<8>(xyz, B, N, M, idx, centers, st);
+    case 12: return launch_fps_w4<12>(xyz, B, N, M, idx, centers, st);
+    case 16: return launch_fps_w4<16>(xyz, B, N, M, idx, centers, st);
+    default: return UPP_ERR_UNSUPPORTED;
+  }
+}
+
 #define UPP_FPS_CASE_P(T, PP) \
   case PP: return launch_fps_reg<T, PP>(xyz, B, N, M, idx, centers, st);
 #define UPP_FPS_CASE_T(T) \
@@ -245,6 +384,11 @@ static int launch_fps_rt(int threads, const float* xyz, int B, int N, int M, int
 int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (N <= kFpsMaxRegPoints) {
+    // 4-warp variant: measured better for 1280 < N <= 2048 at any batch, and for every N <= 2048 once
+    // the batch is large enough that several clouds share an SM (B=512, N=1024: 108 vs 143 us).
+    const int w4 = env_int("UPP_FPS_W4", -1);  // tuning aid: 1 force, 0 forbid
+    if (N > 32 && N <= 2048 && (w4 == 1 || (w4 != 0 && (N > 1280 || B >= 2 * 148))))
+      return dispatch_fps_w4(round_p((N + 127) / 128), xyz, B, N, M, idx, centers, st);
     const int ft = env_int("UPP_FPS_THREADS", 0), fp = env_int("UPP_FPS_P", 0);
     if (ft >= 32 && ft <= 1024 && ft % 32 == 0 && fp > 0 && round_p(fp) == fp &&
         static_cast<long>(ft) * fp >= N && ft <= (fp > 8 ? 512 : 1024)) {

@@ -72,9 +72,15 @@ def main():
             os.environ.pop("UPP_CH_VARIANT", None)
         return
     if args.sweep_fps:
-        for (B, N, M) in [(32, 1228, 1024), (32, 1024, 256), (32, 2048, 256), (128, 8192, 256), (32, 512, 256), (32, 256, 128)]:
+        for (B, N, M) in [(32, 1228, 1024), (32, 1024, 512), (32, 2048, 512), (32, 1536, 512), (32, 512, 256), (32, 256, 256), (32, 128, 128),
+                          (32, 64, 64), (512, 1024, 256)]:
             x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
             rec(f"fps-sweep B{B} N{N} M{M} default", lambda: ops.fps(x, M), lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
+            if N <= 2048:
+                os.environ["UPP_FPS_W4"] = "1"
+                rec(f"fps-sweep B{B} N{N} M{M} W4", lambda: ops.fps(x, M), lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
+                os.environ.pop("UPP_FPS_W4", None)
+                continue
             for p in (1, 2, 3, 4, 6, 8, 12, 16):
                 threads = ((N + p - 1) // p + 31) // 32 * 32
                 if threads > (512 if p > 8 else 1024) or threads < 32:

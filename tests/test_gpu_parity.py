@@ -39,8 +39,19 @@ FPS_SHAPES = [  # (B, N, M)  -- SURVEY.md Appendix A census + edges
 ]
 
 
+@pytest.fixture(params=["default", "w4", "no_w4"])
+def fps_kernel(request, monkeypatch):
+    """Every register-resident FPS kernel family must agree with the oracle: the heuristic's choice, the
+    4-warp variant forced on, and forced off (UPP_FPS_W4 is a tuning switch read per launch)."""
+    if request.param == "w4":
+        monkeypatch.setenv("UPP_FPS_W4", "1")
+    elif request.param == "no_w4":
+        monkeypatch.setenv("UPP_FPS_W4", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("B,N,M", FPS_SHAPES)
-def test_fps_matches_oracle_cube(U, O, dev, B, N, M):
+def test_fps_matches_oracle_cube(U, O, dev, fps_kernel, B, N, M):
     xyz = cube(B, N, 100 + N + M)
     got = U.ops.fps(xyz.to(dev), M).cpu().numpy()
     assert got.dtype == np.int32 and got.shape == (B, M)
@@ -48,7 +59,7 @@ def test_fps_matches_oracle_cube(U, O, dev, B, N, M):
 
 
 @pytest.mark.parametrize("B,N,M", [(4, 1024, 64), (2, 2048, 128), (2, 8192, 1024), (3, 1096, 32)])
-def test_fps_unit_sphere_skip_quirk(U, O, dev, B, N, M):
+def test_fps_unit_sphere_skip_quirk(U, O, dev, fps_kernel, B, N, M):
     """Dataset-normalised clouds have points with |p|^2 <= 1e-3: never selected (upstream quirk)."""
     xyz = unit_sphere(torch.randn(B, N, 3, generator=torch.Generator().manual_seed(7)) * 0.3)
     near = (xyz.pow(2).sum(-1) <= 1e-3)
@@ -60,7 +71,12 @@ def test_fps_unit_sphere_skip_quirk(U, O, dev, B, N, M):
     assert not picked_near.any()
 
 
-def test_fps_exact_ties_lowest_index(U, O, dev):
+def test_fps_large_batch_heuristic_path(U, O, dev):
+    xyz = cube(300, 200, 77)  # B >= 2*148 switches to the 4-warp kernel
+    assert np.array_equal(U.ops.fps(xyz.to(dev), 24).cpu().numpy(), O.fps(xyz.numpy(), 24))
+
+
+def test_fps_exact_ties_lowest_index(U, O, dev, fps_kernel):
     """Integer lattice => many exactly equal distances; tie-break must be the lowest index."""
     ax = torch.arange(8, dtype=torch.float32)
     grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3) + 1.0
