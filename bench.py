@@ -93,22 +93,28 @@ class GpuWorkload:
         self.host = {k: v.pin_memory() for k, v in host.items()}
         self.d = {k: v.to(dev) for k, v in host.items()}
         self.B = next(iter(host.values())).shape[0]
-        self.timers = None  # when set: list collecting (label, start_event, stop_event)
+        self.collect = None  # when set: list collecting (label, fn, args, kwargs) of every labelled op
+        self.side = [torch.cuda.Stream(device=dev) for _ in range(2)]  # independent branches of the step
         U = upp_b200
         self.g32_16, self.g64_32, self.g32_8 = U.Group(32, 16), U.Group(64, 32), U.Group(32, 8)
         self.g128_32 = U.Group(128, 32)
         self.cd_l1 = U.ChamferDistanceL1()
 
-    # -- per-op event timing (roofline pass) --
+    # -- per-op bookkeeping (roofline pass times every labelled op alone, as its own CUDA graph) --
     def _t(self, label, fn, *a, **k):
-        if self.timers is None:
-            return fn(*a, **k)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        out = fn(*a, **k)
-        e.record()
-        self.timers.append((label, s, e))
-        return out
+        if self.collect is not None:
+            self.collect.append((label, fn, a, k))
+        return fn(*a, **k)
+
+    def _fork(self):
+        cur = torch.cuda.current_stream()
+        for st in self.side:
+            st.wait_stream(cur)
+        return cur
+
+    def _join(self, cur):
+        for st in self.side:
+            cur.wait_stream(st)
 
     def h2d_bytes(self):
         keys = {"upp_cls_geometry+chamfer": ("pts", "rebuild", "target")}.get(self.name, tuple(self.host))
@@ -119,31 +125,40 @@ class GpuWorkload:
         o, t = self.ops, self._t
         n = self.name
         if n == "upp_cls_geometry+chamfer":
+            # The step is a DAG with three independent branches: the serial FPS chain of the
+            # completion stage + downstream grouping (critical path), the rectification-stage groupings, and
+            # the Chamfer loss.  They run on three streams (fork/join; captured as one CUDA graph), so the
+            # short branches fill the SMs the one-CTA-per-cloud FPS chain leaves idle.
             B = self.B
-            g1 = t("group N1096 G32 k16", o.group, d["pts"], 32, 16)
-            t("group N32 G32 k16", o.group, g1[1], 32, 16)
+            nglob = float(B * self.world * 1024)
             keep = d["pts"][:, :972].contiguous()
-            t("group N972 G32 k16", o.group, keep, 32, 16)
+            cur = self._fork()
+            with torch.cuda.stream(self.side[0]):
+                g1 = t("group N1096 G32 k16", o.group, d["pts"], 32, 16)
+                t("group N32 G32 k16", o.group, g1[1], 32, 16)
+                t("group N972 G32 k16", o.group, keep, 32, 16)
+            with torch.cuda.stream(self.side[1]):
+                d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward, d["rebuild"], d["target"], True)
+                if self.world > 1:
+                    self.par.reduce_sums(sums)
+                loss = (sums[2] + sums[3]) / (2.0 * nglob)
+                gd1 = (0.25 / nglob) / torch.sqrt(d1)
+                gd2 = (0.25 / nglob) / torch.sqrt(d2)
+                ga, _ = t("chamfer_bwd N1024 M1024", o.chamfer_backward, d["rebuild"], d["target"], j1, j2, gd1, gd2)
             i1, c1 = t("fps N1024 M256", o.fps, d["rebuild"], 256, True)
             cat = torch.cat([keep, c1], 1)
             i2, c2 = t("fps N1228 M1024", o.fps, cat, 1024, True)
             g4 = t("group N1024 G64 k32", o.group, c2, 64, 32)
             g5 = t("group N64 G32 k8", o.group, g4[1], 32, 8)
-            d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward, d["rebuild"], d["target"], True)
-            if self.world > 1:
-                self.par.reduce_sums(sums)
-            nglob = float(B * self.world * 1024)
-            loss = (sums[2] + sums[3]) / (2.0 * nglob)
-            # backward chain: G5 -> G4 -> fps(1228->1024) gather -> fps(1024->256) gather, + Chamfer
+            # backward chain: G5 -> G4 -> fps(1228->1024) gather -> fps(1024->256) gather
             gc4 = t("group_bwd N64", o.group_backward, torch.zeros_like(g5[0]), d["w_c5"], g5[2], g5[3], 64)
             gx = t("group_bwd N1024", o.group_backward, d["w_nb"], gc4, g4[2], g4[3], 1024)
             gcat = t("gather_grad N1228", o.gather_grad, gx.transpose(1, 2).contiguous(), i2, 1228)
             gc1 = gcat[:, :, 972:].contiguous()
             greb = t("gather_grad N1024", o.gather_grad, gc1, i1, 1024).transpose(1, 2)
-            gd1 = (0.25 / nglob) / torch.sqrt(d1)
-            gd2 = (0.25 / nglob) / torch.sqrt(d2)
-            ga, _ = t("chamfer_bwd N1024 M1024", o.chamfer_backward, d["rebuild"], d["target"], j1, j2, gd1, gd2)
+            self._join(cur)
             self.grad = ga + greb
+            self.keepalive = (g1, g4, g5, d1, d2)
             return loss
         if n == "c1":
             nb, ce, _, _ = t("group N1024 G64 k32", o.group, d["pts"], 64, 32)
@@ -169,19 +184,23 @@ class GpuWorkload:
     def run_modules(self, d):
         U, n = self.U, self.name
         if n == "upp_cls_geometry+chamfer":
-            _, ce1 = self.g32_16(d["pts"])
-            self.g32_16(ce1)
             keep = d["pts"][:, :972].contiguous()
-            self.g32_16(keep)
             reb = d["rebuild"].detach().requires_grad_(True)
+            cur = self._fork()
+            with torch.cuda.stream(self.side[0]):
+                _, ce1 = self.g32_16(d["pts"])
+                self.g32_16(ce1)
+                self.g32_16(keep)
+            with torch.cuda.stream(self.side[1]):
+                if self.world > 1:
+                    cd = self.par.sharded_chamfer(reb, d["target"], "l1", n_global_clouds=self.B * self.world)
+                else:
+                    cd = self.cd_l1(reb, d["target"])
             c1, _ = U.fps(reb, 256)
             c2, _ = U.fps(torch.cat([keep, c1], 1), 1024)
             nb4, ce4 = self.g64_32(c2)
             _, ce5 = self.g32_8(ce4)
-            if self.world > 1:
-                cd = self.par.sharded_chamfer(reb, d["target"], "l1", n_global_clouds=self.B * self.world)
-            else:
-                cd = self.cd_l1(reb, d["target"])
+            self._join(cur)
             loss = cd + 1e-9 * ((nb4 * d["w_nb"]).sum() + (ce5 * d["w_c5"]).sum())
             loss.backward()
             self.grad = reb.grad
@@ -480,18 +499,39 @@ def main():
     barrier()
     e2e_ms = sum(s.elapsed_time(e) for s, e in evs)
 
-    # ---- per-kernel pass (roofline): eager ops with CUDA events around every op ----
-    per_op = {}
-    for it in range(args.warmup + args.steps):
-        W.timers = []
-        flush.zero_()
-        W.run_ops(W.d)
-        torch.cuda.synchronize()
-        if it >= args.warmup:
-            for label, s, e in W.timers:
-                per_op.setdefault(label, []).append(s.elapsed_time(e))
-        W.timers = None
-    op_ms = {k: sum(v) / len(v) for k, v in per_op.items()}
+    # ---- per-kernel pass (roofline): every labelled op of the step alone, as its own CUDA graph (no Python or
+    #      launch gaps), CUDA events around REPS back-to-back replays (event resolution here is ~2 us).
+    #      Inputs are the step's own tensors: L2-warm, as they are inside the step (producer -> consumer). ----
+    W.collect = []
+    W.run_ops(W.d)
+    torch.cuda.synchronize()
+    ops_seen, W.collect = W.collect, None
+    op_ms, REPS = {}, 5
+    for label, fn, a, k in ops_seen:
+        if label in op_ms:
+            continue
+        try:
+            for _ in range(2):
+                fn(*a, **k)
+            torch.cuda.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                fn(*a, **k)
+            run = g1.replay
+        except Exception:
+            torch.cuda.synchronize()
+            run = lambda fn=fn, a=a, k=k: fn(*a, **k)  # noqa: E731
+        ts = []
+        for it in range(3 + max(5, args.steps // 3)):
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(REPS):
+                run()
+            e0.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ts.append(s0.elapsed_time(e0) / REPS)
+        op_ms[label] = statistics.median(ts)
 
     # max over ranks
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)

@@ -26,6 +26,42 @@ __device__ __forceinline__ float dist_xyz_acc(float dx, float dy, float dz) {
   return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
+// ---- packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2) ---------------------------
+// One issue slot performs the IEEE-rn operation on both 32-bit halves of a 64-bit register pair:
+// results are bit-identical to the scalar __fsub_rn/__fmul_rn/__fmaf_rn forms above, at half the
+// issue slots -- which is what binds these kernels (scripts/microbench2.cu).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// two distances at once, each half == dist_yxz / dist_xyz_acc of the scalar forms
+__device__ __forceinline__ f32x2 dist2_yxz(f32x2 dx, f32x2 dy, f32x2 dz) {
+  return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+}
+__device__ __forceinline__ f32x2 dist2_xyz_acc(f32x2 dx, f32x2 dy, f32x2 dz) {
+  return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+}
+
 // ---- warp reductions in one instruction (REDUX) ----------------------------------------
 __device__ __forceinline__ int redux_max_s32(int v) {
   int r;

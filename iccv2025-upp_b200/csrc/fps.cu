@@ -223,6 +223,186 @@ __global__ void __launch_bounds__(128, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2 (fps_blk_kernel): the same register-resident scheme re-cut around what the B200 measurements
+// say binds one round (scripts/microbench2.cu): issue slots and the dependent REDUX/BAR/LDS chain.
+//   * BLOCKED ownership: thread t holds points [t*P, t*P+P), P = 2*P2.  A lower lane / lower warp
+//     then always means lower point indices, so "lowest index among equal maxima" is decided by
+//     position: in-thread lowest slot, ballot + find-first-set across lanes, lowest warp across
+//     warps.  No index REDUX anywhere (v1: two REDUX.MIN on the dependent chain).
+//   * PACKED fp32x2 math: the thread's points sit in 64-bit register pairs {x_2r, x_2r+1}; one
+//     FADD2/FMUL2/FFMA2 updates two points (6 issue slots per 2 points instead of 12, results
+//     bit-identical to the scalar spelling).
+//   * the in-thread slot search runs in the shadow of the REDUX (it needs only the thread's own
+//     maximum), the warp's winning lane posts {key, index} and ONE __syncthreads later every
+//     thread resolves the block winner itself: S2 == 0 scans the NW posted pairs with vector
+//     LDS + a select tree (NW <= 8), S2 == 1 does REDUX.MAX + ballot over them (NW >= 16).
+//   * a single warp (NW == 1) needs no shared-memory round trip at all.
+template <int NW, int P2, int S2>
+__global__ void __launch_bounds__(NW * 32)
+    fps_blk_kernel(const float* __restrict__ xyz, int N, int M, int32_t* __restrict__ idx_out,
+                   float* __restrict__ centers_out) {
+  constexpr int P = 2 * P2;
+  extern __shared__ __align__(16) float s_xyz[];  // 3*N floats (AoS, as in global memory)
+  __shared__ __align__(16) int2 s_slot[2][NW];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int b = blockIdx.x;
+  const float* p = xyz + static_cast<size_t>(b) * N * 3;
+  int32_t* out = idx_out + static_cast<size_t>(b) * M;
+  float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
+
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned parity = 0;
+  stage_points(s_xyz, p, N, &s_bar, parity);
+
+  const int base = t * P;
+  f32x2 X[P2], Y[P2], Z[P2];
+  float md[P];
+#pragma unroll
+  for (int r = 0; r < P2; ++r) {
+    float c[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = base + 2 * r + h;
+      if (i < N) {
+        c[h][0] = s_xyz[3 * i];
+        c[h][1] = s_xyz[3 * i + 1];
+        c[h][2] = s_xyz[3 * i + 2];
+        md[2 * r + h] = fps_initial_md(c[h][0], c[h][1], c[h][2]);
+      } else {
+        c[h][0] = c[h][1] = c[h][2] = 0.f;
+        md[2 * r + h] = kOutOfRange;
+      }
+    }
+    X[r] = pack2(c[0][0], c[1][0]);
+    Y[r] = pack2(c[0][1], c[1][1]);
+    Z[r] = pack2(c[0][2], c[1][2]);
+  }
+
+  float cx = s_xyz[0], cy = s_xyz[1], cz = s_xyz[2];
+  if (t == 0) {
+    out[0] = 0;
+    if (cen) { cen[0] = cx; cen[1] = cy; cen[2] = cz; }
+  }
+
+  const unsigned lanes_below = (1u << lane) - 1u;
+  for (int j = 1; j < M; ++j) {
+    const f32x2 CX = pack2(cx, cx), CY = pack2(cy, cy), CZ = pack2(cz, cz);
+    // all P2 packed distance chains are independent: spelled stage by stage so that they are
+    // scheduled interleaved (one warp per scheduler has nobody else to hide a dependent chain)
+    f32x2 D[P2];
+#pragma unroll
+    for (int r = 0; r < P2; ++r) D[r] = sub2(Y[r], CY);
+#pragma unroll
+    for (int r = 0; r < P2; ++r) D[r] = mul2(D[r], D[r]);
+#pragma unroll
+    for (int r = 0; r < P2; ++r) { const f32x2 dx = sub2(X[r], CX); D[r] = fma2(dx, dx, D[r]); }
+#pragma unroll
+    for (int r = 0; r < P2; ++r) { const f32x2 dz = sub2(Z[r], CZ); D[r] = fma2(dz, dz, D[r]); }
+    int key[P];
+#pragma unroll
+    for (int r = 0; r < P2; ++r) {
+      float d0, d1;
+      unpack2(D[r], d0, d1);
+      md[2 * r] = fminf(md[2 * r], d0);
+      md[2 * r + 1] = fminf(md[2 * r + 1], d1);
+      key[2 * r] = __float_as_int(md[2 * r]);
+      key[2 * r + 1] = __float_as_int(md[2 * r + 1]);
+    }
+    int red[P];
+#pragma unroll
+    for (int s = 0; s < P; ++s) red[s] = key[s];
+#pragma unroll
+    for (int n = P; n > 1; n = (n + 2) / 3) {  // balanced VIMNMX3 tree
+#pragma unroll
+      for (int q = 0; q < (n + 2) / 3; ++q) {
+        int v = red[3 * q];
+        if (3 * q + 1 < n) v = max(v, red[3 * q + 1]);
+        if (3 * q + 2 < n) v = max(v, red[3 * q + 2]);
+        red[q] = v;
+      }
+    }
+    const int best = red[0];
+    const int wbest = redux_max_s32(best);
+    // lowest own slot holding the thread's maximum: needs only `best`, so it runs in the shadow of
+    // the REDUX.  Few warps: independent compare/selects + a VIMNMX3 tree (short chain); many
+    // warps: one select chain (fewest issue slots, other warps hide its latency).
+    int ls;
+    if constexpr (NW <= 4) {
+      int cnd[P];
+#pragma unroll
+      for (int s = 0; s < P; ++s) cnd[s] = key[s] == best ? s : P;
+#pragma unroll
+      for (int n = P; n > 1; n = (n + 2) / 3) {
+#pragma unroll
+        for (int q = 0; q < (n + 2) / 3; ++q) {
+          int v = cnd[3 * q];
+          if (3 * q + 1 < n) v = min(v, cnd[3 * q + 1]);
+          if (3 * q + 2 < n) v = min(v, cnd[3 * q + 2]);
+          cnd[q] = v;
+        }
+      }
+      ls = cnd[0];
+    } else {
+      ls = P - 1;
+#pragma unroll
+      for (int s = P - 2; s >= 0; --s)
+        if (key[s] == best) ls = s;
+    }
+    const unsigned winners = __ballot_sync(0xffffffffu, best == wbest);
+    int sel;
+    if constexpr (NW == 1) {
+      sel = __shfl_sync(0xffffffffu, base + ls, __ffs(winners) - 1);
+    } else {
+      int2* slot = s_slot[j & 1];
+      // the lowest lane holding the warp maximum posts (lower lane == lower point indices)
+      if (best == wbest && (winners & lanes_below) == 0u) slot[warp] = make_int2(wbest, base + ls);
+      __syncthreads();
+      if constexpr (S2 == 0) {
+        int v[NW], ix[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w += 2) {
+          const int4 a = *reinterpret_cast<const int4*>(&slot[w]);
+          v[w] = a.x; ix[w] = a.y; v[w + 1] = a.z; ix[w + 1] = a.w;
+        }
+#pragma unroll
+        for (int stride = 1; stride < NW; stride <<= 1)
+#pragma unroll
+          for (int w = 0; w + stride < NW; w += 2 * stride)
+            if (v[w + stride] > v[w]) { v[w] = v[w + stride]; ix[w] = ix[w + stride]; }  // strict: lower warp on ties
+        sel = ix[0];
+      } else {
+        const int2 s = (lane < NW) ? slot[lane] : make_int2(INT_MIN, 0);
+        const int bbest = redux_max_s32(s.x);
+        const unsigned wm = __ballot_sync(0xffffffffu, s.x == bbest);
+        sel = __shfl_sync(0xffffffffu, s.y, __ffs(wm) - 1);
+      }
+    }
+    cx = s_xyz[3 * sel];
+    cy = s_xyz[3 * sel + 1];
+    cz = s_xyz[3 * sel + 2];
+    if (t == 0) out[j] = sel;
+  }
+  // centres (the fused gather of utils/misc.py:19) after the serial chain, by the whole CTA
+  if (cen) {
+    __syncthreads();  // thread 0's out[] stores are visible to the block
+    for (int j = 1 + t; j < M; j += NW * 32) {
+      const int sel = out[j];
+      cen[3 * j] = s_xyz[3 * sel];
+      cen[3 * j + 1] = s_xyz[3 * sel + 1];
+      cen[3 * j + 2] = s_xyz[3 * sel + 2];
+    }
+  }
+}
+
 // Any-N fallback: min-distance array in a global workspace (L2-resident), xyz re-read from
 // global memory every iteration.  Same selection rule, same two-stage arg-max.
 template <int THREADS>
@@ -376,6 +556,61 @@ static int dispatch_fps_w4(int p, const float* xyz, int B, int N, int M, int32_t
   }
 }
 
+// ---- v2 dispatch ---------------------------------------------------------------------------
+struct FpsBlkConfig {
+  int nw, p2, s2;
+};
+
+template <int NW, int P2, int S2>
+static int launch_fps_blk(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
+                          cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(N) * 3 * sizeof(float);
+  auto kern = fps_blk_kernel<NW, P2, S2>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  kern<<<B, NW * 32, smem, st>>>(xyz, N, M, idx, centers);
+  count_launch();
+  return launch_status();
+}
+
+static int dispatch_fps_blk(FpsBlkConfig c, const float* xyz, int B, int N, int M, int32_t* idx,
+                            float* centers, cudaStream_t st) {
+#define UPP_BLK(NW_, P2_, S2_) \
+  if (c.nw == NW_ && c.p2 == P2_ && c.s2 == S2_) return launch_fps_blk<NW_, P2_, S2_>(xyz, B, N, M, idx, centers, st);
+#define UPP_BLK_ROW(NW_, S2_) \
+  UPP_BLK(NW_, 1, S2_) UPP_BLK(NW_, 2, S2_) UPP_BLK(NW_, 3, S2_) UPP_BLK(NW_, 4, S2_) \
+  UPP_BLK(NW_, 5, S2_) UPP_BLK(NW_, 6, S2_) UPP_BLK(NW_, 7, S2_) UPP_BLK(NW_, 8, S2_)
+  UPP_BLK_ROW(1, 0) UPP_BLK_ROW(2, 0) UPP_BLK_ROW(4, 0) UPP_BLK_ROW(4, 1) UPP_BLK_ROW(8, 0) UPP_BLK_ROW(8, 1)
+  UPP_BLK_ROW(16, 0) UPP_BLK_ROW(16, 1)
+  UPP_BLK(32, 1, 1) UPP_BLK(32, 2, 1) UPP_BLK(32, 3, 1) UPP_BLK(32, 4, 1)
+#undef UPP_BLK_ROW
+#undef UPP_BLK
+  return UPP_ERR_UNSUPPORTED;
+}
+
+static bool fps_blk_valid(FpsBlkConfig c, int N) {
+  const bool nw_ok = c.nw == 1 || c.nw == 2 || c.nw == 4 || c.nw == 8 || c.nw == 16 || c.nw == 32;
+  if (!nw_ok || c.p2 < 1 || c.p2 > (c.nw == 32 ? 4 : 8)) return false;
+  if (c.s2 != 0 && c.s2 != 1) return false;
+  if (c.nw <= 2 && c.s2 != 0) return false;
+  if (c.nw == 32 && c.s2 != 1) return false;
+  return static_cast<long>(c.nw) * 64 * c.p2 >= N;
+}
+
+// Warps x point-pairs per thread for a cloud of N points (N <= kFpsMaxRegPoints); B200 sweep
+// (scripts/time_ops.py --sweep-fps2): see DESIGN.md "FPS" for the table this encodes.
+FpsBlkConfig fps_pick_blk(int N, int B) {
+  int nw;
+  if (N <= 256) nw = 1;                               // one warp: no barrier, no shared-memory round trip
+  else if (B >= 2 * 148 && N <= 1024) nw = 2;         // several clouds per SM: fewer, fatter warps
+  else nw = 4;                                        // one warp per SM sub-partition
+  const int p2 = (N + nw * 64 - 1) / (nw * 64);
+  return {nw, p2, 0};
+}
+
 #define UPP_FPS_CASE_P(T, PP) \
   case PP: return launch_fps_reg<T, PP>(xyz, B, N, M, idx, centers, st);
 #define UPP_FPS_CASE_T(T) \
@@ -383,7 +618,19 @@ static int dispatch_fps_w4(int p, const float* xyz, int B, int N, int M, int32_t
 
 int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (N <= kFpsMaxRegPoints) {
+  if (N <= kFpsMaxRegPoints && env_int("UPP_FPS_IMPL", 2) != 1) {
+    // v2 where the B200 sweep says it wins (N <= 2048: 0.16 vs 0.20 us per round at N = 1228); larger
+    // clouds are ALU-pipe bound and stay on the 512-thread v1 kernel below.
+    FpsBlkConfig c = fps_pick_blk(N, B);
+    const FpsBlkConfig forced = {env_int("UPP_FPS_NW", 0), env_int("UPP_FPS_P2", 0), env_int("UPP_FPS_S2", 0)};
+    const bool use_forced = forced.nw > 0 && forced.p2 > 0 && fps_blk_valid(forced, N);  // tuning aid
+    if (use_forced) c = forced;
+    if (use_forced || N <= 2048) {
+      if (!fps_blk_valid(c, N)) return UPP_ERR_UNSUPPORTED;
+      return dispatch_fps_blk(c, xyz, B, N, M, idx, centers, st);
+    }
+  }
+  if (N <= kFpsMaxRegPoints) {  // v1 kernels (UPP_FPS_IMPL=1): kept for A/B timing and parity tests
     // 4-warp variant: measured better for 1280 < N <= 2048 at any batch, and for every N <= 2048 once
     // the batch is large enough that several clouds share an SM (B=512, N=1024: 108 vs 143 us).
     const int w4 = env_int("UPP_FPS_W4", -1);  // tuning aid: 1 force, 0 forbid

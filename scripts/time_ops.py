@@ -13,7 +13,7 @@ import upp_b200  # noqa: E402
 from upp_b200 import ops  # noqa: E402
 
 
-def timeit(fn, iters=20, warm=5, flush=None):
+def timeit(fn, iters=20, warm=5, flush=None, reps=4):
     """Kernel-only time: the op is captured into a CUDA graph and replayed (no Python / launch gaps)."""
     for _ in range(3):
         fn()
@@ -31,10 +31,11 @@ def timeit(fn, iters=20, warm=5, flush=None):
             flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        fn()
+        for _ in range(reps):  # CUDA-event resolution on this part is ~2 us: average a few replays
+            fn()
         e.record()
         torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e) * 1e3)
+        ts.append(s.elapsed_time(e) * 1e3 / reps)
     ts.sort()
     return ts[len(ts) // 2], ts[0]
 
@@ -44,6 +45,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--sweep-fps", action="store_true")
     ap.add_argument("--sweep-chamfer", action="store_true")
+    ap.add_argument("--sweep-fps2", action="store_true", help="v2 FPS kernel: warps x point-pairs x stage-2 variant")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -60,6 +62,29 @@ def main():
         rows.append(r)
         print(json.dumps(r), flush=True)
 
+    if args.sweep_fps2:
+        shapes = [(32, 1228, 1024), (32, 1024, 256), (32, 1024, 64), (32, 1096, 32), (32, 972, 32), (32, 64, 32), (32, 32, 32),
+                  (128, 8192, 1024), (128, 1024, 64), (32, 2048, 128), (32, 1843, 1536), (32, 1536, 128), (1, 6144, 1024),
+                  (1, 2048, 1024), (512, 1024, 256), (32, 256, 256), (32, 128, 128), (32, 512, 256), (32, 4096, 512), (16, 8192, 1024)]
+        for (B, N, M) in shapes:
+            x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+            os.environ["UPP_FPS_IMPL"] = "1"
+            want = ops.fps(x, M)
+            rec(f"fps2-sweep B{B} N{N} M{M} v1", lambda: ops.fps(x, M), lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
+            os.environ.pop("UPP_FPS_IMPL")
+            rec(f"fps2-sweep B{B} N{N} M{M} v2-default", lambda: ops.fps(x, M), lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
+            for nw in (1, 2, 4, 8, 16, 32):
+                p2 = (N + nw * 64 - 1) // (nw * 64)
+                if p2 > (4 if nw == 32 else 8):
+                    continue
+                for s2 in ((0,) if nw <= 2 else (1,) if nw == 32 else (0, 1)):
+                    os.environ["UPP_FPS_NW"], os.environ["UPP_FPS_P2"], os.environ["UPP_FPS_S2"] = str(nw), str(p2), str(s2)
+                    ok = bool(torch.equal(ops.fps(x, M), want))
+                    rec(f"fps2-sweep B{B} N{N} M{M} nw{nw} p2={p2} s2={s2}", lambda: ops.fps(x, M),
+                        lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
+            for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_S2"):
+                os.environ.pop(k, None)
+        return
     if args.sweep_chamfer:
         for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 1024, 1024), (32, 256, 256), (8, 2048, 2048)]:
             a = torch.rand(B, N, 3, generator=g).to(dev)

@@ -39,14 +39,27 @@ FPS_SHAPES = [  # (B, N, M)  -- SURVEY.md Appendix A census + edges
 ]
 
 
-@pytest.fixture(params=["default", "w4", "no_w4"])
+FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
+    "default": {},                                                        # v2, heuristic warps x pairs
+    "v2_nw1": {"UPP_FPS_NW": "1", "UPP_FPS_P2": "8"},                     # single warp, no barrier (N <= 512)
+    "v2_nw2": {"UPP_FPS_NW": "2", "UPP_FPS_P2": "8"},                     # (N <= 1024)
+    "v2_nw4_redux": {"UPP_FPS_NW": "4", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1"},
+    "v2_nw8_redux": {"UPP_FPS_NW": "8", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1"},
+    "v2_nw8_scan": {"UPP_FPS_NW": "8", "UPP_FPS_P2": "7", "UPP_FPS_S2": "0"},
+    "v2_nw16_scan": {"UPP_FPS_NW": "16", "UPP_FPS_P2": "8", "UPP_FPS_S2": "0"},
+    "v2_nw16_redux": {"UPP_FPS_NW": "16", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1"},
+    "v2_nw32": {"UPP_FPS_NW": "32", "UPP_FPS_P2": "4", "UPP_FPS_S2": "1"},
+    "v1": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "0"},                       # round-1a strided kernels
+    "v1_w4": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "1"},
+}
+
+
+@pytest.fixture(params=sorted(FPS_KERNELS))
 def fps_kernel(request, monkeypatch):
-    """Every register-resident FPS kernel family must agree with the oracle: the heuristic's choice, the
-    4-warp variant forced on, and forced off (UPP_FPS_W4 is a tuning switch read per launch)."""
-    if request.param == "w4":
-        monkeypatch.setenv("UPP_FPS_W4", "1")
-    elif request.param == "no_w4":
-        monkeypatch.setenv("UPP_FPS_W4", "0")
+    """Every register-resident FPS kernel family must agree with the oracle.  A forced v2 shape that
+    cannot hold the cloud (warps x 64 x pairs < N) falls back to the heuristic's choice."""
+    for k, v in FPS_KERNELS[request.param].items():
+        monkeypatch.setenv(k, v)
     return request.param
 
 
