@@ -118,19 +118,19 @@ __global__ void __launch_bounds__(THREADS)
   }
 }
 
-// Predicated (branch-free) RED.MIN.U64 of the key (bits << 32 | code), issued only by lanes whose
-// value equals the warp minimum.
+// Predicated RED.MIN.U64 of the key (bits << 32 | code), issued only by lanes whose value equals the
+// warp minimum.  The key is assembled outside the predicate so that ptxas keeps a single predicated
+// REDG instead of a divergent branch (BSSY / BRA / BSYNC) around it.
 __device__ __forceinline__ void red_min_key_if_equal(unsigned long long* addr, unsigned mine,
                                                      unsigned warp_min, unsigned code) {
+  const unsigned long long key = (static_cast<unsigned long long>(warp_min) << 32) | code;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      ".reg .b64 key;\n\t"
       "setp.eq.u32 p, %1, %2;\n\t"
-      "mov.b64 key, {%3, %2};\n\t"
-      "@p red.global.min.u64 [%0], key;\n\t"
+      "@p red.global.min.u64 [%0], %3;\n\t"
       "}" ::"l"(addr),
-      "r"(mine), "r"(warp_min), "r"(code)
+      "r"(mine), "r"(warp_min), "l"(key)
       : "memory");
 }
 
@@ -266,6 +266,187 @@ __global__ void __launch_bounds__(WC * 32)
     distA[static_cast<size_t>(b) * NA + j] = bb;
     idxA[static_cast<size_t>(b) * NA + j] = bi;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass forward, packed: the same algorithm as chamfer_fwd_both_kernel with the two changes the
+// B200 measurements asked for (scripts/microbench2.cu, profiles/r01b_chamfer_both_R8W8.txt):
+//   * PACKED fp32x2 distances: a thread's R rows sit in R/2 register pairs; one FADD2/FMUL2/FFMA2
+//     evaluates a column against two rows -- 6 issue slots per 2 pairs instead of 12, bit-identical
+//     results -- which frees the issue port for the FMNMX bookkeeping (the FMA pipe needs 2 cycles
+//     per packed instruction): the loop is FMA-pipe bound at 6 cycles per pair instead of
+//     issue bound at ~8.25.
+//   * COLUMN CHUNKS (blockIdx.z): a work item is (cloud, 32*R rows, one chunk of columns), so the
+//     grid can be cut to a whole number of SM-waves (the R8W8 profile ran 1.15 waves).  With more
+//     than one chunk the row side also merges through RED.MIN.U64 keys (distance bits << 32 | column
+//     group) and chamfer_finalize_kernel resolves both sides; with one chunk rows are written directly.
+template <int R, int WC>
+__global__ void __launch_bounds__(WC * 32)
+    chamfer_fwd_packed_kernel(const float* __restrict__ xyzA, const float* __restrict__ xyzB, int NA,
+                              int NB, int NA8, int NB8, int chunk, float* __restrict__ distA,
+                              int32_t* __restrict__ idxA, unsigned long long* __restrict__ rowbest,
+                              unsigned long long* __restrict__ colbest) {
+  static_assert(R % 2 == 0, "rows are processed in packed pairs");
+  constexpr int ROWS = 32 * R;
+  constexpr int THREADS = WC * 32;
+  constexpr int RP = R / 2;
+  static_assert(WC * ROWS * 8 <= kChTile * 12, "row-combine scratch must fit in the tile buffer");
+  __shared__ __align__(16) float s_ref[kChTile * 3];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);  // warp-uniform for the compiler
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.z * chunk;
+  const int c1 = min(NB, c0 + chunk);
+  const float* ap = xyzA + static_cast<size_t>(b) * NA * 3;
+  const float* bp = xyzB + static_cast<size_t>(b) * NB * 3;
+  unsigned long long* cb = colbest + static_cast<size_t>(b) * NB8;
+  const int row0 = blockIdx.x * ROWS + lane * R;
+  const unsigned code = static_cast<unsigned>(blockIdx.x * 32 + lane);  // row block id = row0 / R
+
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned parity = 0;
+
+  f32x2 QX[RP], QY[RP], QZ[RP];
+  float best[R];
+  int bg[R];
+#pragma unroll
+  for (int rp = 0; rp < RP; ++rp) {
+    float c[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = row0 + 2 * rp + h;
+      const bool ok = j < NA;  // rows past the end are NaN: they never win a min
+#pragma unroll
+      for (int a = 0; a < 3; ++a) c[h][a] = ok ? __ldg(ap + 3 * j + a) : __int_as_float(0x7fc00000);
+    }
+    QX[rp] = pack2(c[0][0], c[1][0]);
+    QY[rp] = pack2(c[0][1], c[1][1]);
+    QZ[rp] = pack2(c[0][2], c[1][2]);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    best[r] = __int_as_float(0x7f800000);
+    bg[r] = 0;
+  }
+
+  for (int base = c0; base < c1; base += kChTile) {
+    const int tile = min(kChTile, c1 - base);
+    const int tile8 = (tile + 7) & ~7;
+    if (base > c0) __syncthreads();
+    // pad the last group of eight with NaN: (q - NaN)^2 = NaN, and fminf() drops NaN operands
+    for (int i = tile * 3 + t; i < tile8 * 3; i += THREADS) s_ref[i] = __int_as_float(0x7fc00000);
+    stage_points(s_ref, bp + static_cast<size_t>(base) * 3, tile, &s_bar, parity);
+
+    const int ngroups = tile8 >> 3;
+    for (int g = warp; g < ngroups; g += WC) {
+      const float4* s4 = reinterpret_cast<const float4*>(s_ref) + g * 6;
+      unsigned long long* cbk = cb + base + g * 8;
+      float m[R];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {  // four column pairs per group of 8
+        const float4 v0 = s4[(6 * h) >> 2];
+        const float4 v1 = s4[((6 * h) >> 2) + 1];
+        float ax, ay, az, bx, by, bz;
+        if ((h & 1) == 0) { ax = v0.x; ay = v0.y; az = v0.z; bx = v0.w; by = v1.x; bz = v1.y; }
+        else              { ax = v0.z; ay = v0.w; az = v1.x; bx = v1.y; by = v1.z; bz = v1.w; }
+        // (q - ref): the sign is squared away, and packed-minus-broadcast is one FADD2
+        const f32x2 AX = pack2(ax, ax), AY = pack2(ay, ay), AZ = pack2(az, az);
+        const f32x2 BX = pack2(bx, bx), BY = pack2(by, by), BZ = pack2(bz, bz);
+        float ca = 0.f, cbm = 0.f;
+#pragma unroll
+        for (int rp = 0; rp < RP; ++rp) {
+          float a0, a1, b0, b1;
+          unpack2(dist2_yxz(sub2(QX[rp], AX), sub2(QY[rp], AY), sub2(QZ[rp], AZ)), a0, a1);
+          unpack2(dist2_yxz(sub2(QX[rp], BX), sub2(QY[rp], BY), sub2(QZ[rp], BZ)), b0, b1);
+          m[2 * rp] = h == 0 ? fminf(a0, b0) : fminf(fminf(m[2 * rp], a0), b0);
+          m[2 * rp + 1] = h == 0 ? fminf(a1, b1) : fminf(fminf(m[2 * rp + 1], a1), b1);
+          ca = rp == 0 ? fminf(a0, a1) : fminf(fminf(ca, a0), a1);
+          cbm = rp == 0 ? fminf(b0, b1) : fminf(fminf(cbm, b0), b1);
+        }
+        const unsigned ua = __float_as_uint(ca), ub = __float_as_uint(cbm);
+        const unsigned wa = redux_min_u32(ua), wb = redux_min_u32(ub);
+        red_min_key_if_equal(cbk + 2 * h, ua, wa, code);
+        red_min_key_if_equal(cbk + 2 * h + 1, ub, wb, code);
+      }
+      const int kk = base + g * 8;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (m[r] < best[r]) { best[r] = m[r]; bg[r] = kk; }
+    }
+  }
+
+  // ---- row side: combine the WC partials per row, then either resolve + write, or merge by key ----
+  __syncthreads();  // every warp is done reading the tile
+  float* s_best = s_ref;
+  int* s_bg = reinterpret_cast<int*>(s_ref + WC * ROWS);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    s_best[warp * ROWS + lane * R + r] = best[r];
+    s_bg[warp * ROWS + lane * R + r] = bg[r];
+  }
+  __syncthreads();
+  for (int rho = t; rho < ROWS; rho += THREADS) {
+    const int j = blockIdx.x * ROWS + rho;
+    if (j >= NA) continue;
+    float bb = __int_as_float(0x7f800000);
+    int gg = 0;
+#pragma unroll
+    for (int w = 0; w < WC; ++w) {
+      const float v = s_best[w * ROWS + rho];
+      const int g = s_bg[w * ROWS + rho];
+      if (v < bb || (v == bb && g < gg)) { bb = v; gg = g; }
+    }
+    if (rowbest != nullptr) {  // several column chunks: smallest distance, then lowest column group
+      const unsigned long long key =
+          (static_cast<unsigned long long>(__float_as_uint(bb)) << 32) | static_cast<unsigned>(gg);
+      atomicMin(rowbest + static_cast<size_t>(b) * NA8 + j, key);
+      continue;
+    }
+    const float px = __ldg(ap + 3 * j), py = __ldg(ap + 3 * j + 1), pz = __ldg(ap + 3 * j + 2);
+    int bi = gg;
+#pragma unroll
+    for (int u = 7; u >= 0; --u) {  // 8 independent (clamped) loads in flight, lowest match wins
+      const int kcol = min(gg + u, NB - 1);
+      const float* p = bp + static_cast<size_t>(kcol) * 3;
+      const float d = dist_yxz(__ldg(p) - px, __ldg(p + 1) - py, __ldg(p + 2) - pz);
+      if (d == bb && gg + u < NB) bi = gg + u;
+    }
+    distA[static_cast<size_t>(b) * NA + j] = bb;
+    idxA[static_cast<size_t>(b) * NA + j] = bi;
+  }
+}
+
+// Second half of the key merge: turn each packed key (distance bits << 32 | code) of cloud `self`
+// into (distance, lowest matching index in `other`) by recomputing the `cnt` (<= 8) distances of the
+// winning span other[code * mult .. + cnt).  One thread per point, all loads independent.
+__global__ void __launch_bounds__(256)
+    chamfer_finalize_kernel(const float* __restrict__ self, const float* __restrict__ other, int n_self,
+                            int n_other, int n_self8, const unsigned long long* __restrict__ keys,
+                            int mult, int cnt, float* __restrict__ dist_out, int32_t* __restrict__ idx_out) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_self) return;
+  const float* op = other + static_cast<size_t>(b) * n_other * 3;
+  const float* sp = self + (static_cast<size_t>(b) * n_self + k) * 3;
+  const unsigned long long key = keys[static_cast<size_t>(b) * n_self8 + k];
+  const unsigned bits = static_cast<unsigned>(key >> 32);
+  const int j0 = static_cast<int>(static_cast<unsigned>(key)) * mult;
+  const float rx = __ldg(sp), ry = __ldg(sp + 1), rz = __ldg(sp + 2);
+  int bi = j0;
+#pragma unroll
+  for (int u = 7; u >= 0; --u) {
+    const int j = min(j0 + u, n_other - 1);
+    const float* p = op + static_cast<size_t>(j) * 3;
+    const float d = dist_yxz(rx - __ldg(p), ry - __ldg(p + 1), rz - __ldg(p + 2));
+    if (u < cnt && __float_as_uint(d) == bits && j0 + u < n_other) bi = j0 + u;
+  }
+  dist_out[static_cast<size_t>(b) * n_self + k] = __uint_as_float(bits);
+  idx_out[static_cast<size_t>(b) * n_self + k] = bi;
 }
 
 // Column side, second half: turn each packed key into (distance, lowest matching row index) by
@@ -417,8 +598,59 @@ static void launch_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int 
 
 size_t chamfer_fwd_workspace_bytes(int B, int N, int M) {
   if (B <= 0 || N <= 0 || M <= 0) return 0;
-  const size_t nb8 = (static_cast<size_t>(min(N, M)) + 7) & ~static_cast<size_t>(7);
-  return static_cast<size_t>(B) * nb8 * 8;
+  // one 64-bit key per point of either cloud (the column side always merges by key, the row side
+  // when the columns are cut into chunks)
+  const size_t n8 = (static_cast<size_t>(N) + 7) & ~static_cast<size_t>(7);
+  const size_t m8 = (static_cast<size_t>(M) + 7) & ~static_cast<size_t>(7);
+  return static_cast<size_t>(B) * (n8 + m8) * 8;
+}
+
+// Column chunks for the packed kernel: cut B * rowblocks work items so that they fill a whole number
+// of rounds over the 148 SMs (every resident CTA of an SM shares its issue bandwidth, so the make-span
+// is ceil(items / 148) item-times).  Fewest chunks within 3 % of the best fill; chunks stay >= 512
+// columns (below that the per-item prologue / epilogue shows: measured) and a multiple of 64.
+static int chamfer_pick_chunks(long items0, int NB) {
+  const int max_chunks = NB >= 1024 ? (NB / 512 < 32 ? NB / 512 : 32) : 1;
+  double best_eff = 0.0;
+  for (int c = 1; c <= max_chunks; ++c) {
+    const long items = items0 * c;
+    const double eff = static_cast<double>(items) / (148.0 * ((items + 147) / 148));
+    if (eff > best_eff) best_eff = eff;
+  }
+  for (int c = 1; c <= max_chunks; ++c) {
+    const long items = items0 * c;
+    const double eff = static_cast<double>(items) / (148.0 * ((items + 147) / 148));
+    if (eff >= best_eff - 0.03) return c;
+  }
+  return 1;
+}
+
+template <int R, int WC>
+static int launch_chamfer_packed(const float* a, const float* bpts, int B, int NA, int NB, float* dA,
+                                 int32_t* iA, float* dB, int32_t* iB, void* ws, int force_chunks,
+                                 cudaStream_t st) {
+  const int na8 = (NA + 7) & ~7, nb8 = (NB + 7) & ~7;
+  const int rowblocks = (NA + 32 * R - 1) / (32 * R);
+  int chunks = force_chunks > 0 ? force_chunks : chamfer_pick_chunks(static_cast<long>(B) * rowblocks, NB);
+  int chunk = ((NB + chunks - 1) / chunks + 63) & ~63;
+  chunks = (NB + chunk - 1) / chunk;
+  unsigned long long* colkeys = static_cast<unsigned long long*>(ws);
+  unsigned long long* rowkeys = chunks > 1 ? colkeys + static_cast<size_t>(B) * nb8 : nullptr;
+  const size_t keys = static_cast<size_t>(B) * (nb8 + (chunks > 1 ? na8 : 0)) * 8;
+  cudaError_t e = cudaMemsetAsync(ws, 0xFF, keys, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  dim3 grid(rowblocks, B, chunks);
+  chamfer_fwd_packed_kernel<R, WC><<<grid, WC * 32, 0, st>>>(a, bpts, NA, NB, na8, nb8, chunk, dA, iA, rowkeys, colkeys);
+  count_launch();
+  int rc = launch_status();
+  if (rc != UPP_OK) return rc;
+  chamfer_finalize_kernel<<<dim3((NB + 255) / 256, B), 256, 0, st>>>(bpts, a, NB, NA, nb8, colkeys, R, R, dB, iB);
+  count_launch();
+  if (chunks > 1) {
+    chamfer_finalize_kernel<<<dim3((NA + 255) / 256, B), 256, 0, st>>>(a, bpts, NA, NB, na8, rowkeys, 1, 8, dA, iA);
+    count_launch();
+  }
+  return launch_status();
 }
 
 template <int R, int WC>
@@ -439,6 +671,11 @@ static int launch_chamfer_both(const float* a, const float* bpts, int B, int NA,
   return UPP_OK;
 }
 
+static int env_chunks() {
+  const char* v = getenv("UPP_CH_CHUNKS");  // tuning aid: force the number of column chunks
+  return v ? atoi(v) : 0;
+}
+
 int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                        float* dist2, int32_t* idx1, int32_t* idx2, float* sums, void* workspace,
                        size_t workspace_bytes, cudaStream_t st) {
@@ -457,13 +694,19 @@ int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M
     int32_t* iA = swap ? idx2 : idx1; int32_t* iB = swap ? idx1 : idx2;
     const long ctas8 = static_cast<long>(B) * ((na + 255) / 256);
     int rc;
-    int pick = variant >= 20 ? variant : (ctas8 >= 2 * 148 ? 20 : 21);
+    // default: the packed kernel; 20..22 = the scalar single-pass kernel (A/B timing)
+    int pick = variant >= 20 ? variant : 30;
+    const int fc = env_chunks();
+    (void)ctas8;
     switch (pick) {
+      case 20: rc = launch_chamfer_both<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
       case 21: rc = launch_chamfer_both<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
       case 22: rc = launch_chamfer_both<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
-      case 23: rc = launch_chamfer_both<4, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
-      case 24: rc = launch_chamfer_both<2, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
-      default: rc = launch_chamfer_both<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
+      case 31: rc = launch_chamfer_packed<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, st); break;
+      case 32: rc = launch_chamfer_packed<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, st); break;
+      case 33: rc = launch_chamfer_packed<6, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, st); break;
+      // measured best on B200: 8 rows per thread, 4 warps per CTA (5 CTAs / SM)
+      default: rc = launch_chamfer_packed<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, st); break;
     }
     if (rc != UPP_OK) return rc;
   } else {

@@ -223,6 +223,72 @@ __global__ void __launch_bounds__(128, 1)
   }
 }
 
+// One span [R0, R1) of a thread's point pairs: distances to the new centre, running-min update,
+// span maximum (order-preserving float bits) and the lowest slot holding it.  TREE: independent
+// compare/selects + a VIMNMX3 tree (short dependent chain) instead of one select chain.
+template <int P2, int R0, int R1, bool TREE>
+__device__ __forceinline__ void fps_span(const f32x2 (&X)[P2], const f32x2 (&Y)[P2], const f32x2 (&Z)[P2],
+                                         float (&md)[2 * P2], f32x2 CX, f32x2 CY, f32x2 CZ, int& best,
+                                         int& ls) {
+  constexpr int NP = R1 - R0, NS = 2 * NP;
+  // all packed distance chains are independent: spelled stage by stage so that they are scheduled
+  // interleaved (one warp per scheduler has nobody else to hide a dependent chain)
+  f32x2 D[NP];
+#pragma unroll
+  for (int r = 0; r < NP; ++r) D[r] = sub2(Y[R0 + r], CY);
+#pragma unroll
+  for (int r = 0; r < NP; ++r) D[r] = mul2(D[r], D[r]);
+#pragma unroll
+  for (int r = 0; r < NP; ++r) { const f32x2 dx = sub2(X[R0 + r], CX); D[r] = fma2(dx, dx, D[r]); }
+#pragma unroll
+  for (int r = 0; r < NP; ++r) { const f32x2 dz = sub2(Z[R0 + r], CZ); D[r] = fma2(dz, dz, D[r]); }
+  int key[NS];
+#pragma unroll
+  for (int r = 0; r < NP; ++r) {
+    float d0, d1;
+    unpack2(D[r], d0, d1);
+    md[2 * (R0 + r)] = fminf(md[2 * (R0 + r)], d0);
+    md[2 * (R0 + r) + 1] = fminf(md[2 * (R0 + r) + 1], d1);
+    key[2 * r] = __float_as_int(md[2 * (R0 + r)]);
+    key[2 * r + 1] = __float_as_int(md[2 * (R0 + r) + 1]);
+  }
+  int red[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) red[s] = key[s];
+#pragma unroll
+  for (int n = NS; n > 1; n = (n + 2) / 3) {  // balanced VIMNMX3 tree
+#pragma unroll
+    for (int q = 0; q < (n + 2) / 3; ++q) {
+      int v = red[3 * q];
+      if (3 * q + 1 < n) v = max(v, red[3 * q + 1]);
+      if (3 * q + 2 < n) v = max(v, red[3 * q + 2]);
+      red[q] = v;
+    }
+  }
+  best = red[0];
+  if constexpr (TREE) {
+    int cnd[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) cnd[s] = key[s] == best ? 2 * R0 + s : 2 * P2;
+#pragma unroll
+    for (int n = NS; n > 1; n = (n + 2) / 3) {
+#pragma unroll
+      for (int q = 0; q < (n + 2) / 3; ++q) {
+        int v = cnd[3 * q];
+        if (3 * q + 1 < n) v = min(v, cnd[3 * q + 1]);
+        if (3 * q + 2 < n) v = min(v, cnd[3 * q + 2]);
+        cnd[q] = v;
+      }
+    }
+    ls = cnd[0];
+  } else {
+    ls = 2 * R0 + NS - 1;
+#pragma unroll
+    for (int s = NS - 2; s >= 0; --s)
+      if (key[s] == best) ls = 2 * R0 + s;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // v2 (fps_blk_kernel): the same register-resident scheme re-cut around what the B200 measurements
 // say binds one round (scripts/microbench2.cu): issue slots and the dependent REDUX/BAR/LDS chain.
@@ -296,67 +362,12 @@ __global__ void __launch_bounds__(NW * 32)
   const unsigned lanes_below = (1u << lane) - 1u;
   for (int j = 1; j < M; ++j) {
     const f32x2 CX = pack2(cx, cx), CY = pack2(cy, cy), CZ = pack2(cz, cz);
-    // all P2 packed distance chains are independent: spelled stage by stage so that they are
-    // scheduled interleaved (one warp per scheduler has nobody else to hide a dependent chain)
-    f32x2 D[P2];
-#pragma unroll
-    for (int r = 0; r < P2; ++r) D[r] = sub2(Y[r], CY);
-#pragma unroll
-    for (int r = 0; r < P2; ++r) D[r] = mul2(D[r], D[r]);
-#pragma unroll
-    for (int r = 0; r < P2; ++r) { const f32x2 dx = sub2(X[r], CX); D[r] = fma2(dx, dx, D[r]); }
-#pragma unroll
-    for (int r = 0; r < P2; ++r) { const f32x2 dz = sub2(Z[r], CZ); D[r] = fma2(dz, dz, D[r]); }
-    int key[P];
-#pragma unroll
-    for (int r = 0; r < P2; ++r) {
-      float d0, d1;
-      unpack2(D[r], d0, d1);
-      md[2 * r] = fminf(md[2 * r], d0);
-      md[2 * r + 1] = fminf(md[2 * r + 1], d1);
-      key[2 * r] = __float_as_int(md[2 * r]);
-      key[2 * r + 1] = __float_as_int(md[2 * r + 1]);
-    }
-    int red[P];
-#pragma unroll
-    for (int s = 0; s < P; ++s) red[s] = key[s];
-#pragma unroll
-    for (int n = P; n > 1; n = (n + 2) / 3) {  // balanced VIMNMX3 tree
-#pragma unroll
-      for (int q = 0; q < (n + 2) / 3; ++q) {
-        int v = red[3 * q];
-        if (3 * q + 1 < n) v = max(v, red[3 * q + 1]);
-        if (3 * q + 2 < n) v = max(v, red[3 * q + 2]);
-        red[q] = v;
-      }
-    }
-    const int best = red[0];
+    // The in-thread slot search needs only the thread's own maximum, so it runs in the shadow of the
+    // REDUX.  (Splitting the pairs into two spans so that the first span's search issues under the
+    // second span's FMA work was measured: no gain -- one warp per scheduler is latency-, not pipe-bound.)
+    int best, ls;
+    fps_span<P2, 0, P2, (NW <= 4)>(X, Y, Z, md, CX, CY, CZ, best, ls);
     const int wbest = redux_max_s32(best);
-    // lowest own slot holding the thread's maximum: needs only `best`, so it runs in the shadow of
-    // the REDUX.  Few warps: independent compare/selects + a VIMNMX3 tree (short chain); many
-    // warps: one select chain (fewest issue slots, other warps hide its latency).
-    int ls;
-    if constexpr (NW <= 4) {
-      int cnd[P];
-#pragma unroll
-      for (int s = 0; s < P; ++s) cnd[s] = key[s] == best ? s : P;
-#pragma unroll
-      for (int n = P; n > 1; n = (n + 2) / 3) {
-#pragma unroll
-        for (int q = 0; q < (n + 2) / 3; ++q) {
-          int v = cnd[3 * q];
-          if (3 * q + 1 < n) v = min(v, cnd[3 * q + 1]);
-          if (3 * q + 2 < n) v = min(v, cnd[3 * q + 2]);
-          cnd[q] = v;
-        }
-      }
-      ls = cnd[0];
-    } else {
-      ls = P - 1;
-#pragma unroll
-      for (int s = P - 2; s >= 0; --s)
-        if (key[s] == best) ls = s;
-    }
     const unsigned winners = __ballot_sync(0xffffffffu, best == wbest);
     int sel;
     if constexpr (NW == 1) {

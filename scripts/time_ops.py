@@ -63,9 +63,11 @@ def main():
         print(json.dumps(r), flush=True)
 
     if args.sweep_fps2:
-        shapes = [(32, 1228, 1024), (32, 1024, 256), (32, 1024, 64), (32, 1096, 32), (32, 972, 32), (32, 64, 32), (32, 32, 32),
-                  (128, 8192, 1024), (128, 1024, 64), (32, 2048, 128), (32, 1843, 1536), (32, 1536, 128), (1, 6144, 1024),
-                  (1, 2048, 1024), (512, 1024, 256), (32, 256, 256), (32, 128, 128), (32, 512, 256), (32, 4096, 512), (16, 8192, 1024)]
+        shapes = [(32, 1228, 1024), (32, 1024, 256), (32, 64, 512), (32, 32, 512), (128, 1024, 512), (32, 2048, 512), (32, 1843, 1536),
+                  (32, 1536, 512), (1, 2048, 1024), (512, 1024, 256), (32, 256, 256), (32, 128, 256), (32, 512, 256), (32, 384, 256)]
+        if args.only == "big":
+            shapes = [(128, 8192, 1024), (1, 6144, 1024), (32, 4096, 512), (16, 8192, 1024)]
+            args.only = ""
         for (B, N, M) in shapes:
             x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
             os.environ["UPP_FPS_IMPL"] = "1"
@@ -89,11 +91,14 @@ def main():
         for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 1024, 1024), (32, 256, 256), (8, 2048, 2048)]:
             a = torch.rand(B, N, 3, generator=g).to(dev)
             b = torch.rand(B, M, 3, generator=g).to(dev)
-            for v, name in [(0, "2pass R2T128"), (6, "2pass R2T256"), (8, "2pass R1T128"), (9, "2pass R1T256"), (20, "1pass R8W8"),
-                            (21, "1pass R4W8"), (22, "1pass R8W4"), (23, "1pass R4W4"), (-1, "default")]:
+            for v, ch, name in [(0, 0, "2pass R2T128"), (20, 0, "1pass scalar R8W8"), (30, 1, "packed R8W4 1 chunk"), (30, 0, "packed R8W4 auto"),
+                                (30, 2, "packed R8W4 2 chunks"), (30, 4, "packed R8W4 4 chunks"),
+                                (31, 0, "packed R4W8 auto"), (33, 0, "packed R6W8 auto"), (32, 0, "packed R8W8 auto(v32)"), (-1, 0, "default")]:
                 os.environ["UPP_CH_VARIANT"] = str(v)
+                os.environ["UPP_CH_CHUNKS"] = str(ch)
                 rec(f"chamfer-sweep {name} B{B} N{N} M{M}", lambda: ops.chamfer_forward(a, b),
-                    lambda us: {"tflops_16NM": round(16.0 * N * M * B / us / 1e6, 2)})
+                    lambda us: {"tflops_8NM": round(8.0 * N * M * B / us / 1e6, 2)})
+            os.environ.pop("UPP_CH_CHUNKS", None)
             os.environ.pop("UPP_CH_VARIANT", None)
         return
     if args.sweep_fps:

@@ -207,12 +207,24 @@ CH_SHAPES = [  # (B, N, M)
 ]
 
 
-@pytest.fixture(params=["single_pass", "two_pass"])
+CH_KERNELS = {  # name -> tuning environment (read per launch by chamfer_fwd_launch)
+    "packed": {},                                                   # default: packed single pass, heuristic chunks
+    "packed_1chunk": {"UPP_CH_CHUNKS": "1"},                        # rows written directly
+    "packed_3chunks": {"UPP_CH_CHUNKS": "3"},                       # row side merged by key too
+    "packed_many_chunks": {"UPP_CH_CHUNKS": "32"},
+    "packed_r4": {"UPP_CH_VARIANT": "31", "UPP_CH_CHUNKS": "2"},
+    "packed_r6": {"UPP_CH_VARIANT": "33"},
+    "packed_w8": {"UPP_CH_VARIANT": "32"},
+    "scalar_single_pass": {"UPP_CH_VARIANT": "20"},                 # round-1b kernel
+    "two_pass": {"UPP_CH_VARIANT": "0"},                            # directed kernel (no workspace needed)
+}
+
+
+@pytest.fixture(params=sorted(CH_KERNELS))
 def chamfer_path(request, monkeypatch):
-    """Both forward kernels must give identical results: the single-pass kernel (default when the
-    binding passes a workspace) and the directed two-pass kernel (UPP_CH_VARIANT=0 forces it)."""
-    if request.param == "two_pass":
-        monkeypatch.setenv("UPP_CH_VARIANT", "0")
+    """Every forward kernel family must give identical (bit-exact) results."""
+    for k, v in CH_KERNELS[request.param].items():
+        monkeypatch.setenv(k, v)
     return request.param
 
 
