@@ -64,7 +64,8 @@ def make_inputs(workload, B, seed):
     if workload == "c4":
         return {"pts": unit_sphere(torch.randn(B, 8192, 3, generator=g) * 0.35).contiguous()}
     if workload == "c5":
-        return {"pts": unit_sphere(torch.randn(B, 2048, 3, generator=g) * 0.35).contiguous()}
+        return {"pts": unit_sphere(torch.randn(B, 2048, 3, generator=g) * 0.35).contiguous(),
+                "feat": torch.randn(B, 128, 1152, generator=g)}  # (B,128,1152) group features to propagate
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -76,7 +77,8 @@ DESCR = {
     "c1": "Point-MAE Group divider FPS 64 + kNN k=32, B=32, N=1024 (BASELINE configs[0])",
     "c3": "Chamfer L1 fwd+bwd B=64, 2048 vs 2048 (BASELINE configs[2])",
     "c4": "ShapeNet55-scale grouping FPS 8192->1024 then Group(64,32), B=128 (BASELINE configs[3])",
-    "c5": "ShapeNetPart Group(128,32) on 2048 points, B=32 (BASELINE configs[4], grouping part)",
+    "c5": "ShapeNetPart Group(128,32) on 2048 points + kNN feature propagation 2048<-128, 3-NN, 1152-d, B=32 "
+          "(BASELINE configs[4], geometry part)",
 }
 
 
@@ -117,7 +119,7 @@ class GpuWorkload:
             cur.wait_stream(st)
 
     def h2d_bytes(self):
-        keys = {"upp_cls_geometry+chamfer": ("pts", "rebuild", "target")}.get(self.name, tuple(self.host))
+        keys = {"upp_cls_geometry+chamfer": ("pts", "rebuild", "target"), "c5": ("pts",)}.get(self.name, tuple(self.host))
         return sum(self.host[k].numel() * 4 for k in keys), keys
 
     # -- ops-level step --
@@ -177,7 +179,9 @@ class GpuWorkload:
             return ce[0, 0, 0]
         if n == "c5":
             nb, ce, _, _ = t("group N2048 G128 k32", o.group, d["pts"], 128, 32)
-            return ce[0, 0, 0]
+            up = t("interp N2048 S128 C1152 k3", o.interp_forward, d["pts"], ce, d["feat"], 3, 1e-4)[0]
+            self.keepalive = (nb, up)
+            return up[0, 0, 0]
         raise SystemExit(n)
 
     # -- module-level step (public API + autograd), used for e2e --
@@ -223,7 +227,8 @@ class GpuWorkload:
             return ce[0, 0, 0]
         if n == "c5":
             nb, ce = self.g128_32(d["pts"])
-            return ce[0, 0, 0]
+            up = U.interpolate_features(d["pts"], ce, d["feat"], 3, eps=1e-4)
+            return up[0, 0, 0]
         raise SystemExit(n)
 
 
@@ -244,6 +249,9 @@ def op_work(label):
     if kind == "chamfer_bwd":
         N, M = v["N"], v["M"]
         return 0.0, 56.0 * (N + M)
+    if kind == "interp":  # HBM: out written once, features + coordinates read once (the k re-reads hit L2)
+        N, S, C, k = v["N"], v["S"], v["C"], v["k"]
+        return 0.0, 4.0 * N * C + 4.0 * S * C + 12.0 * (N + S) + 12.0 * N * k
     if kind == "group_bwd":
         return 0.0, 0.0
     if kind == "gather_grad":
@@ -324,7 +332,8 @@ def cpu_step(workload, host):
         c, _ = T.fps(host["pts"], 1024)
         return float(T.group(c, 64, 32)[1][0, 0, 0])
     if workload == "c5":
-        return float(T.group(host["pts"], 128, 32)[1][0, 0, 0])
+        _, ce = T.group(host["pts"], 128, 32)
+        return float(T.interpolate(host["pts"], ce, host["feat"], 3, 1e-4)[0, 0, 0])
     raise SystemExit(workload)
 
 
@@ -406,16 +415,19 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm: CUDA-graph replay of the ops-level step ----
+    # The step's critical path (the serial FPS chain) is captured on a high-priority stream, the two
+    # independent branches on default-priority side streams: pending CTAs of the chain are placed first.
+    hp = torch.cuda.Stream(device=dev, priority=-1)
     for _ in range(2):
         W.run_ops(W.d)
     torch.cuda.synchronize()
-    graph, use_graph = None, not args.no_graph and world == 1
+    graph, use_graph = None, not args.no_graph  # world > 1: the 16-byte NCCL all-reduce is captured too
     launches_per_step = None
     if use_graph:
         try:
             graph = torch.cuda.CUDAGraph()
             c0 = upp_b200.launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=hp):
                 static_loss = W.run_ops(W.d)
             launches_per_step = upp_b200.launch_count() - c0
         except Exception as ex:  # capture unsupported: fall back to eager launches, and say so
@@ -459,7 +471,7 @@ def main():
         dd[k] = torch.empty_like(W.d[k])
         dd[k].copy_(W.host[k])
     e2e_graph, e2e_loss, e2e_mode = None, None, "eager"
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -469,7 +481,7 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             e2e_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(e2e_graph):
+            with torch.cuda.graph(e2e_graph, stream=hp):
                 e2e_loss = W.run_modules(dd)
             e2e_mode = "cuda_graph_replay"
         except Exception as ex:
@@ -539,8 +551,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dist)
         return
 
     clouds = B * world * args.steps
@@ -583,8 +594,20 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _, _ = time_cpu(args.workload, B, 0, 5, 1)
     print(json.dumps(line), flush=True)
+    _finish(world, dist)
+
+
+def _finish(world, dist):
+    """N > 1: leave without tearing the NCCL communicator down.  The CUDA graphs replayed above hold captured
+    NCCL kernels, and destroy_process_group() behind them was seen to block until torchrun's timeout; every
+    result has been printed and flushed by now, so the ranks rendezvous once and exit."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -24,6 +24,13 @@ int group_gather_launch(const float*, const float*, const int64_t*, int, int, in
 int group_bwd_launch(const float*, const float*, const int64_t*, const int32_t*, int, int, int, int,
                      float*, cudaStream_t);
 
+int knn_points_launch(const float*, const float*, int, int, int, int, float*, int64_t*, float*, cudaStream_t);
+int interp_fwd_launch(const float*, const float*, const float*, const float*, float, float, int, int, int, int,
+                      int, float*, int32_t*, float*, float*, cudaStream_t);
+int interp_bwd_launch(const float*, const int32_t*, const float*, const float*, const float*, const float*,
+                      const float*, float, float, int, int, int, int, int, float*, float*, float*, float*,
+                      cudaStream_t);
+
 }  // namespace upp
 
 using namespace upp;
@@ -151,6 +158,41 @@ int upp_group_bwd_f32(const float* grad_nb, const float* grad_center, const int6
   UPP_REQUIRE(grad_xyz != nullptr);
   UPP_REQUIRE(static_cast<size_t>(B) * G == 0 || (grad_nb && idx && center_idx));
   return group_bwd_launch(grad_nb, grad_center, idx, center_idx, B, N, G, k, grad_xyz, S(stream));
+}
+
+int upp_knn_points_f32(const float* p1, const float* p2, int B, int N1, int N2, int K, float* dist2_out,
+                       int64_t* idx_out, float* nn_out, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N1 >= 0 && N2 >= 0);
+  UPP_REQUIRE(K >= 1 && K <= N2 && K <= 32);
+  if (B == 0 || N1 == 0) return UPP_OK;
+  UPP_REQUIRE(p1 && p2 && idx_out);
+  return knn_points_launch(p1, p2, B, N1, N2, K, dist2_out, idx_out, nn_out, S(stream));
+}
+
+int upp_interp_fwd_f32(const float* xyz1, const float* xyz2, const float* feat2, const float* base, float alpha,
+                       float eps, int B, int N, int S, int C, int k, float* out, int32_t* idx, float* weight,
+                       float* dist, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && S >= 0 && C >= 0);
+  UPP_REQUIRE(k >= 1 && k <= S && k <= 32);
+  if (B == 0 || N == 0) return UPP_OK;
+  UPP_REQUIRE(xyz1 && xyz2 && idx && weight);
+  UPP_REQUIRE(C == 0 || (feat2 && out));
+  return interp_fwd_launch(xyz1, xyz2, feat2, base, alpha, eps, B, N, S, C, k, out, idx, weight, dist,
+                           static_cast<cudaStream_t>(stream));  // (the size S shadows the helper here)
+}
+
+int upp_interp_bwd_f32(const float* grad_out, const int32_t* idx, const float* weight, const float* dist,
+                       const float* feat2, const float* xyz1, const float* xyz2, float alpha, float eps, int B,
+                       int N, int S, int C, int k, float* grad_feat2, float* grad_xyz1, float* grad_xyz2,
+                       float* gd_workspace, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && S >= 0 && C >= 0);
+  UPP_REQUIRE(k >= 1 && k <= 32);
+  if (B == 0 || S == 0) return UPP_OK;
+  UPP_REQUIRE(grad_feat2 != nullptr || C == 0);
+  UPP_REQUIRE(N == 0 || (grad_out && idx && weight));
+  if (gd_workspace) UPP_REQUIRE(N == 0 || (dist && feat2 && xyz1 && xyz2));
+  return interp_bwd_launch(grad_out, idx, weight, dist, feat2, xyz1, xyz2, alpha, eps, B, N, S, C, k, grad_feat2,
+                           grad_xyz1, grad_xyz2, gd_workspace, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

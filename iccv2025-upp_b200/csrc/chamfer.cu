@@ -449,6 +449,108 @@ __global__ void __launch_bounds__(256)
   idx_out[static_cast<size_t>(b) * n_self + k] = bi;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed path, second (and last) launch: ONE kernel resolves the merged keys of both sides and
+// produces the call's partial sums, replacing {cols finalize, rows finalize, sums} = 3 launches.
+//   blockIdx.z == 0 : column side (cloud B): key -> (distance, lowest matching row of A)
+//   blockIdx.z == 1 : row side (cloud A): from keys when the columns were cut into chunks, else the
+//                     main kernel already wrote distA/idxA and these CTAs only read distA for the sums
+//                     (the z == 1 slice is not launched at all when neither is needed).
+// Sums { sum d, sum sqrt d } per side: fixed-shape block reduction -> partials[cta]; the CTA that
+// draws the last ticket adds the partials in index order.  Fixed partition + fixed order: the value
+// is identical run to run whichever CTA happens to be last.  The ticket word sits behind the keys and
+// is preset to 0xFFFFFFFF by the same memset node, so the last of T CTAs draws ticket T - 2 (mod 2^32).
+__device__ __forceinline__ float2 block_sum2_256(float a, float b, float2* s_w) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_w[warp] = make_float2(a, b);
+  __syncthreads();
+  float2 r = make_float2(0.f, 0.f);
+  if (warp == 0) {
+    const float2 v = lane < 8 ? s_w[lane] : make_float2(0.f, 0.f);
+    r.x = warp_sum(v.x);
+    r.y = warp_sum(v.y);
+  }
+  __syncthreads();
+  return r;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256)
+    chamfer_finalize2_kernel(const float* __restrict__ xyzA, const float* __restrict__ xyzB, int NA, int NB,
+                             int NA8, int NB8, const unsigned long long* __restrict__ colkeys,
+                             const unsigned long long* __restrict__ rowkeys, int R,
+                             float* __restrict__ distA, int32_t* __restrict__ idxA,
+                             float* __restrict__ distB, int32_t* __restrict__ idxB,
+                             float2* __restrict__ partials, unsigned* __restrict__ ticket,
+                             float* __restrict__ sums, int swapped) {
+  __shared__ float2 s_w[8];
+  __shared__ bool s_last;
+  const int side = blockIdx.z;  // 0: B (columns), 1: A (rows)
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_self = side == 0 ? NB : NA, n_other = side == 0 ? NA : NB;
+  float d = 0.f;
+  if (k < n_self) {
+    if (side == 1 && rowkeys == nullptr) {
+      d = distA[static_cast<size_t>(b) * NA + k];  // written by the main kernel (previous launch)
+    } else {
+      const float* self = side == 0 ? xyzB : xyzA;
+      const float* op = (side == 0 ? xyzA : xyzB) + static_cast<size_t>(b) * n_other * 3;
+      const float* sp = self + (static_cast<size_t>(b) * n_self + k) * 3;
+      const unsigned long long key = side == 0 ? colkeys[static_cast<size_t>(b) * NB8 + k]
+                                               : rowkeys[static_cast<size_t>(b) * NA8 + k];
+      const int mult = side == 0 ? R : 1, cnt = side == 0 ? R : 8;
+      const unsigned bits = static_cast<unsigned>(key >> 32);
+      const int j0 = static_cast<int>(static_cast<unsigned>(key)) * mult;
+      const float rx = __ldg(sp), ry = __ldg(sp + 1), rz = __ldg(sp + 2);
+      int bi = j0;
+#pragma unroll
+      for (int u = 15; u >= 0; --u) {  // independent (clamped) loads, lowest match wins
+        if (u < cnt) {
+          const int j = min(j0 + u, n_other - 1);
+          const float* p = op + static_cast<size_t>(j) * 3;
+          const float dd = dist_yxz(rx - __ldg(p), ry - __ldg(p + 1), rz - __ldg(p + 2));
+          if (__float_as_uint(dd) == bits && j0 + u < n_other) bi = j0 + u;
+        }
+      }
+      d = __uint_as_float(bits);
+      (side == 0 ? distB : distA)[static_cast<size_t>(b) * n_self + k] = d;
+      (side == 0 ? idxB : idxA)[static_cast<size_t>(b) * n_self + k] = bi;
+    }
+  }
+  if (partials == nullptr) return;
+  const unsigned per_side = gridDim.x * gridDim.y;
+  const unsigned cta = side * per_side + blockIdx.y * gridDim.x + blockIdx.x;
+  const float2 part = block_sum2_256(d, k < n_self ? __fsqrt_rn(d) : 0.f, s_w);
+  if (threadIdx.x == 0) {
+    partials[cta] = part;
+    __threadfence();
+    const unsigned total = per_side * gridDim.z;
+    s_last = (atomicAdd(ticket, 1u) + 2u == total);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: side 0 = cloud B, side 1 = cloud A; output order { d1, d2, sqrt d1, sqrt d2 }
+  for (int sd = 0; sd < 2; ++sd) {
+    float a0 = 0.f, a1 = 0.f;
+    if (sd < static_cast<int>(gridDim.z)) {
+      const volatile float2* pp = partials + sd * per_side;
+      for (unsigned i = threadIdx.x; i < per_side; i += 256) {
+        a0 += pp[i].x;
+        a1 += pp[i].y;
+      }
+    }
+    const float2 tot = block_sum2_256(a0, a1, s_w);
+    if (threadIdx.x == 0) {
+      const int first = (sd == 1) != (swapped != 0);  // is this side the caller's xyz1?
+      sums[first ? 0 : 1] = tot.x;
+      sums[first ? 2 : 3] = tot.y;
+    }
+  }
+}
+
 // Column side, second half: turn each packed key into (distance, lowest matching row index) by
 // recomputing the R distances of the winning row block.  One thread per column, all loads independent.
 template <int R>
@@ -602,54 +704,61 @@ size_t chamfer_fwd_workspace_bytes(int B, int N, int M) {
   // when the columns are cut into chunks)
   const size_t n8 = (static_cast<size_t>(N) + 7) & ~static_cast<size_t>(7);
   const size_t m8 = (static_cast<size_t>(M) + 7) & ~static_cast<size_t>(7);
-  return static_cast<size_t>(B) * (n8 + m8) * 8;
+  // + the ticket word (16 B) and one float2 partial per finalize CTA (2 sides x B x ceil(max/256))
+  const size_t ctas = 2 * static_cast<size_t>(B) * ((static_cast<size_t>(N > M ? N : M) + 255) / 256);
+  return static_cast<size_t>(B) * (n8 + m8) * 8 + 16 + ctas * 8;
 }
 
-// Column chunks for the packed kernel: cut B * rowblocks work items so that they fill a whole number
-// of rounds over the 148 SMs (every resident CTA of an SM shares its issue bandwidth, so the make-span
-// is ceil(items / 148) item-times).  Fewest chunks within 3 % of the best fill; chunks stay >= 512
-// columns (below that the per-item prologue / epilogue shows: measured) and a multiple of 64.
+// Column chunks for the packed kernel.  An SM keeps up to 5 of these CTAs resident and needs several of
+// them (one warp per scheduler each) to keep its FMA pipe fed, so the grid should hold at least one full
+// residency wave (5 x 148 items) and then fill whole waves.  B200 sweep (scripts/time_ops.py
+// --sweep-chamfer): B32 1024x1024 1 chunk 33.8 us -> 4 chunks 27.6; B64 2048x2048 1 chunk 107.5 -> 4 chunks
+// 93.2; B64 2048x8192 (2048 items already) best with 1.  Chunks stay >= 256 columns and a multiple of 64.
 static int chamfer_pick_chunks(long items0, int NB) {
-  const int max_chunks = NB >= 1024 ? (NB / 512 < 32 ? NB / 512 : 32) : 1;
+  const long wave = 5 * 148;
+  const int cap = NB / 256 < 1 ? 1 : (NB / 256 > 32 ? 32 : NB / 256);
+  long cmin = (wave + items0 - 1) / items0;
+  if (cmin < 1) cmin = 1;
+  if (cmin >= cap) return cap;
+  int best = static_cast<int>(cmin);
   double best_eff = 0.0;
-  for (int c = 1; c <= max_chunks; ++c) {
+  for (int c = static_cast<int>(cmin); c <= cap && c <= 2 * cmin; ++c) {
     const long items = items0 * c;
-    const double eff = static_cast<double>(items) / (148.0 * ((items + 147) / 148));
-    if (eff > best_eff) best_eff = eff;
+    const double eff = static_cast<double>(items) / (static_cast<double>(wave) * ((items + wave - 1) / wave));
+    if (eff > best_eff + 0.03) { best_eff = eff; best = c; }  // fewest chunks within 3 % of the best fill
   }
-  for (int c = 1; c <= max_chunks; ++c) {
-    const long items = items0 * c;
-    const double eff = static_cast<double>(items) / (148.0 * ((items + 147) / 148));
-    if (eff >= best_eff - 0.03) return c;
-  }
-  return 1;
+  return best;
 }
 
 template <int R, int WC>
 static int launch_chamfer_packed(const float* a, const float* bpts, int B, int NA, int NB, float* dA,
                                  int32_t* iA, float* dB, int32_t* iB, void* ws, int force_chunks,
-                                 cudaStream_t st) {
+                                 float* sums, bool swapped, cudaStream_t st) {
+  static_assert(R <= 16, "chamfer_finalize2_kernel scans at most 16 rows per key");
   const int na8 = (NA + 7) & ~7, nb8 = (NB + 7) & ~7;
   const int rowblocks = (NA + 32 * R - 1) / (32 * R);
   int chunks = force_chunks > 0 ? force_chunks : chamfer_pick_chunks(static_cast<long>(B) * rowblocks, NB);
   int chunk = ((NB + chunks - 1) / chunks + 63) & ~63;
   chunks = (NB + chunk - 1) / chunk;
+  // workspace: [col keys B*nb8][row keys B*na8][ticket, 16 B][partials]; keys and ticket preset to 0xFF
   unsigned long long* colkeys = static_cast<unsigned long long*>(ws);
-  unsigned long long* rowkeys = chunks > 1 ? colkeys + static_cast<size_t>(B) * nb8 : nullptr;
-  const size_t keys = static_cast<size_t>(B) * (nb8 + (chunks > 1 ? na8 : 0)) * 8;
-  cudaError_t e = cudaMemsetAsync(ws, 0xFF, keys, st);
+  unsigned long long* rowkeys_all = colkeys + static_cast<size_t>(B) * nb8;
+  unsigned long long* rowkeys = chunks > 1 ? rowkeys_all : nullptr;
+  unsigned* ticket = reinterpret_cast<unsigned*>(rowkeys_all + static_cast<size_t>(B) * na8);
+  float2* partials = reinterpret_cast<float2*>(ticket + 4);
+  const size_t preset = static_cast<size_t>(B) * (nb8 + na8) * 8 + 16;
+  cudaError_t e = cudaMemsetAsync(ws, 0xFF, preset, st);
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(rowblocks, B, chunks);
   chamfer_fwd_packed_kernel<R, WC><<<grid, WC * 32, 0, st>>>(a, bpts, NA, NB, na8, nb8, chunk, dA, iA, rowkeys, colkeys);
   count_launch();
   int rc = launch_status();
   if (rc != UPP_OK) return rc;
-  chamfer_finalize_kernel<<<dim3((NB + 255) / 256, B), 256, 0, st>>>(bpts, a, NB, NA, nb8, colkeys, R, R, dB, iB);
+  const bool rows_too = chunks > 1 || sums != nullptr;
+  dim3 fgrid(((rows_too ? max(NA, NB) : NB) + 255) / 256, B, rows_too ? 2 : 1);
+  chamfer_finalize2_kernel<<<fgrid, 256, 0, st>>>(a, bpts, NA, NB, na8, nb8, colkeys, rowkeys, R, dA, iA, dB, iB,
+                                                  sums ? partials : nullptr, ticket, sums, swapped ? 1 : 0);
   count_launch();
-  if (chunks > 1) {
-    chamfer_finalize_kernel<<<dim3((NA + 255) / 256, B), 256, 0, st>>>(a, bpts, NA, NB, na8, rowkeys, 1, 8, dA, iA);
-    count_launch();
-  }
   return launch_status();
 }
 
@@ -682,8 +791,9 @@ int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M
   const char* v = getenv("UPP_CH_VARIANT");  // tuning aid
   const int variant = v ? atoi(v) : -1;
   const bool have_ws = workspace != nullptr && workspace_bytes >= chamfer_fwd_workspace_bytes(B, N, M);
-  // single pass pays off once both clouds fill the 32*R-row tiles; tiny clouds stay on the directed kernel
-  const bool single = have_ws && min(N, M) >= 128 && (variant < 0 || variant >= 20);
+  // single pass: rows = the larger cloud (fills the 32*R-row tiles), columns = the smaller one (any size);
+  // two tiny clouds stay on the directed kernel
+  const bool single = have_ws && max(N, M) >= 128 && (variant < 0 || variant >= 20);
   if (single) {
     // rows = the larger cloud (more CTAs), columns = the smaller one (fewer keys)
     const bool swap = M > N;
@@ -702,13 +812,17 @@ int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M
       case 20: rc = launch_chamfer_both<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
       case 21: rc = launch_chamfer_both<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
       case 22: rc = launch_chamfer_both<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
-      case 31: rc = launch_chamfer_packed<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, st); break;
-      case 32: rc = launch_chamfer_packed<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, st); break;
-      case 33: rc = launch_chamfer_packed<6, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, st); break;
+      case 31: rc = launch_chamfer_packed<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
+      case 32: rc = launch_chamfer_packed<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
+      case 33: rc = launch_chamfer_packed<6, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
       // measured best on B200: 8 rows per thread, 4 warps per CTA (5 CTAs / SM)
-      default: rc = launch_chamfer_packed<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, st); break;
+      case 34: rc = launch_chamfer_packed<12, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
+      case 35: rc = launch_chamfer_packed<16, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
+      case 36: rc = launch_chamfer_packed<16, 2>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
+      default: rc = launch_chamfer_packed<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
     }
     if (rc != UPP_OK) return rc;
+    if (pick >= 30) return UPP_OK;  // the packed path's finalize kernel has produced the sums too
   } else {
     switch (variant) {
       case 1: launch_chamfer_fwd<4, 64>(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, st); break;

@@ -223,6 +223,68 @@ __global__ void __launch_bounds__(128, 1)
   }
 }
 
+// Ternary max tree over a thread's NS keys with its intermediate levels kept (for SEARCH == 2): the
+// slot of the lowest-index maximum is then found by DESCENDING the tree (first child equal to the
+// maximum, ~2 compares per level) instead of comparing every slot.  Only the one lane per warp that
+// posts the warp's winner walks it, so for 16-32 points per thread the search costs ~16 issued
+// instructions per warp and round instead of 2 per slot (the integer/ALU pipe, 16 lanes per scheduler,
+// is what binds large clouds: profiles/r01d_fps8k_nw32.txt).
+template <int NS>
+struct KeyTree {
+  static constexpr int N1 = (NS + 2) / 3, N2 = (N1 + 2) / 3, N3 = (N2 + 2) / 3, N4 = (N3 + 2) / 3;
+  static_assert(N4 == 1, "KeyTree covers up to 81 keys");
+  int l0[NS], l1[N1], l2[N2], l3[N3], l4[1];
+
+  template <int NI, int NO>
+  static __device__ __forceinline__ void fold(const int (&in)[NI], int (&out)[NO]) {
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+      int v = in[3 * q];
+      if (3 * q + 1 < NI) v = max(v, in[3 * q + 1]);
+      if (3 * q + 2 < NI) v = max(v, in[3 * q + 2]);
+      out[q] = v;
+    }
+  }
+  __device__ __forceinline__ int build() {
+    fold(l0, l1); fold(l1, l2); fold(l2, l3); fold(l3, l4);
+    return l4[0];
+  }
+  template <int LEVEL>
+  __device__ __forceinline__ int at(int q) const {
+    if constexpr (LEVEL == 0) return l0[q];
+    else if constexpr (LEVEL == 1) return l1[q];
+    else if constexpr (LEVEL == 2) return l2[q];
+    else if constexpr (LEVEL == 3) return l3[q];
+    else return l4[q];
+  }
+  template <int LEVEL>
+  static __host__ __device__ constexpr int size() {
+    return LEVEL == 0 ? NS : LEVEL == 1 ? N1 : LEVEL == 2 ? N2 : LEVEL == 3 ? N3 : 1;
+  }
+  // lowest slot whose key equals `best` (== the root), node Q of level LEVEL known to contain it
+  template <int LEVEL, int Q>
+  __device__ __forceinline__ int descend(int best) const {
+    if constexpr (LEVEL == 0) {
+      return Q;
+    } else {
+      constexpr int n = size<LEVEL - 1>();
+      constexpr int c0 = 3 * Q;
+      if constexpr (c0 + 1 >= n) {
+        return descend<LEVEL - 1, c0>(best);
+      } else {
+        if (at<LEVEL - 1>(c0) == best) return descend<LEVEL - 1, c0>(best);
+        if constexpr (c0 + 2 < n) {
+          if (at<LEVEL - 1>(c0 + 1) == best) return descend<LEVEL - 1, c0 + 1>(best);
+          return descend<LEVEL - 1, c0 + 2>(best);
+        } else {
+          return descend<LEVEL - 1, c0 + 1>(best);
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ int find(int best) const { return descend<4, 0>(best); }
+};
+
 // One span [R0, R1) of a thread's point pairs: distances to the new centre, running-min update,
 // span maximum (order-preserving float bits) and the lowest slot holding it.  TREE: independent
 // compare/selects + a VIMNMX3 tree (short dependent chain) instead of one select chain.
@@ -304,7 +366,9 @@ __device__ __forceinline__ void fps_span(const f32x2 (&X)[P2], const f32x2 (&Y)[
 //     thread resolves the block winner itself: S2 == 0 scans the NW posted pairs with vector
 //     LDS + a select tree (NW <= 8), S2 == 1 does REDUX.MAX + ballot over them (NW >= 16).
 //   * a single warp (NW == 1) needs no shared-memory round trip at all.
-template <int NW, int P2, int S2>
+// SEARCH: 0 = in-thread slot search in the shadow of the REDUX (select chain / min tree; small clouds,
+// latency bound), 2 = the posting lane descends a kept max tree after the vote (large clouds, ALU bound).
+template <int NW, int P2, int S2, int SEARCH = 0>
 __global__ void __launch_bounds__(NW * 32)
     fps_blk_kernel(const float* __restrict__ xyz, int N, int M, int32_t* __restrict__ idx_out,
                    float* __restrict__ centers_out) {
@@ -365,8 +429,32 @@ __global__ void __launch_bounds__(NW * 32)
     // The in-thread slot search needs only the thread's own maximum, so it runs in the shadow of the
     // REDUX.  (Splitting the pairs into two spans so that the first span's search issues under the
     // second span's FMA work was measured: no gain -- one warp per scheduler is latency-, not pipe-bound.)
-    int best, ls;
-    fps_span<P2, 0, P2, (NW <= 4)>(X, Y, Z, md, CX, CY, CZ, best, ls);
+    int best, ls = 0;
+    KeyTree<SEARCH == 2 ? P : 1> kt;
+    if constexpr (SEARCH == 2) {
+      static_assert(NW > 1, "the deferred search posts through shared memory");
+      f32x2 D[P2];
+#pragma unroll
+      for (int r = 0; r < P2; ++r) D[r] = sub2(Y[r], CY);
+#pragma unroll
+      for (int r = 0; r < P2; ++r) D[r] = mul2(D[r], D[r]);
+#pragma unroll
+      for (int r = 0; r < P2; ++r) { const f32x2 dx = sub2(X[r], CX); D[r] = fma2(dx, dx, D[r]); }
+#pragma unroll
+      for (int r = 0; r < P2; ++r) { const f32x2 dz = sub2(Z[r], CZ); D[r] = fma2(dz, dz, D[r]); }
+#pragma unroll
+      for (int r = 0; r < P2; ++r) {
+        float d0, d1;
+        unpack2(D[r], d0, d1);
+        md[2 * r] = fminf(md[2 * r], d0);
+        md[2 * r + 1] = fminf(md[2 * r + 1], d1);
+        kt.l0[2 * r] = __float_as_int(md[2 * r]);
+        kt.l0[2 * r + 1] = __float_as_int(md[2 * r + 1]);
+      }
+      best = kt.build();
+    } else {
+      fps_span<P2, 0, P2, (NW <= 4)>(X, Y, Z, md, CX, CY, CZ, best, ls);
+    }
     const int wbest = redux_max_s32(best);
     const unsigned winners = __ballot_sync(0xffffffffu, best == wbest);
     int sel;
@@ -375,7 +463,10 @@ __global__ void __launch_bounds__(NW * 32)
     } else {
       int2* slot = s_slot[j & 1];
       // the lowest lane holding the warp maximum posts (lower lane == lower point indices)
-      if (best == wbest && (winners & lanes_below) == 0u) slot[warp] = make_int2(wbest, base + ls);
+      if (best == wbest && (winners & lanes_below) == 0u) {
+        if constexpr (SEARCH == 2) ls = kt.find(wbest);
+        slot[warp] = make_int2(wbest, base + ls);
+      }
       __syncthreads();
       if constexpr (S2 == 0) {
         int v[NW], ix[NW];
@@ -475,6 +566,20 @@ static int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
+// FPS is a serial latency chain: one warp per scheduler, ~40 % issue utilisation, every instruction on
+// the critical path.  Any co-resident CTA of a throughput kernel (measured: the packed Chamfer kernel
+// running on another stream, 5 CTAs x 4 warps per SM) takes issue slots from it and stretches every
+// round -- the whole-step graph went from 0.27 ms to 0.34-0.43 ms.  So when there are no more clouds
+// than SMs, each FPS CTA asks for (nearly) all of the SM's shared memory: nothing with a shared-memory
+// footprint can be placed beside it, the cloud has the SM to itself, and the other 148 - B SMs carry
+// the concurrent work.  With more clouds than SMs the request is the real footprint (clouds share SMs).
+constexpr int kNumSMs = 148;
+constexpr size_t kExclusiveSmem = 232448 - 2048;  // 227 KB opt-in limit minus static + headroom
+static size_t fps_smem_request(size_t need, int B) {
+  if (env_int("UPP_FPS_SHARE_SM", 0) == 1) return need;  // A/B aid: allow co-residency
+  return (B <= kNumSMs && need < kExclusiveSmem) ? kExclusiveSmem : need;
+}
+
 static const int kPs[] = {1, 2, 3, 4, 6, 8, 12, 16};
 
 static int round_p(int p) {
@@ -509,9 +614,9 @@ FpsConfig fps_pick_config(int N) {
 template <int THREADS, int P>
 static int launch_fps_reg(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                           cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(N) * 3 * sizeof(float);
+  const size_t smem = fps_smem_request(static_cast<size_t>(N) * 3 * sizeof(float), B);
   auto kern = fps_reg_kernel<THREADS, P>;
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -525,9 +630,9 @@ static int launch_fps_reg(const float* xyz, int B, int N, int M, int32_t* idx, f
 template <int P>
 static int launch_fps_rt(int threads, const float* xyz, int B, int N, int M, int32_t* idx,
                          float* centers, cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(N) * 3 * sizeof(float);
+  const size_t smem = fps_smem_request(static_cast<size_t>(N) * 3 * sizeof(float), B);
   auto kern = fps_reg_kernel<0, P>;
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -540,9 +645,9 @@ static int launch_fps_rt(int threads, const float* xyz, int B, int N, int M, int
 template <int P>
 static int launch_fps_w4(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                          cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(N) * 3 * sizeof(float);
+  const size_t smem = fps_smem_request(static_cast<size_t>(N) * 3 * sizeof(float), B);
   auto kern = fps_w4_kernel<P>;
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -569,15 +674,15 @@ static int dispatch_fps_w4(int p, const float* xyz, int B, int N, int M, int32_t
 
 // ---- v2 dispatch ---------------------------------------------------------------------------
 struct FpsBlkConfig {
-  int nw, p2, s2;
+  int nw, p2, s2, search;
 };
 
-template <int NW, int P2, int S2>
+template <int NW, int P2, int S2, int SEARCH = 0>
 static int launch_fps_blk(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                           cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(N) * 3 * sizeof(float);
-  auto kern = fps_blk_kernel<NW, P2, S2>;
-  if (smem > 48 * 1024) {
+  const size_t smem = fps_smem_request(static_cast<size_t>(N) * 3 * sizeof(float), B);
+  auto kern = fps_blk_kernel<NW, P2, S2, SEARCH>;
+  if (smem > 40 * 1024) {  // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -602,8 +707,30 @@ static int dispatch_fps_blk(FpsBlkConfig c, const float* xyz, int B, int N, int 
   return UPP_ERR_UNSUPPORTED;
 }
 
+// large clouds (2048 < N <= 8192): deferred tree search, 8 or 16 warps, up to 32 points per thread
+static int dispatch_fps_blk_big(FpsBlkConfig c, const float* xyz, int B, int N, int M, int32_t* idx,
+                                float* centers, cudaStream_t st) {
+#define UPP_BIG(NW_, P2_, S2_) \
+  if (c.nw == NW_ && c.p2 == P2_ && c.s2 == S2_) return launch_fps_blk<NW_, P2_, S2_, 2>(xyz, B, N, M, idx, centers, st);
+#define UPP_BIG_ROW(NW_, S2_) \
+  UPP_BIG(NW_, 3, S2_) UPP_BIG(NW_, 4, S2_) UPP_BIG(NW_, 5, S2_) UPP_BIG(NW_, 6, S2_) UPP_BIG(NW_, 7, S2_) UPP_BIG(NW_, 8, S2_)
+  UPP_BIG_ROW(8, 0) UPP_BIG_ROW(8, 1) UPP_BIG_ROW(16, 0) UPP_BIG_ROW(16, 1)
+  UPP_BIG(8, 10, 0) UPP_BIG(8, 12, 0) UPP_BIG(8, 14, 0) UPP_BIG(8, 16, 0)
+  UPP_BIG(8, 10, 1) UPP_BIG(8, 12, 1) UPP_BIG(8, 14, 1) UPP_BIG(8, 16, 1)
+  UPP_BIG(32, 2, 1) UPP_BIG(32, 3, 1) UPP_BIG(32, 4, 1)
+#undef UPP_BIG_ROW
+#undef UPP_BIG
+  return UPP_ERR_UNSUPPORTED;
+}
+
 static bool fps_blk_valid(FpsBlkConfig c, int N) {
   const bool nw_ok = c.nw == 1 || c.nw == 2 || c.nw == 4 || c.nw == 8 || c.nw == 16 || c.nw == 32;
+  if (c.search == 2) {  // the combinations dispatch_fps_blk_big instantiates
+    const bool p_ok = (c.nw == 8 && ((c.p2 >= 3 && c.p2 <= 8) || c.p2 == 10 || c.p2 == 12 || c.p2 == 14 || c.p2 == 16)) ||
+                      (c.nw == 16 && c.p2 >= 3 && c.p2 <= 8) || (c.nw == 32 && c.p2 >= 2 && c.p2 <= 4 && c.s2 == 1);
+    return p_ok && (c.s2 == 0 || c.s2 == 1) && static_cast<long>(c.nw) * 64 * c.p2 >= N;
+  }
+  if (c.search != 0) return false;
   if (!nw_ok || c.p2 < 1 || c.p2 > (c.nw == 32 ? 4 : 8)) return false;
   if (c.s2 != 0 && c.s2 != 1) return false;
   if (c.nw <= 2 && c.s2 != 0) return false;
@@ -619,7 +746,7 @@ FpsBlkConfig fps_pick_blk(int N, int B) {
   else if (B >= 2 * 148 && N <= 1024) nw = 2;         // several clouds per SM: fewer, fatter warps
   else nw = 4;                                        // one warp per SM sub-partition
   const int p2 = (N + nw * 64 - 1) / (nw * 64);
-  return {nw, p2, 0};
+  return {nw, p2, 0, 0};
 }
 
 #define UPP_FPS_CASE_P(T, PP) \
@@ -630,14 +757,24 @@ FpsBlkConfig fps_pick_blk(int N, int B) {
 int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (N <= kFpsMaxRegPoints && env_int("UPP_FPS_IMPL", 2) != 1) {
-    // v2 where the B200 sweep says it wins (N <= 2048: 0.16 vs 0.20 us per round at N = 1228); larger
-    // clouds are ALU-pipe bound and stay on the 512-thread v1 kernel below.
+    // v2 (blocked ownership, packed fp32x2) everywhere the register-resident scheme reaches; the v1 kernels
+    // below stay for A/B timing (UPP_FPS_IMPL=1) and as a parity cross-check.
     FpsBlkConfig c = fps_pick_blk(N, B);
-    const FpsBlkConfig forced = {env_int("UPP_FPS_NW", 0), env_int("UPP_FPS_P2", 0), env_int("UPP_FPS_S2", 0)};
+    const FpsBlkConfig forced = {env_int("UPP_FPS_NW", 0), env_int("UPP_FPS_P2", 0), env_int("UPP_FPS_S2", 0),
+                                 env_int("UPP_FPS_SEARCH", 0)};
     const bool use_forced = forced.nw > 0 && forced.p2 > 0 && fps_blk_valid(forced, N);  // tuning aid
     if (use_forced) c = forced;
-    if (use_forced || N <= 2048) {
+    if (!use_forced && N > 2048) {
+      // large clouds: 8 fat warps (B200 sweep, us per round v1 -> here): N 2500 0.335 -> 0.255, 3000 0.335 -> 0.270,
+      // 4096 0.388 -> 0.367, 6144 0.475 -> 0.452, 8192 0.570 -> 0.544 (deferred tree search from 18 points per thread)
+      const int p2 = (N + 511) / 512;
+      if (N <= 3072) c = {8, p2, 1, 0};
+      else if (N <= 4096) c = {8, p2, 0, 0};
+      else c = {8, p2 + (p2 & 1), 0, 2};
+    }
+    if (use_forced || fps_blk_valid(c, N)) {
       if (!fps_blk_valid(c, N)) return UPP_ERR_UNSUPPORTED;
+      if (c.search == 2) return dispatch_fps_blk_big(c, xyz, B, N, M, idx, centers, st);
       return dispatch_fps_blk(c, xyz, B, N, M, idx, centers, st);
     }
   }

@@ -5,7 +5,7 @@
 // batch and, per cloud, materialises the N x Q distance matrix in global memory, then sorts
 // each column with ONE THREAD per query (stride-Q global accesses), then a sqrt kernel.
 //
-// Here (knn_warp_kernel): the cloud's reference points are staged once per CTA into shared
+// Here (knn_warp_kernel + topk.cuh): the cloud's reference points are staged once per CTA into shared
 // memory by a TMA bulk copy; one WARP owns one query and works through the references in blocks
 // of 1024 (32 per lane), all of a lane's distances held in registers.
 //   1. per block, every lane computes its 32 distances (independent FMA chains) and its minimum;
@@ -23,37 +23,14 @@
 // (models/Point_MAE_unify.py:72-88) without another launch.
 #include <float.h>
 
-#include "common.cuh"
+#include "topk.cuh"
 
 namespace upp {
 
-constexpr int kKnnWarps = 8;     // queries in flight per CTA
-constexpr int kKnnTile = 2048;   // reference points staged per pass (24 KB)
-constexpr int kKnnSlots = 32;    // distances per lane per block (block = 1024 refs)
-
-__device__ __forceinline__ bool key_less(float da, int ia, float db, int ib) {
-  return da < db || (da == db && ia < ib);
-}
-
-// Bitonic sort of one (d, i) pair per lane, ascending by (d, i) over lanes 0..31, via shuffles.
-__device__ __forceinline__ void warp_bitonic_sort(float& d, int& i, int lane) {
-#pragma unroll
-  for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, d, stride);
-      const int oi = __shfl_xor_sync(0xffffffffu, i, stride);
-      const bool ascending = ((lane & size) == 0);  // direction of the merge this lane is in
-      const bool lower = ((lane & stride) == 0);    // lower lane of the compared pair
-      const bool keep_min = (lower == ascending);
-      const bool take = keep_min ? key_less(od, oi, d, i) : key_less(d, i, od, oi);
-      if (take) { d = od; i = oi; }
-    }
-  }
-}
-
-// k <= 32.
-template <bool GATHER>
+// k <= 32.  The per-warp selection itself lives in topk.cuh (shared with interp.cu).
+// RAW selects the pytorch3d.ops.knn_points convention: SQUARED distances and, with GATHER, the neighbours
+// themselves (no centre subtraction).
+template <bool GATHER, bool RAW, int SLOTS>
 __global__ void __launch_bounds__(kKnnWarps * kWarp)
     knn_warp_kernel(const float* __restrict__ ref, const float* __restrict__ query, int N, int Q,
                     int k, float* __restrict__ dist_out, int64_t* __restrict__ idx_out,
@@ -81,80 +58,20 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
     qy = __ldg(qp + 1);
     qz = __ldg(qp + 2);
   }
-  const float kInf = __int_as_float(0x7f800000);
-  float ld = kInf;      // lane i: squared distance of the i-th best so far
-  int li = 0x7fffffff;  //         and its reference index
-  float thr_d = kInf;   // current k-th best (warp-uniform)
-  int thr_i = 0x7fffffff;
-  bool seeded = false;
-
-  for (int base = 0; base < N; base += kKnnTile) {
-    const int tile = min(kKnnTile, N - base);
-    if (base > 0) __syncthreads();  // everyone done reading the previous tile
-    stage_points(s_ref, rb + static_cast<size_t>(base) * 3, tile, &s_bar, parity);
-    if (!active) continue;
-    for (int blk = 0; blk < tile; blk += kKnnSlots * kWarp) {
-      // ---- 1. distances of this block into registers; slot s <-> ref index blk + s*32 + lane ----
-      float d[kKnnSlots];
-      float lmin = kInf;
-      int lmin_s = 0;
-#pragma unroll
-      for (int s = 0; s < kKnnSlots; ++s) {
-        const int c = blk + s * kWarp + lane;
-        d[s] = kInf;
-        if (blk + s * kWarp < tile) {  // warp-uniform guard, then the per-lane tail
-          if (c < tile) d[s] = dist_xyz_acc(s_ref[3 * c] - qx, s_ref[3 * c + 1] - qy, s_ref[3 * c + 2] - qz);
-          if (d[s] < lmin) { lmin = d[s]; lmin_s = s; }  // strict '<': lowest index among equal minima
-        }
-      }
-      // ---- 2. seed the list with the sorted lane minima (first block only) ----
-      if (!seeded) {
-        seeded = true;
-        ld = lmin;
-        li = lmin < kInf ? base + blk + lmin_s * kWarp + lane : 0x7fffffff;
-        warp_bitonic_sort(ld, li, lane);
-#pragma unroll
-        for (int s = 0; s < kKnnSlots; ++s)
-          if (s == lmin_s) d[s] = kInf;  // consumed
-        thr_d = __shfl_sync(0xffffffffu, ld, k - 1);
-        thr_i = __shfl_sync(0xffffffffu, li, k - 1);
-      }
-      // ---- 3. stream the register slots through the threshold filter ----
-#pragma unroll
-      for (int s = 0; s < kKnnSlots; ++s) {
-        if (blk + s * kWarp < tile) {  // warp-uniform
-          const int myi = base + blk + s * kWarp + lane;
-          unsigned m = __ballot_sync(0xffffffffu, key_less(d[s], myi, thr_d, thr_i));
-          if (m != 0) {
-            while (m) {
-              const int src = __ffs(m) - 1;
-              m &= m - 1;
-              const float cd = __shfl_sync(0xffffffffu, d[s], src);
-              const int ci = base + blk + s * kWarp + src;
-              const float ud = __shfl_up_sync(0xffffffffu, ld, 1);
-              const int ui = __shfl_up_sync(0xffffffffu, li, 1);
-              // entries greater than the candidate shift right by one; the first of them is replaced
-              const bool mine_gt = key_less(cd, ci, ld, li);
-              const bool left_gt = (lane > 0) && key_less(cd, ci, ud, ui);
-              li = mine_gt ? (left_gt ? ui : ci) : li;
-              ld = mine_gt ? (left_gt ? ud : cd) : ld;
-            }
-            thr_d = __shfl_sync(0xffffffffu, ld, k - 1);
-            thr_i = __shfl_sync(0xffffffffu, li, k - 1);
-          }
-        }
-      }
-    }
-  }
+  DistDirect dist;
+  dist.set(qx, qy, qz);
+  float ld;  // lane i: squared distance of the i-th nearest
+  int li;    //         and its reference index
+  warp_topk_scan<DistDirect, SLOTS>(rb, N, k, dist, active, s_ref, &s_bar, parity, ld, li);
   if (active && lane < k) {
     const size_t o = (static_cast<size_t>(b) * Q + q) * k + lane;
-    if (dist_out) dist_out[o] = __fsqrt_rn(ld);
+    if (dist_out) dist_out[o] = RAW ? ld : __fsqrt_rn(ld);
     idx_out[o] = static_cast<int64_t>(li);
     if (GATHER) {
       const float* p = rb + static_cast<size_t>(li) * 3;
-      nb_out[3 * o + 0] = __ldg(p) - qx;
-      nb_out[3 * o + 1] = __ldg(p + 1) - qy;
-      nb_out[3 * o + 2] = __ldg(p + 2) - qz;
+      nb_out[3 * o + 0] = RAW ? __ldg(p) : __ldg(p) - qx;
+      nb_out[3 * o + 1] = RAW ? __ldg(p + 1) : __ldg(p + 1) - qy;
+      nb_out[3 * o + 2] = RAW ? __ldg(p + 2) : __ldg(p + 2) - qz;
     }
   }
 }
@@ -206,6 +123,16 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
   }
 }
 
+template <bool GATHER, bool RAW>
+static void launch_knn_warp(dim3 grid, size_t smem, cudaStream_t st, const float* ref, const float* query, int N,
+                            int Q, int k, float* dist_out, int64_t* idx_out, float* nb_out) {
+  const int threads = kKnnWarps * kWarp;
+  // slots per lane sized to the cloud: short unrolled loops for the small second-level groupings
+  if (N <= 128) knn_warp_kernel<GATHER, RAW, 4><<<grid, threads, smem, st>>>(ref, query, N, Q, k, dist_out, idx_out, nb_out);
+  else if (N <= 256) knn_warp_kernel<GATHER, RAW, 8><<<grid, threads, smem, st>>>(ref, query, N, Q, k, dist_out, idx_out, nb_out);
+  else knn_warp_kernel<GATHER, RAW, 32><<<grid, threads, smem, st>>>(ref, query, N, Q, k, dist_out, idx_out, nb_out);
+}
+
 // nb_out != nullptr fuses the Group gather (neighbourhood = ref[idx] - query).
 int knn_launch(const float* ref, const float* query, int B, int N, int Q, int k, float* dist_out,
                int64_t* idx_out, float* nb_out, cudaStream_t st) {
@@ -213,12 +140,24 @@ int knn_launch(const float* ref, const float* query, int B, int N, int Q, int k,
   const int threads = kKnnWarps * kWarp;
   if (k <= kWarp) {
     const size_t smem = static_cast<size_t>(min(N, kKnnTile)) * 3 * sizeof(float);
-    if (nb_out) knn_warp_kernel<true><<<grid, threads, smem, st>>>(ref, query, N, Q, k, dist_out, idx_out, nb_out);
-    else knn_warp_kernel<false><<<grid, threads, smem, st>>>(ref, query, N, Q, k, dist_out, idx_out, nullptr);
+    if (nb_out) launch_knn_warp<true, false>(grid, smem, st, ref, query, N, Q, k, dist_out, idx_out, nb_out);
+    else launch_knn_warp<false, false>(grid, smem, st, ref, query, N, Q, k, dist_out, idx_out, nullptr);
   } else {
     if (nb_out) knn_extract_kernel<true><<<grid, threads, 0, st>>>(ref, query, N, Q, k, dist_out, idx_out, nb_out);
     else knn_extract_kernel<false><<<grid, threads, 0, st>>>(ref, query, N, Q, k, dist_out, idx_out, nullptr);
   }
+  count_launch();
+  return launch_status();
+}
+
+// pytorch3d.ops.knn_points(p1, p2, K, return_nn) convention (k <= 32): squared distances ascending,
+// int64 indices into p2, optionally the gathered neighbours p2[idx] (B,N1,K,3).
+int knn_points_launch(const float* p1, const float* p2, int B, int N1, int N2, int k, float* dist2_out,
+                      int64_t* idx_out, float* nn_out, cudaStream_t st) {
+  dim3 grid((N1 + kKnnWarps - 1) / kKnnWarps, B);
+  const size_t smem = static_cast<size_t>(min(N2, kKnnTile)) * 3 * sizeof(float);
+  if (nn_out) launch_knn_warp<true, true>(grid, smem, st, p2, p1, N2, N1, k, dist2_out, idx_out, nn_out);
+  else launch_knn_warp<false, true>(grid, smem, st, p2, p1, N2, N1, k, dist2_out, idx_out, nullptr);
   count_launch();
   return launch_status();
 }

@@ -1,0 +1,146 @@
+// topk.cuh -- warp-level exact top-k (k <= 32) of one query against a reference cloud staged in
+// shared memory; shared by knn.cu (knn_cuda.KNN / Group) and interp.cu (propagate / feature
+// propagation).  One WARP owns one query and works through the references in blocks of 1024
+// (32 per lane), all of a lane's distances held in registers:
+//   1. per block, every lane computes its 32 distances (independent FMA chains) and its minimum;
+//   2. first block: the 32 lane minima -- real (distance, index) pairs -- are sorted across the
+//      warp by a 15-stage shuffle bitonic network and become the initial top-32 list, so the
+//      k-th-best threshold is tight from the start (instead of 32 serial insertions from +inf);
+//   3. each register slot is filtered against the current k-th best with one ballot; survivors are
+//      admitted with one shuffle-up (every lane decides from its own and its left neighbour's
+//      entry, no ballot/popc on the dependent chain).
+// Order is the total order (distance, index): ascending distance, equal distances keep the lower
+// reference index first (== a stable sort by distance).
+#pragma once
+#include "common.cuh"
+
+namespace upp {
+
+constexpr int kKnnWarps = 8;     // queries in flight per CTA
+constexpr int kKnnTile = 2048;   // reference points staged per pass (24 KB)
+constexpr int kKnnSlots = 32;    // distances per lane per block (block = 1024 refs)
+
+// ---- distance forms ---------------------------------------------------------------------
+// KNN_CUDA 0.2 knn.cu (cuComputeDistanceGlobal): ssd += (r - q)^2 over x, y, z.
+struct DistDirect {
+  float qx, qy, qz;
+  __device__ __forceinline__ void set(float x, float y, float z) { qx = x; qy = y; qz = z; }
+  __device__ __forceinline__ float operator()(float rx, float ry, float rz) const {
+    return dist_xyz_acc(rx - qx, ry - qy, rz - qz);
+  }
+};
+// models/modules.py:13-32 square_distance(src, dst): -2 * (src . dst) + sum(src^2) + sum(dst^2),
+// in that association (the form propagate / PointNetFeaturePropagation sort on).  It can be slightly
+// negative for coincident points, exactly like the reference's.
+struct DistExpanded {
+  float qx, qy, qz, s1;
+  __device__ __forceinline__ void set(float x, float y, float z) {
+    qx = x; qy = y; qz = z;
+    s1 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+  }
+  __device__ __forceinline__ float operator()(float rx, float ry, float rz) const {
+    const float dot = __fmaf_rn(qz, rz, __fmaf_rn(qy, ry, __fmul_rn(qx, rx)));
+    const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+    return __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), s1), s2);
+  }
+};
+
+__device__ __forceinline__ bool key_less(float da, int ia, float db, int ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+// Bitonic sort of one (d, i) pair per lane, ascending by (d, i) over lanes 0..31, via shuffles.
+__device__ __forceinline__ void warp_bitonic_sort(float& d, int& i, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, stride);
+      const int oi = __shfl_xor_sync(0xffffffffu, i, stride);
+      const bool ascending = ((lane & size) == 0);  // direction of the merge this lane is in
+      const bool lower = ((lane & stride) == 0);    // lower lane of the compared pair
+      const bool keep_min = (lower == ascending);
+      const bool take = keep_min ? key_less(od, oi, d, i) : key_less(d, i, od, oi);
+      if (take) { d = od; i = oi; }
+    }
+  }
+}
+
+// Scans the N references of one cloud (rb, AoS) for the k (<= 32) nearest to this warp's query.
+// Every thread of the CTA must call it (the tile staging uses __syncthreads); warps with
+// active == false only help staging.  On return lane j < k holds the j-th nearest (ld, li).
+// SLOTS = distances per lane per block (block = 32 * SLOTS references): 32 for large clouds; 4 / 8 keep the
+// unrolled loops short when the whole cloud is at most 128 / 256 points.
+template <class Dist, int SLOTS = kKnnSlots>
+__device__ __forceinline__ void warp_topk_scan(const float* __restrict__ rb, int N, int k, const Dist& dist,
+                                               bool active, float* s_ref, uint64_t* s_bar, unsigned& parity,
+                                               float& ld, int& li) {
+  const int lane = threadIdx.x & 31;
+  const float kInf = __int_as_float(0x7f800000);
+  ld = kInf;           // lane i: distance of the i-th best so far
+  li = 0x7fffffff;     //         and its reference index
+  float thr_d = kInf;  // current k-th best (warp-uniform)
+  int thr_i = 0x7fffffff;
+  bool seeded = false;
+
+  for (int base = 0; base < N; base += kKnnTile) {
+    const int tile = min(kKnnTile, N - base);
+    if (base > 0) __syncthreads();  // everyone done reading the previous tile
+    stage_points(s_ref, rb + static_cast<size_t>(base) * 3, tile, s_bar, parity);
+    if (!active) continue;
+    for (int blk = 0; blk < tile; blk += SLOTS * kWarp) {
+      // ---- 1. distances of this block into registers; slot s <-> ref index blk + s*32 + lane ----
+      float d[SLOTS];
+      float lmin = kInf;
+      int lmin_s = 0;
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        const int c = blk + s * kWarp + lane;
+        d[s] = kInf;
+        if (blk + s * kWarp < tile) {  // warp-uniform guard, then the per-lane tail
+          if (c < tile) d[s] = dist(s_ref[3 * c], s_ref[3 * c + 1], s_ref[3 * c + 2]);
+          if (d[s] < lmin) { lmin = d[s]; lmin_s = s; }  // strict '<': lowest index among equal minima
+        }
+      }
+      // ---- 2. seed the list with the sorted lane minima (first block only) ----
+      if (!seeded) {
+        seeded = true;
+        ld = lmin;
+        li = lmin < kInf ? base + blk + lmin_s * kWarp + lane : 0x7fffffff;
+        warp_bitonic_sort(ld, li, lane);
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+          if (s == lmin_s) d[s] = kInf;  // consumed
+        thr_d = __shfl_sync(0xffffffffu, ld, k - 1);
+        thr_i = __shfl_sync(0xffffffffu, li, k - 1);
+      }
+      // ---- 3. stream the register slots through the threshold filter ----
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        if (blk + s * kWarp < tile) {  // warp-uniform
+          const int myi = base + blk + s * kWarp + lane;
+          unsigned m = __ballot_sync(0xffffffffu, key_less(d[s], myi, thr_d, thr_i));
+          if (m != 0) {
+            while (m) {
+              const int src = __ffs(m) - 1;
+              m &= m - 1;
+              const float cd = __shfl_sync(0xffffffffu, d[s], src);
+              const int ci = base + blk + s * kWarp + src;
+              const float ud = __shfl_up_sync(0xffffffffu, ld, 1);
+              const int ui = __shfl_up_sync(0xffffffffu, li, 1);
+              // entries greater than the candidate shift right by one; the first of them is replaced
+              const bool mine_gt = key_less(cd, ci, ld, li);
+              const bool left_gt = (lane > 0) && key_less(cd, ci, ud, ui);
+              li = mine_gt ? (left_gt ? ui : ci) : li;
+              ld = mine_gt ? (left_gt ? ud : cd) : ld;
+            }
+            thr_d = __shfl_sync(0xffffffffu, ld, k - 1);
+            thr_i = __shfl_sync(0xffffffffu, li, k - 1);
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace upp

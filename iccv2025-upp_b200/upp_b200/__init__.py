@@ -5,6 +5,8 @@ reference's own operator API.
     KNN                                                        (knn_cuda)
     chamfer.forward / chamfer.backward                         (extensions/chamfer_dist)
     fps, Group, ChamferFunction, ChamferDistanceL1/L2/L2_split (reference Python, mirrored)
+    propagate, interpolate_features                            (kNN inverse-distance feature interpolation)
+    knn_points                                                 (pytorch3d.ops.knn_points convention)
     parallel                                                   (batch sharding + NCCL loss all-reduce)
 
 Everything computes in libupp_geom.so (hand-written CUDA); importing this package without the
@@ -17,7 +19,7 @@ _lib.load()  # fail loudly, at import, if the CUDA library is missing
 from . import chamfer, ops, parallel, pointnet2_utils  # noqa: E402,F401
 from .knn import KNN  # noqa: E402,F401
 from .modules import (ChamferDistanceL1, ChamferDistanceL2, ChamferDistanceL2_split,  # noqa: E402,F401
-                      ChamferFunction, Group, fps)
+                      ChamferFunction, Group, fps, interpolate_features, knn_points, propagate)
 
 __version__ = "0.1.0"
 launch_count = _lib.launch_count

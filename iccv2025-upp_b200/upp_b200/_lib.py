@@ -12,6 +12,7 @@ LIB_PATH = os.path.abspath(os.path.join(_HERE, os.pardir, "lib", "libupp_geom.so
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _sz = ctypes.c_size_t
+_f = ctypes.c_float
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/upp_geom.h
 _SIGNATURES = {
@@ -28,6 +29,9 @@ _SIGNATURES = {
     "upp_chamfer_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "upp_group_f32": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "upp_group_bwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "upp_knn_points_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "upp_interp_fwd_f32": [_vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "upp_interp_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
 }
 _RESTYPES = {
     "upp_error_string": ctypes.c_char_p,

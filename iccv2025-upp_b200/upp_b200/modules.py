@@ -5,7 +5,13 @@ signatures, return conventions and error behaviour, over the sm_100a kernels.
   Group                       models/Point_MAE_unify.py:51-92
   ChamferFunction             extensions/chamfer_dist/__init__.py:13-25
   ChamferDistanceL2/_split/L1 extensions/chamfer_dist/__init__.py:28-84
+  knn_points                  pytorch3d.ops.knn_points as called at models/Point_MAE_pretask_dev.py:680
+  propagate                   models/Point_MAE_unify.py:22-48
+  interpolate_features        the interpolation inside PointNetFeaturePropagation.forward
+                              (models/Point_MAE_unify_segment.py:289-313, models/Point_MAE_pretask_dev.py:437-461)
 """
+import collections
+
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -141,3 +147,92 @@ class ChamferDistanceL1(_ChamferBase):
     def forward(self, xyz1, xyz2):
         dist1, dist2 = self._dists(xyz1, xyz2)
         return (torch.mean(torch.sqrt(dist1)) + torch.mean(torch.sqrt(dist2))) / 2
+
+
+class _Interpolate(Function):
+    """out = (base or 0) + alpha * sum_j w_j points2[idx_j]; differentiable w.r.t. points2, base and -- through the
+    weights, as autograd is through the reference's square_distance -- xyz1 / xyz2."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, points2, base, k, eps, alpha):
+        out, idx, w, d = ops.interp_forward(xyz1, xyz2, points2, k, eps, base=base, alpha=alpha)
+        ctx.save_for_backward(xyz1, xyz2, points2, idx, w, d)
+        ctx.eps, ctx.alpha, ctx.has_base = float(eps), float(alpha), base is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xyz1, xyz2, points2, idx, w, d = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        need_xyz = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        terms = (d, points2, xyz1, xyz2, ctx.eps) if need_xyz else None
+        gp2, g1, g2 = ops.interp_backward(grad_out, idx, w, points2.size(1), alpha=ctx.alpha, xyz_terms=terms)
+        return (g1 if ctx.needs_input_grad[0] else None, g2 if ctx.needs_input_grad[1] else None,
+                gp2 if ctx.needs_input_grad[2] else None,
+                grad_out if (ctx.has_base and ctx.needs_input_grad[3]) else None, None, None, None)
+
+
+def interpolate_features(xyz1, xyz2, points2, k, eps=1e-4):
+    """The interpolation of PointNetFeaturePropagation.forward: xyz1 (B,N,3), xyz2 (B,S,3), points2 (B,S,D)
+    -> (B,N,D).  S == 1 repeats the single source row, as the reference does; k is clipped to S like the
+    reference's slice `[:, :, :k]`."""
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    if S == 1:
+        return points2.repeat(1, N, 1)
+    return _Interpolate.apply(xyz1.contiguous(), xyz2.contiguous(), points2.contiguous(), None,
+                              min(int(k), S), float(eps), 1.0)
+
+
+def propagate(xyz1, xyz2, points1, points2, de_neighbors=64, dist_e=1e-8):
+    """points1 + 0.3 * (inverse-distance interpolation of points2 over the de_neighbors nearest of xyz2);
+    same signature and defaults as the reference function.  de_neighbors is clipped to S like the reference's
+    slice; more than 32 neighbours is outside what the kernel covers (the UPP configs use 3..16) and raises."""
+    S = xyz2.shape[1]
+    return _Interpolate.apply(xyz1.contiguous(), xyz2.contiguous(), points2.contiguous(), points1.contiguous(),
+                              min(int(de_neighbors), S), float(dist_e), 0.3)
+
+
+_KNN = collections.namedtuple("KNN", "dists idx knn")  # pytorch3d's return type
+
+
+class _KnnPoints(Function):
+    """Squared distances + indices from the kernel; gradients of the distances w.r.t. both clouds
+    (d/dp1 = 2 (p1 - p2[idx]), d/dp2[idx] = -2 (p1 - p2[idx])), as pytorch3d provides."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, K):
+        d, i, _ = ops.knn_points(p1, p2, K)
+        ctx.save_for_backward(p1, p2, i)
+        ctx.mark_non_differentiable(i)
+        return d, i
+
+    @staticmethod
+    def backward(ctx, grad_d, _grad_i):
+        p1, p2, i = ctx.saved_tensors
+        B, N1, K = i.shape
+        flat = i.reshape(B, N1 * K, 1).expand(-1, -1, 3)
+        diff = p1.unsqueeze(2) - torch.gather(p2, 1, flat).view(B, N1, K, 3)
+        v = 2.0 * grad_d.unsqueeze(-1) * diff
+        g2 = torch.zeros_like(p2).scatter_add_(1, flat, -v.reshape(B, N1 * K, 3))
+        return v.sum(2), g2, None
+
+
+def knn_points(p1, p2, lengths1=None, lengths2=None, norm=2, K=1, version=-1, return_nn=False, return_sorted=True):
+    """Drop-in for pytorch3d.ops.knn_points on equal-length 3-D clouds (the UPP call site:
+    `knn_points(noise, partial, K=4, return_nn=True)`): -> KNN(dists (B,N1,K) squared ascending,
+    idx (B,N1,K) int64, knn (B,N1,K,3) or None).  Heterogeneous lengths / L1 norm are outside the path."""
+    if lengths1 is not None or lengths2 is not None:
+        raise NotImplementedError("upp_b200.knn_points covers equal-length clouds (lengths1/lengths2 = None)")
+    if norm != 2:
+        raise NotImplementedError("upp_b200.knn_points covers norm=2 (the UPP call site)")
+    p1, p2 = p1.contiguous(), p2.contiguous()
+    if not (p1.requires_grad or p2.requires_grad):
+        d, i, nn_ = ops.knn_points(p1, p2, K, want_nn=return_nn)
+        return _KNN(dists=d, idx=i, knn=nn_)
+    d, i = _KnnPoints.apply(p1, p2, int(K))
+    nn_ = None
+    if return_nn:  # knn_gather: differentiable w.r.t. p2
+        B, N1, k = i.shape
+        nn_ = torch.gather(p2, 1, i.reshape(B, N1 * k, 1).expand(-1, -1, 3)).view(B, N1, k, 3)
+    return _KNN(dists=d, idx=i, knn=nn_)

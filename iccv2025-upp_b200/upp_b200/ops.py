@@ -219,3 +219,88 @@ def group_backward(grad_nb, grad_center, idx, center_idx, N):
                                            B, int(N), G, k, _ptr(gx), _stream(grad_nb))
     _lib.check(rc, "upp_group_bwd_f32")
     return gx
+
+
+def interp_forward(xyz1, xyz2, points2, k, eps, base=None, alpha=1.0, want_dist=True):
+    """k-nearest inverse-distance interpolation of points2 (B,S,C) from xyz2 (B,S,3) onto xyz1 (B,N,3):
+    the body of propagate (models/Point_MAE_unify.py:22-48) and of PointNetFeaturePropagation's
+    interpolation (models/Point_MAE_unify_segment.py:289-313) in one launch.
+    -> out (B,N,C) = (base or 0) + alpha * interpolated, idx (B,N,k) int32, weight (B,N,k), dist (B,N,k)."""
+    _xyz("xyz1", xyz1)
+    _xyz("xyz2", xyz2)
+    _need("points2", points2, torch.float32, 3)
+    B, N, _ = xyz1.shape
+    S, C = points2.shape[1], points2.shape[2]
+    if xyz2.shape[0] != B or points2.shape[0] != B or xyz2.shape[1] != S:
+        raise ValueError(f"shape mismatch: xyz1 {tuple(xyz1.shape)}, xyz2 {tuple(xyz2.shape)}, points2 {tuple(points2.shape)}")
+    k = int(k)
+    if not 1 <= k <= min(S, 32):
+        raise ValueError(f"k={k} must be in [1, min(S={S}, 32)]")
+    if base is not None:
+        _need("base", base, torch.float32, 3)
+        if tuple(base.shape) != (B, N, C):
+            raise ValueError(f"base must be {(B, N, C)}, got {tuple(base.shape)}")
+    dev = xyz1.device
+    out = torch.empty((B, N, C), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, N, k), dtype=torch.int32, device=dev)
+    w = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+    d = torch.empty((B, N, k), dtype=torch.float32, device=dev) if want_dist else None
+    with _on(xyz1):
+        rc = _lib.load().upp_interp_fwd_f32(_ptr(xyz1), _ptr(xyz2), _ptr(points2), _ptr(base), float(alpha), float(eps),
+                                            B, N, S, C, k, _ptr(out), _ptr(idx), _ptr(w), _ptr(d), _stream(xyz1))
+    _lib.check(rc, "upp_interp_fwd_f32")
+    return out, idx, w, d
+
+
+def interp_backward(grad_out, idx, weight, S, alpha=1.0, xyz_terms=None):
+    """Gradients of interp_forward: grad_points2 (B,S,C) always; with xyz_terms = (dist, points2, xyz1, xyz2, eps)
+    also grad_xyz1 (B,N,3), grad_xyz2 (B,S,3) (the path through the weights).  Deterministic, no atomics."""
+    _need("grad_out", grad_out, torch.float32, 3)
+    _need("idx", idx, torch.int32, 3)
+    _need("weight", weight, torch.float32, 3)
+    B, N, C = grad_out.shape
+    k = idx.shape[2]
+    dev = grad_out.device
+    gp2 = torch.empty((B, int(S), C), dtype=torch.float32, device=dev)
+    g1 = g2 = gd = None
+    dist = points2 = xyz1 = xyz2 = None
+    eps = 0.0
+    if xyz_terms is not None:
+        dist, points2, xyz1, xyz2, eps = xyz_terms
+        _need("dist", dist, torch.float32, 3)
+        _need("points2", points2, torch.float32, 3)
+        _xyz("xyz1", xyz1)
+        _xyz("xyz2", xyz2)
+        g1 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        g2 = torch.empty((B, int(S), 3), dtype=torch.float32, device=dev)
+        gd = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+    with _on(grad_out):
+        rc = _lib.load().upp_interp_bwd_f32(_ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(dist), _ptr(points2),
+                                            _ptr(xyz1), _ptr(xyz2), float(alpha), float(eps), B, N, int(S), C, k,
+                                            _ptr(gp2), _ptr(g1), _ptr(g2), _ptr(gd), _stream(grad_out))
+    _lib.check(rc, "upp_interp_bwd_f32")
+    return gp2, g1, g2
+
+
+def knn_points(p1, p2, K, want_nn=False):
+    """pytorch3d.ops.knn_points convention (models/Point_MAE_pretask_dev.py:680): p1 (B,N1,3) queries,
+    p2 (B,N2,3) references -> dists (B,N1,K) f32 SQUARED ascending, idx (B,N1,K) int64 [, nn (B,N1,K,3)]."""
+    _xyz("p1", p1)
+    _xyz("p2", p2)
+    if p1.shape[0] != p2.shape[0]:
+        raise ValueError("pts1 and pts2 must have the same batch dimension.")
+    if p1.device != p2.device:
+        raise RuntimeError("p1 and p2 must be on the same device")
+    B, N1, _ = p1.shape
+    N2 = p2.shape[1]
+    K = int(K)
+    if not 1 <= K <= min(N2, 32):
+        raise ValueError(f"K={K} must be in [1, min(N2={N2}, 32)]")
+    dev = p1.device
+    d = torch.empty((B, N1, K), dtype=torch.float32, device=dev)
+    i = torch.empty((B, N1, K), dtype=torch.int64, device=dev)
+    nn = torch.empty((B, N1, K, 3), dtype=torch.float32, device=dev) if want_nn else None
+    with _on(p1):
+        rc = _lib.load().upp_knn_points_f32(_ptr(p1), _ptr(p2), B, N1, N2, K, _ptr(d), _ptr(i), _ptr(nn), _stream(p1))
+    _lib.check(rc, "upp_knn_points_f32")
+    return d, i, nn

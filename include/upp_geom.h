@@ -152,6 +152,46 @@ UPP_API int upp_group_bwd_f32(const float* grad_nb, const float* grad_center, co
                       upp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K nearest neighbours in the pytorch3d convention.
+ * Replaces pytorch3d.ops.knn_points(p1, p2, K=K, return_nn=True) (third-party, un-pinned; call site
+ *   models/Point_MAE_pretask_dev.py:680: K = 4 clean neighbours of every noise point).
+ * p1 (B,N1,3) queries, p2 (B,N2,3) references -> dist2_out (B,N1,K) f32 SQUARED distances ascending
+ * (nullable), idx_out (B,N1,K) int64 into p2, nn_out (B,N1,K,3) = p2[idx] (nullable).  Equal distances
+ * keep the lower index first.  d = fma(dz,dz,fma(dy,dy,dx*dx)).  Requires 1 <= K <= min(N2, 32).
+ */
+UPP_API int upp_knn_points_f32(const float* p1, const float* p2, int B, int N1, int N2, int K,
+                       float* dist2_out, int64_t* idx_out, float* nn_out, upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * k-nearest inverse-distance feature interpolation.
+ * Replaces the pure-torch body of
+ *   propagate(xyz1, xyz2, points1, points2, de_neighbors, dist_e)   models/Point_MAE_unify.py:22-48
+ *   PointNetFeaturePropagation.forward (interpolation part)         models/Point_MAE_unify_segment.py:289-313,
+ *                                                                   models/Point_MAE_pretask_dev.py:437-461
+ * i.e. square_distance (models/modules.py:13-32, expanded form) -> full sort -> first k ->
+ * 1/(d+eps) weights normalised -> index_points gather -> weighted sum.
+ * xyz1 (B,N,3) targets, xyz2 (B,S,3) sources, feat2 (B,S,C) channel-last source features ->
+ *   out (B,N,C) = (base ? base : 0) + alpha * sum_j weight_j * feat2[idx_j]
+ *   (propagate: base = points1, alpha = 0.3, eps = 1e-8; feature propagation: base NULL, alpha 1, eps 1e-4)
+ * idx (B,N,k) int32, weight (B,N,k), dist (B,N,k, nullable): the selection, saved for backward;
+ * neighbours ascending by (distance, source index).  Requires 1 <= k <= min(S, 32).
+ */
+UPP_API int upp_interp_fwd_f32(const float* xyz1, const float* xyz2, const float* feat2, const float* base,
+                       float alpha, float eps, int B, int N, int S, int C, int k, float* out,
+                       int32_t* idx, float* weight, float* dist, upp_stream_t stream);
+
+/* Backward of the interpolation (deterministic, no atomics).
+ * grad_feat2 (B,S,C) is OVERWRITTEN with alpha * sum_{(n,j): idx = s} weight * grad_out[b,n,:].
+ * Coordinate gradients (through the weights) are produced when gd_workspace (B*N*k floats) is given:
+ * grad_xyz1 (B,N,3) and grad_xyz2 (B,S,3) are then OVERWRITTEN (either may be NULL) and dist, feat2,
+ * xyz1, xyz2 must be the forward's; with gd_workspace == NULL those five pointers are ignored.
+ * (The gradient w.r.t. base is grad_out itself.) */
+UPP_API int upp_interp_bwd_f32(const float* grad_out, const int32_t* idx, const float* weight, const float* dist,
+                       const float* feat2, const float* xyz1, const float* xyz2, float alpha, float eps,
+                       int B, int N, int S, int C, int k, float* grad_feat2, float* grad_xyz1,
+                       float* grad_xyz2, float* gd_workspace, upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Introspection used by bench.py / tests: number of kernel launches the library has issued
  * since load (monotonic, process-wide, relaxed atomic). */
 UPP_API unsigned long long upp_launch_count(void);

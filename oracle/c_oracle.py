@@ -156,3 +156,56 @@ def group(xyz, G, k):
     if rc != 0:
         raise ValueError(f"group: k={k} must be in [1, N={N}]")
     return nb, ce, idx, cidx
+
+
+def interp_fwd(xyz1, xyz2, feat2, k, eps, base=None, alpha=1.0):
+    """propagate / PointNetFeaturePropagation interpolation (reference
+    models/Point_MAE_unify.py:22-48, models/Point_MAE_unify_segment.py:289-313).
+    -> out (B,N,C), idx (B,N,k) int32, weight (B,N,k), dist (B,N,k)."""
+    xyz1, xyz2, feat2 = _f32(xyz1), _f32(xyz2), _f32(feat2)
+    B, N, _ = xyz1.shape
+    S, C = feat2.shape[1], feat2.shape[2]
+    out = np.empty((B, N, C), dtype=np.float32)
+    idx = np.empty((B, N, k), dtype=np.int32)
+    w = np.empty((B, N, k), dtype=np.float32)
+    d = np.empty((B, N, k), dtype=np.float32)
+    bp = _p(_f32(base), _f32p) if base is not None else None
+    lib().upp_oracle_interp_fwd.restype = ctypes.c_int
+    rc = lib().upp_oracle_interp_fwd(_p(xyz1, _f32p), _p(xyz2, _f32p), _p(feat2, _f32p), bp,
+                                     ctypes.c_float(alpha), ctypes.c_float(eps), B, N, S, C, int(k),
+                                     _p(out, _f32p), _p(idx, _i32p), _p(w, _f32p), _p(d, _f32p))
+    if rc != 0:
+        raise ValueError(f"interp: k={k} must be in [1, S={S}]")
+    return out, idx, w, d
+
+
+def interp_bwd(gout, feat2, xyz1, xyz2, idx, weight, dist, eps, alpha=1.0):
+    """Analytic gradients of interp_fwd -> grad_feat2 (B,S,C), grad_xyz1 (B,N,3), grad_xyz2 (B,S,3)."""
+    gout, feat2, xyz1, xyz2 = _f32(gout), _f32(feat2), _f32(xyz1), _f32(xyz2)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    weight, dist = _f32(weight), _f32(dist)
+    B, N, C = gout.shape
+    S = feat2.shape[1]
+    k = idx.shape[2]
+    gf = np.empty((B, S, C), dtype=np.float32)
+    g1 = np.empty((B, N, 3), dtype=np.float32)
+    g2 = np.empty((B, S, 3), dtype=np.float32)
+    lib().upp_oracle_interp_bwd(_p(gout, _f32p), _p(feat2, _f32p), _p(xyz1, _f32p), _p(xyz2, _f32p),
+                                _p(idx, _i32p), _p(weight, _f32p), _p(dist, _f32p), ctypes.c_float(alpha),
+                                ctypes.c_float(eps), B, N, S, C, k, _p(gf, _f32p), _p(g1, _f32p), _p(g2, _f32p))
+    return gf, g1, g2
+
+
+def knn_points(p1, p2, K):
+    """pytorch3d.ops.knn_points(p1, p2, K=K) convention (reference models/Point_MAE_pretask_dev.py:680):
+    -> dists (B,N1,K) squared ascending, idx (B,N1,K) int64."""
+    p1, p2 = _f32(p1), _f32(p2)
+    B, N1, _ = p1.shape
+    N2 = p2.shape[1]
+    D = np.empty((B, N1, K), dtype=np.float32)
+    I = np.empty((B, N1, K), dtype=np.int64)
+    lib().upp_oracle_knn_points.restype = ctypes.c_int
+    rc = lib().upp_oracle_knn_points(_p(p1, _f32p), _p(p2, _f32p), B, N1, N2, int(K), _p(D, _f32p), _p(I, _i64p))
+    if rc != 0:
+        raise ValueError(f"knn_points: K={K} must be in [1, N2={N2}]")
+    return D, I

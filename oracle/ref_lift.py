@@ -67,3 +67,17 @@ def misc_fps(pointnet2_utils_impl):
     """The reference's own utils.misc.fps (utils/misc.py:13-20) bound to a stand-in for
     `pointnet2_ops.pointnet2_utils`."""
     return lift("utils/misc.py", ["fps"], {"pointnet2_utils": pointnet2_utils_impl}).fps
+
+
+def interpolation():
+    """The reference's own propagate (models/Point_MAE_unify.py:22-48) and PointNetFeaturePropagation
+    (models/Point_MAE_unify_segment.py:277-325), bound to its square_distance / index_points
+    (models/modules.py:13-51)."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    h = lift("models/modules.py", ["square_distance", "index_points"], {"torch": torch})
+    env = {"torch": torch, "nn": nn, "F": F, "square_distance": h.square_distance, "index_points": h.index_points}
+    p = lift("models/Point_MAE_unify.py", ["propagate"], env)
+    fp = lift("models/Point_MAE_unify_segment.py", ["PointNetFeaturePropagation"], env)
+    return types.SimpleNamespace(propagate=p.propagate, PointNetFeaturePropagation=fp.PointNetFeaturePropagation)

@@ -12,6 +12,8 @@ same geometry which run anywhere:
   farthest sampling datasets/ModelNetDataset.py:29-50 (numpy, random start; restated
                     batched in torch with start index 0 to match the CUDA op)
   Group.forward     models/Point_MAE_unify.py:58-92
+  interpolate       models/Point_MAE_unify_segment.py:289-313 / models/Point_MAE_unify.py:22-48
+                    (square_distance -> full sort -> first k -> inverse-distance weights -> index_points)
   Chamfer L1/L2     extensions/chamfer_dist/__init__.py:28-84 reductions over a
                     cdist-based nearest-neighbour distance
 
@@ -87,3 +89,13 @@ def chamfer_l2(xyz1, xyz2):
 def chamfer_l1(xyz1, xyz2):
     d1, d2 = chamfer_sq(xyz1, xyz2)
     return (d1.sqrt().mean() + d2.sqrt().mean()) / 2
+
+
+def interpolate(xyz1, xyz2, points2, k, eps):
+    """PointNetFeaturePropagation / propagate interpolation: (B,N,3),(B,S,3),(B,S,C) -> (B,N,C)."""
+    B, N, _ = xyz1.shape
+    d, idx = square_distance(xyz1, xyz2).sort(dim=-1)
+    d, idx = d[:, :, :k], idx[:, :, :k]
+    r = 1.0 / (d + eps)
+    w = r / r.sum(dim=2, keepdim=True)
+    return (index_points(points2, idx) * w.view(B, N, k, 1)).sum(dim=2)

@@ -222,7 +222,7 @@ ORACLE_API void upp_oracle_gather_grad(const float* gout, const int32_t* idx,
  * Layout: ref (B,N,3), query (B,Q,3), dist/idx (B,Q,k).  Returns -1 if k > N
  * (upstream reads out of bounds there; the replacement rejects it).
  */
-typedef struct { const float* ref; const float* query; int N, Q, k; float* dist_out; int64_t* idx_out; } knn_ctx;
+typedef struct { const float* ref; const float* query; int N, Q, k; float* dist_out; int64_t* idx_out; int squared; } knn_ctx;
 
 static void knn_cloud(int b, void* vctx) {
   const knn_ctx* c = (const knn_ctx*)vctx;
@@ -269,7 +269,7 @@ static void knn_cloud(int b, void* vctx) {
         }
       }
       for (int j = 0; j < k; ++j) {
-        dist_out[((size_t)b * Q + q) * k + j] = sqrtf(col[j]);
+        dist_out[((size_t)b * Q + q) * k + j] = c->squared ? col[j] : sqrtf(col[j]);
         idx_out[((size_t)b * Q + q) * k + j] = ind[j] - 1;
       }
     }
@@ -280,7 +280,18 @@ static void knn_cloud(int b, void* vctx) {
 ORACLE_API int upp_oracle_knn(const float* ref, const float* query, int B, int N,
                               int Q, int k, float* dist_out, int64_t* idx_out) {
   if (k > N || k <= 0) return -1;
-  knn_ctx c = {ref, query, N, Q, k, dist_out, idx_out};
+  knn_ctx c = {ref, query, N, Q, k, dist_out, idx_out, 0};
+  parallel_for(B, knn_cloud, &c);
+  return 0;
+}
+
+/* pytorch3d.ops.knn_points convention (reference call site models/Point_MAE_pretask_dev.py:680; the
+ * package itself is third-party and absent -> parity unpinned, like KNN_CUDA): same selection, SQUARED
+ * distances, p1 = queries, p2 = references. */
+ORACLE_API int upp_oracle_knn_points(const float* p1, const float* p2, int B, int N1, int N2, int K,
+                                     float* dist2_out, int64_t* idx_out) {
+  if (K > N2 || K <= 0) return -1;
+  knn_ctx c = {p2, p1, N2, N1, K, dist2_out, idx_out, 1};
   parallel_for(B, knn_cloud, &c);
   return 0;
 }
@@ -393,4 +404,113 @@ ORACLE_API int upp_oracle_group(const float* xyz, int B, int N, int G, int k,
                             center[((size_t)b * G + g) * 3 + c];
         }
   return 0;
+}
+
+/* ---- k-nearest inverse-distance interpolation ------------------------------
+ * Restates the reference's pure-torch
+ *   propagate()                         models/Point_MAE_unify.py:22-48
+ *   PointNetFeaturePropagation.forward  models/Point_MAE_unify_segment.py:289-313
+ *                                       (same code: models/Point_MAE_pretask_dev.py:437-461)
+ * on top of square_distance (models/modules.py:13-32, the EXPANDED form
+ * -2 a.b + |a|^2 + |b|^2) and index_points (models/modules.py:35-51):
+ *   dists = square_distance(xyz1, xyz2); sort ascending; keep k
+ *   dist_recip = 1/(dists + eps); weight = dist_recip / sum(dist_recip)
+ *   interpolated = sum_j index_points(points2, idx)[...,j,:] * weight[...,j]
+ *   out = (base ? base : 0) + alpha * interpolated     (propagate: base=points1, alpha=0.3)
+ * The sort is restated as a stable selection on (distance, index) -- equal
+ * distances keep the lower source index (torch.sort makes no promise there).
+ * Parity of THIS restatement against the reference's own Python: goldens made by
+ * tests/golden/make_golden.py from the lifted functions (outputs to tolerance:
+ * the matmul inside square_distance rounds differently from the fma chain here).
+ */
+static inline float sqdist_expanded(const float* a, const float* b) {
+  const float s1 = (a[0] * a[0] + a[1] * a[1]) + a[2] * a[2];
+  const float s2 = (b[0] * b[0] + b[1] * b[1]) + b[2] * b[2];
+  const float dot = fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0]));
+  return (-2.0f * dot + s1) + s2;
+}
+
+/* xyz1 (B,N,3), xyz2 (B,S,3), feat2 (B,S,C), base (B,N,C) or NULL ->
+ * out (B,N,C), idx (B,N,k) int32, weight (B,N,k), dist (B,N,k).  Returns -1 if k > S. */
+ORACLE_API int upp_oracle_interp_fwd(const float* xyz1, const float* xyz2, const float* feat2,
+                                     const float* base, float alpha, float eps, int B, int N,
+                                     int S, int C, int k, float* out, int32_t* idx, float* weight,
+                                     float* dist) {
+  if (k <= 0 || k > S) return -1;
+  float* col = (float*)malloc(sizeof(float) * (size_t)S);
+  unsigned char* used = (unsigned char*)malloc((size_t)S);
+  for (int b = 0; b < B; ++b)
+    for (int n = 0; n < N; ++n) {
+      const size_t row = (size_t)b * N + n;
+      const float* p = xyz1 + row * 3;
+      for (int s = 0; s < S; ++s) { col[s] = sqdist_expanded(p, xyz2 + ((size_t)b * S + s) * 3); used[s] = 0; }
+      float norm = 0.f;
+      for (int j = 0; j < k; ++j) { /* stable selection: strict '<' keeps the lower index */
+        int best = -1;
+        for (int s = 0; s < S; ++s)
+          if (!used[s] && (best < 0 || col[s] < col[best])) best = s;
+        used[best] = 1;
+        idx[row * k + j] = best;
+        dist[row * k + j] = col[best];
+        const float r = 1.0f / (col[best] + eps);
+        weight[row * k + j] = r;
+        norm = norm + r;
+      }
+      for (int j = 0; j < k; ++j) weight[row * k + j] = weight[row * k + j] / norm;
+      for (int c = 0; c < C; ++c) {
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j)
+          acc = acc + feat2[((size_t)b * S + idx[row * k + j]) * C + c] * weight[row * k + j];
+        float o = alpha * acc;
+        if (base) o = base[row * C + c] + o;
+        out[row * C + c] = o;
+      }
+    }
+  free(col); free(used);
+  return 0;
+}
+
+/* Analytic gradients of the forward above (what autograd derives through the reference code):
+ *   grad_feat2[b,s,:] = alpha * sum_{(n,j): idx=s} w * grad_out[b,n,:]
+ *   with G = alpha*grad_out[b,n,:], dot_j = <G, f_j>, m = sum_j w_j dot_j, r_j = 1/(d_j+eps):
+ *   g_dj = -(r_j w_j)(dot_j - m);  grad_xyz1[b,n] = sum_j g_dj 2(x1 - x2_j);  grad_xyz2[b,s] -= g_dj 2(x1 - x2_s)
+ * Accumulated in double (this is the checker, not a bit-level restatement). */
+ORACLE_API void upp_oracle_interp_bwd(const float* gout, const float* feat2, const float* xyz1,
+                                      const float* xyz2, const int32_t* idx, const float* weight,
+                                      const float* dist, float alpha, float eps, int B, int N, int S,
+                                      int C, int k, float* gfeat2, float* gxyz1, float* gxyz2) {
+  double* gf = (double*)calloc((size_t)B * S * C, sizeof(double));
+  double* g2 = (double*)calloc((size_t)B * S * 3, sizeof(double));
+  double* dot = (double*)malloc(sizeof(double) * (size_t)k);
+  for (int b = 0; b < B; ++b)
+    for (int n = 0; n < N; ++n) {
+      const size_t row = (size_t)b * N + n;
+      double m = 0.0;
+      for (int j = 0; j < k; ++j) {
+        const int s = idx[row * k + j];
+        double d = 0.0;
+        for (int c = 0; c < C; ++c) {
+          const double g = (double)alpha * gout[row * C + c];
+          d += g * feat2[((size_t)b * S + s) * C + c];
+          gf[((size_t)b * S + s) * C + c] += g * weight[row * k + j];
+        }
+        dot[j] = d;
+        m += (double)weight[row * k + j] * d;
+      }
+      double a[3] = {0, 0, 0};
+      for (int j = 0; j < k; ++j) {
+        const int s = idx[row * k + j];
+        const double r = 1.0 / ((double)dist[row * k + j] + (double)eps);
+        const double gd = -(r * weight[row * k + j]) * (dot[j] - m);
+        for (int c = 0; c < 3; ++c) {
+          const double v = gd * 2.0 * ((double)xyz1[row * 3 + c] - (double)xyz2[((size_t)b * S + s) * 3 + c]);
+          a[c] += v;
+          g2[((size_t)b * S + s) * 3 + c] -= v;
+        }
+      }
+      for (int c = 0; c < 3; ++c) gxyz1[row * 3 + c] = (float)a[c];
+    }
+  for (size_t i = 0; i < (size_t)B * S * C; ++i) gfeat2[i] = (float)gf[i];
+  for (size_t i = 0; i < (size_t)B * S * 3; ++i) gxyz2[i] = (float)g2[i];
+  free(gf); free(g2); free(dot);
 }

@@ -23,4 +23,10 @@ for _ in range(4):
     elif what == "knn":
         r = (torch.rand(32, 1024, 3, generator=g) * 2 - 1).to(dev)
         ops.knn(r, r[:, :64].contiguous(), 32)
+    elif what == "interp":
+        x1 = (torch.rand(32, 2048, 3, generator=g) * 2 - 1).to(dev)
+        x2 = (torch.rand(32, 128, 3, generator=g) * 2 - 1).to(dev)
+        p2, go = torch.randn(32, 128, 1152, generator=g).to(dev), torch.randn(32, 2048, 1152, generator=g).to(dev)
+        out, idx, w, d = ops.interp_forward(x1, x2, p2, 3, 1e-4)
+        ops.interp_backward(go, idx, w, 128, xyz_terms=(d, p2, x1, x2, 1e-4))
     torch.cuda.synchronize()

@@ -66,7 +66,7 @@ def main():
         shapes = [(32, 1228, 1024), (32, 1024, 256), (32, 64, 512), (32, 32, 512), (128, 1024, 512), (32, 2048, 512), (32, 1843, 1536),
                   (32, 1536, 512), (1, 2048, 1024), (512, 1024, 256), (32, 256, 256), (32, 128, 256), (32, 512, 256), (32, 384, 256)]
         if args.only == "big":
-            shapes = [(128, 8192, 1024), (1, 6144, 1024), (32, 4096, 512), (16, 8192, 1024)]
+            shapes = [(128, 8192, 1024), (1, 6144, 1024), (32, 4096, 512), (32, 3000, 512), (32, 2500, 512)]
             args.only = ""
         for (B, N, M) in shapes:
             x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
@@ -75,28 +75,37 @@ def main():
             rec(f"fps2-sweep B{B} N{N} M{M} v1", lambda: ops.fps(x, M), lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
             os.environ.pop("UPP_FPS_IMPL")
             rec(f"fps2-sweep B{B} N{N} M{M} v2-default", lambda: ops.fps(x, M), lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4)})
-            for nw in (1, 2, 4, 8, 16, 32):
-                p2 = (N + nw * 64 - 1) // (nw * 64)
-                if p2 > (4 if nw == 32 else 8):
-                    continue
-                for s2 in ((0,) if nw <= 2 else (1,) if nw == 32 else (0, 1)):
-                    os.environ["UPP_FPS_NW"], os.environ["UPP_FPS_P2"], os.environ["UPP_FPS_S2"] = str(nw), str(p2), str(s2)
-                    ok = bool(torch.equal(ops.fps(x, M), want))
-                    rec(f"fps2-sweep B{B} N{N} M{M} nw{nw} p2={p2} s2={s2}", lambda: ops.fps(x, M),
-                        lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
-            for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_S2"):
+            for search in (0, 2):
+                for nw in (1, 2, 4, 8, 16, 32):
+                    p2 = (N + nw * 64 - 1) // (nw * 64)
+                    if search == 2:  # deferred tree search: the instantiated large-cloud combinations
+                        if nw == 8 and p2 > 8:
+                            p2 += p2 % 2
+                        if not ((nw == 8 and 3 <= p2 <= 16) or (nw == 16 and 3 <= p2 <= 8) or (nw == 32 and 2 <= p2 <= 4)):
+                            continue
+                    elif p2 > (4 if nw == 32 else 8):
+                        continue
+                    for s2 in ((0,) if nw <= 2 else (1,) if nw == 32 else (0, 1)):
+                        os.environ["UPP_FPS_NW"], os.environ["UPP_FPS_P2"], os.environ["UPP_FPS_S2"] = str(nw), str(p2), str(s2)
+                        os.environ["UPP_FPS_SEARCH"] = str(search)
+                        ok = bool(torch.equal(ops.fps(x, M), want))
+                        rec(f"fps2-sweep B{B} N{N} M{M} nw{nw} p2={p2} s2={s2} search={search}", lambda: ops.fps(x, M),
+                            lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
+            for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_S2", "UPP_FPS_SEARCH"):
                 os.environ.pop(k, None)
         return
     if args.sweep_chamfer:
-        for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 1024, 1024), (32, 256, 256), (8, 2048, 2048)]:
+        for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 1024, 1024), (64, 32, 1024), (8, 2048, 2048)]:
             a = torch.rand(B, N, 3, generator=g).to(dev)
             b = torch.rand(B, M, 3, generator=g).to(dev)
-            for v, ch, name in [(0, 0, "2pass R2T128"), (20, 0, "1pass scalar R8W8"), (30, 1, "packed R8W4 1 chunk"), (30, 0, "packed R8W4 auto"),
+            for v, ch, name in [(0, 0, "2pass R2T128"), (30, 1, "packed R8W4 1 chunk"), (30, 0, "packed R8W4 auto"),
                                 (30, 2, "packed R8W4 2 chunks"), (30, 4, "packed R8W4 4 chunks"),
-                                (31, 0, "packed R4W8 auto"), (33, 0, "packed R6W8 auto"), (32, 0, "packed R8W8 auto(v32)"), (-1, 0, "default")]:
+                                (32, 0, "packed R8W8 auto"), (34, 0, "packed R12W4 auto"), (34, 1, "packed R12W4 1 chunk"),
+                                (35, 0, "packed R16W4 auto"), (35, 1, "packed R16W4 1 chunk"), (35, 2, "packed R16W4 2 chunks"),
+                                (36, 0, "packed R16W2 auto"), (36, 1, "packed R16W2 1 chunk"), (-1, 0, "default")]:
                 os.environ["UPP_CH_VARIANT"] = str(v)
                 os.environ["UPP_CH_CHUNKS"] = str(ch)
-                rec(f"chamfer-sweep {name} B{B} N{N} M{M}", lambda: ops.chamfer_forward(a, b),
+                rec(f"chamfer-sweep {name} B{B} N{N} M{M} +sums", lambda: ops.chamfer_forward(a, b, True),
                     lambda us: {"tflops_8NM": round(8.0 * N * M * B / us / 1e6, 2)})
             os.environ.pop("UPP_CH_CHUNKS", None)
             os.environ.pop("UPP_CH_VARIANT", None)
@@ -135,6 +144,22 @@ def main():
     for (B, N, G, k) in [(32, 1024, 64, 32), (128, 1024, 64, 32), (32, 2048, 128, 32)]:
         x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
         rec(f"group B{B} N{N} G{G} k{k}", lambda: ops.group(x, G, k))
+    for (B, N, S, C, k) in [(32, 2048, 128, 1152, 3), (32, 64, 32, 384, 8), (32, 1096, 32, 96, 16)]:
+        if args.only and "interp" not in args.only:
+            break
+        x1 = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+        x2 = (torch.rand(B, S, 3, generator=g) * 2 - 1).to(dev)
+        p2, go = torch.randn(B, S, C, generator=g).to(dev), torch.randn(B, N, C, generator=g).to(dev)
+        hbm = 4.0 * B * (N * C + S * C)
+        rec(f"interp_fwd B{B} N{N} S{S} C{C} k{k}", lambda: ops.interp_forward(x1, x2, p2, k, 1e-4),
+            lambda us: {"gbs": round(hbm / us / 1e3, 1)})
+        out, idx, w, d = ops.interp_forward(x1, x2, p2, k, 1e-4)
+        rec(f"interp_bwd_feat B{B} N{N} S{S} C{C} k{k}", lambda: ops.interp_backward(go, idx, w, S),
+            lambda us: {"gbs": round(hbm / us / 1e3, 1)})
+        rec(f"interp_bwd_feat+xyz B{B} N{N} S{S} C{C} k{k}",
+            lambda: ops.interp_backward(go, idx, w, S, xyz_terms=(d, p2, x1, x2, 1e-4)), lambda us: {"gbs": round(hbm / us / 1e3, 1)})
+    if args.only and "interp" in args.only:
+        return
     try:
         from oracle import ref_gpu
         ref = ref_gpu.load()   # the reference's own chamfer.cu, compiled unmodified (legacy default stream)

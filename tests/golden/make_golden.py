@@ -13,7 +13,12 @@ outputs are stored as small .npz files that travel to the GPU box.
                              utils/misc.py:13-20 fps and float64/numpy stand-ins for the two
                              third-party ops
 
-    python tests/golden/make_golden.py
+  golden_interp.npz          models/Point_MAE_unify.py:22-48 propagate and the interpolation of
+                             models/Point_MAE_unify_segment.py:277-325 PointNetFeaturePropagation (empty MLP),
+                             run unmodified in fp32 (outputs) and float64 (autograd gradients)
+
+    python tests/golden/make_golden.py            # everything
+    python tests/golden/make_golden.py interp     # only golden_interp.npz
 """
 import os
 import sys
@@ -63,8 +68,50 @@ class _F64Chamfer:
         return ga.to(xyz1.dtype), gb.to(xyz2.dtype)
 
 
+def make_interp():
+    """propagate + PointNetFeaturePropagation interpolation, from the reference's own code."""
+    R = ref_lift.interpolation()
+    g = torch.Generator().manual_seed(9)
+    out = {}
+    # case A: propagate(level-1 centres <- level-2 centres), de_neighbors=8, dist_e=1e-3 (models/Point_MAE_pretask_dev.py:298)
+    x1 = torch.from_numpy(lattice_cloud(3, 64, 21))
+    x2 = torch.from_numpy(lattice_cloud(3, 32, 22))
+    p1 = torch.randn(3, 64, 48, generator=g)
+    p2 = torch.randn(3, 32, 48, generator=g)
+    wgt = torch.randn(3, 64, 48, generator=g).double()  # fp32-representable loss weights
+    out.update(a_xyz1=x1.numpy(), a_xyz2=x2.numpy(), a_p1=p1.numpy(), a_p2=p2.numpy(), a_w=wgt.numpy())
+    out["a_out"] = R.propagate(x1, x2, p1, p2, de_neighbors=8, dist_e=1e-3).numpy()
+    t = [v.double().clone().requires_grad_(True) for v in (x1, x2, p1, p2)]
+    (R.propagate(*t, de_neighbors=8, dist_e=1e-3) * wgt).sum().backward()
+    for name, v in zip(("a_gx1", "a_gx2", "a_gp1", "a_gp2"), t):
+        out[name] = v.grad.numpy()
+    # case B: propagate with its defaults clipped by S (de_neighbors=6, dist_e=1e-8; models/Point_MAE_unify.py:598)
+    out["b_out"] = R.propagate(x1, x2, p1, p2, de_neighbors=6).numpy()
+    # case C: feature propagation, 3 neighbours, eps 1e-4, wide channels (models/Point_MAE_unify_segment.py:420,605-607)
+    fp = R.PointNetFeaturePropagation(in_channel=0, mlp=[], interpolate_neighbors=3)
+    y1 = torch.from_numpy(lattice_cloud(2, 200, 23))
+    y2 = torch.from_numpy(lattice_cloud(2, 40, 24))
+    q2 = torch.randn(2, 40, 36, generator=g)
+    q1 = torch.randn(2, 200, 5, generator=g)
+    out.update(c_xyz1=y1.numpy(), c_xyz2=y2.numpy(), c_p2=q2.numpy(), c_p1=q1.numpy())
+    out["c_out"] = fp(y1, y2, None, q2).detach().numpy()             # interpolated only
+    out["c_out_cat"] = fp(y1, y2, q1, q2).detach().numpy()           # cat([points1, interpolated])
+    wc = torch.randn(2, 200, 36, generator=g).double()
+    t = [v.double().clone().requires_grad_(True) for v in (y1, y2, q2)]
+    (fp(t[0], t[1], None, t[2]) * wc).sum().backward()
+    out.update(c_w=wc.numpy(), c_gx1=t[0].grad.numpy(), c_gx2=t[1].grad.numpy(), c_gp2=t[2].grad.numpy())
+    # case D: a single source point (S == 1) is repeated
+    out["d_out"] = fp(y1, y2[:, :1], None, q2[:, :1]).detach().numpy()
+    out = {k: (v.astype(np.float32) if isinstance(v, np.ndarray) and v.dtype == np.float64 else v) for k, v in out.items()}
+    np.savez_compressed(os.path.join(HERE, "golden_interp.npz"), **out)
+
+
 def main():
     assert ref_lift.available(), "needs /root/reference"
+    if sys.argv[1:] == ["interp"]:
+        make_interp()
+        return
+    make_interp()
     H = ref_lift.torch_helpers()
 
     # ---- knn_point ----

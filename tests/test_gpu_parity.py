@@ -35,7 +35,7 @@ FPS_SHAPES = [  # (B, N, M)  -- SURVEY.md Appendix A census + edges
     (3, 1, 1), (2, 5, 5), (2, 31, 7), (4, 32, 32), (4, 33, 16), (4, 64, 32), (3, 511, 64), (3, 513, 64),
     (3, 972, 32), (4, 1024, 64), (2, 1023, 256), (2, 1025, 64), (3, 1096, 32), (2, 1228, 1024),
     (2, 1459, 32), (2, 1536, 128), (2, 1624, 32), (2, 1843, 1536), (2, 2048, 128), (1, 6144, 1024),
-    (2, 8192, 1024),
+    (2, 8192, 1024), (2, 2500, 300), (2, 3000, 64), (2, 4096, 200), (2, 4100, 64), (1, 5000, 300), (1, 7000, 64),
 ]
 
 
@@ -49,6 +49,12 @@ FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
     "v2_nw16_scan": {"UPP_FPS_NW": "16", "UPP_FPS_P2": "8", "UPP_FPS_S2": "0"},
     "v2_nw16_redux": {"UPP_FPS_NW": "16", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1"},
     "v2_nw32": {"UPP_FPS_NW": "32", "UPP_FPS_P2": "4", "UPP_FPS_S2": "1"},
+    # deferred decision-tree slot search (large clouds)
+    "v2_tree_nw8_p16": {"UPP_FPS_NW": "8", "UPP_FPS_P2": "16", "UPP_FPS_S2": "0", "UPP_FPS_SEARCH": "2"},
+    "v2_tree_nw8_p12_redux": {"UPP_FPS_NW": "8", "UPP_FPS_P2": "12", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
+    "v2_tree_nw8_p5": {"UPP_FPS_NW": "8", "UPP_FPS_P2": "5", "UPP_FPS_S2": "0", "UPP_FPS_SEARCH": "2"},
+    "v2_tree_nw16_p8": {"UPP_FPS_NW": "16", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
+    "v2_tree_nw32_p4": {"UPP_FPS_NW": "32", "UPP_FPS_P2": "4", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
     "v1": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "0"},                       # round-1a strided kernels
     "v1_w4": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "1"},
 }
@@ -215,6 +221,9 @@ CH_KERNELS = {  # name -> tuning environment (read per launch by chamfer_fwd_lau
     "packed_r4": {"UPP_CH_VARIANT": "31", "UPP_CH_CHUNKS": "2"},
     "packed_r6": {"UPP_CH_VARIANT": "33"},
     "packed_w8": {"UPP_CH_VARIANT": "32"},
+    "packed_r12": {"UPP_CH_VARIANT": "34"},
+    "packed_r16": {"UPP_CH_VARIANT": "35", "UPP_CH_CHUNKS": "2"},
+    "packed_r16w2": {"UPP_CH_VARIANT": "36"},
     "scalar_single_pass": {"UPP_CH_VARIANT": "20"},                 # round-1b kernel
     "two_pass": {"UPP_CH_VARIANT": "0"},                            # directed kernel (no workspace needed)
 }
@@ -346,6 +355,25 @@ def test_chamfer_empty_and_sums(U, O, dev):
     np.testing.assert_allclose(sums.cpu().numpy(), want, rtol=1e-5)
 
 
+@pytest.mark.parametrize("B,N,M", [(5, 700, 900), (5, 900, 700), (64, 32, 1024), (3, 1024, 32), (2, 2048, 2048),
+                                   (2, 40, 50), (1, 1, 300), (7, 257, 4099)])
+def test_chamfer_partial_sums_every_path(U, dev, chamfer_path, B, N, M):
+    """{sum d1, sum d2, sum sqrt d1, sum sqrt d2} from the fused finalize (packed paths: ticketed two-level
+    reduction) or the cluster kernel (other paths): right slot whichever cloud became the row side,
+    identical bits run to run, and the dist/idx outputs unchanged by asking for the sums."""
+    g = torch.Generator().manual_seed(B * 1000 + N + M)
+    a, b = torch.rand(B, N, 3, generator=g).to(dev), torch.rand(B, M, 3, generator=g).to(dev)
+    d1, d2, i1, i2, sums = U.ops.chamfer_forward(a, b, want_sums=True)
+    e1, e2, j1, j2 = U.ops.chamfer_forward(a, b)
+    assert torch.equal(d1, e1) and torch.equal(d2, e2) and torch.equal(i1, j1) and torch.equal(i2, j2)
+    want = np.array([d1.double().sum().item(), d2.double().sum().item(),
+                     d1.double().sqrt().sum().item(), d2.double().sqrt().sum().item()])
+    np.testing.assert_allclose(sums.cpu().numpy(), want, rtol=2e-5)
+    for _ in range(3):
+        again = U.ops.chamfer_forward(a, b, want_sums=True)[4]
+        assert torch.equal(again, sums), "partial sums must be run-to-run deterministic"
+
+
 # ------------------------------------------------------------------ Group --------------------
 
 
@@ -453,3 +481,134 @@ def test_golden_reference_group_forward(U, dev, fused):
     assert np.array_equal(nb.cpu().numpy(), g["neighborhood"]) and np.array_equal(ce.cpu().numpy(), g["center"])
     _, _, fidx, fcidx = grp(x, require_index=True, gather_idx=False)
     assert np.array_equal(fidx.cpu().numpy(), g["flat_idx"]) and np.array_equal(fcidx.cpu().numpy(), g["flat_center_idx"])
+
+
+# ------------------------------------------------------------------ interpolation ---
+
+INTERP_SHAPES = [  # (B, N targets, S sources, C channels, k)
+    (3, 64, 32, 384, 8),      # Block propagate: level-1 <- level-2 centres (models/Point_MAE_pretask_dev.py:298)
+    (3, 32, 32, 384, 6),      # completion propagate de_neighbors=6 (models/Point_MAE_unify.py:598)
+    (2, 2048, 128, 1152, 3),  # seg feature propagation (models/Point_MAE_unify_segment.py:420,605-607)
+    (2, 1096, 32, 96, 16),    # rectify prompter propagation (models/Point_MAE_pretask_dev.py:454-461)
+    (2, 100, 2500, 10, 5),    # more sources than one staged tile; C not a multiple of 4
+    (1, 7, 3, 1, 3), (2, 33, 40, 4, 1), (2, 5, 64, 2304, 32),
+]
+
+
+@pytest.mark.parametrize("B,N,S,C,k", INTERP_SHAPES)
+@pytest.mark.parametrize("with_base", [False, True])
+def test_interp_forward_matches_oracle(U, O, dev, B, N, S, C, k, with_base):
+    g = torch.Generator().manual_seed(N * 31 + S)
+    x1, x2 = torch.rand(B, N, 3, generator=g) * 2 - 1, torch.rand(B, S, 3, generator=g) * 2 - 1
+    p2 = torch.randn(B, S, C, generator=g)
+    base = torch.randn(B, N, C, generator=g) if with_base else None
+    alpha, eps = (0.3, 1e-3) if with_base else (1.0, 1e-4)
+    out, idx, w, d = U.ops.interp_forward(x1.to(dev), x2.to(dev), p2.to(dev), k, eps,
+                                          base=base.to(dev) if with_base else None, alpha=alpha)
+    o_out, o_idx, o_w, o_d = O.interp_fwd(x1.numpy(), x2.numpy(), p2.numpy(), k, eps,
+                                          base=base.numpy() if with_base else None, alpha=alpha)
+    assert idx.dtype == torch.int32 and np.array_equal(idx.cpu().numpy(), o_idx)   # bit-exact selection
+    assert np.array_equal(d.cpu().numpy(), o_d) and np.array_equal(w.cpu().numpy(), o_w)
+    np.testing.assert_allclose(out.cpu().numpy(), o_out, rtol=RTOL, atol=1e-6)
+
+
+def test_interp_ties_and_coincident_points(U, O, dev):
+    """Targets that ARE sources (level-2 centres are a subset of level-1 centres) and lattice ties."""
+    ax = torch.arange(4, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3).repeat(2, 1, 1)
+    x2 = grid[:, ::2].contiguous()
+    p2 = torch.randn(2, x2.shape[1], 8, generator=torch.Generator().manual_seed(2))
+    for eps in (1e-8, 1e-4):
+        out, idx, w, d = U.ops.interp_forward(grid.to(dev), x2.to(dev), p2.to(dev), 6, eps)
+        o_out, o_idx, o_w, o_d = O.interp_fwd(grid.numpy(), x2.numpy(), p2.numpy(), 6, eps)
+        assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(w.cpu().numpy(), o_w)
+        np.testing.assert_allclose(out.cpu().numpy(), o_out, rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,N,S,C,k", [(3, 64, 32, 384, 8), (2, 700, 48, 1152, 3), (2, 300, 2100, 24, 16), (1, 9, 4, 2500, 4)])
+def test_interp_backward_matches_oracle_and_is_deterministic(U, O, dev, B, N, S, C, k):
+    g = torch.Generator().manual_seed(S + C)
+    x1, x2 = torch.rand(B, N, 3, generator=g) * 2 - 1, torch.rand(B, S, 3, generator=g) * 2 - 1
+    p2, go = torch.randn(B, S, C, generator=g), torch.randn(B, N, C, generator=g)
+    eps, alpha = 1e-3, 0.3
+    out, idx, w, d = U.ops.interp_forward(x1.to(dev), x2.to(dev), p2.to(dev), k, eps, alpha=alpha)
+    terms = (d, p2.to(dev), x1.to(dev), x2.to(dev), eps)
+    gp2, g1, g2 = U.ops.interp_backward(go.to(dev), idx, w, S, alpha=alpha, xyz_terms=terms)
+    o_gp2, o_g1, o_g2 = O.interp_bwd(go.numpy(), p2.numpy(), x1.numpy(), x2.numpy(), idx.cpu().numpy(),
+                                     w.cpu().numpy(), d.cpu().numpy(), eps, alpha=alpha)
+    scale = max(1.0, float(np.abs(o_gp2).max()))
+    np.testing.assert_allclose(gp2.cpu().numpy(), o_gp2, rtol=1e-4, atol=1e-5 * scale)
+    for got, want in ((g1, o_g1), (g2, o_g2)):
+        s = max(1e-6, float(np.abs(want).max()))
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-3, atol=2e-4 * s)
+    only_feat, n1, n2 = U.ops.interp_backward(go.to(dev), idx, w, S, alpha=alpha)
+    assert n1 is None and n2 is None and torch.equal(only_feat, gp2)
+    for _ in range(2):  # atomic-free: bit-identical run to run
+        a, b1, b2 = U.ops.interp_backward(go.to(dev), idx, w, S, alpha=alpha, xyz_terms=terms)
+        assert torch.equal(a, gp2) and torch.equal(b1, g1) and torch.equal(b2, g2)
+
+
+def test_golden_reference_propagate_and_feature_propagation(U, dev):
+    """The reference's own propagate / PointNetFeaturePropagation outputs and float64 autograd gradients
+    (tests/golden/golden_interp.npz) against the drop-in functions, autograd included."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_interp.npz"))
+    T = lambda k: torch.from_numpy(g[k]).to(dev)  # noqa: E731
+    t = [T(k).requires_grad_(True) for k in ("a_xyz1", "a_xyz2", "a_p1", "a_p2")]
+    out = U.propagate(*t, de_neighbors=8, dist_e=1e-3)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["a_out"], rtol=1e-5, atol=2e-6)
+    (out * T("a_w")).sum().backward()
+    for v, name, tol in zip(t, ("a_gx1", "a_gx2", "a_gp1", "a_gp2"), (1e-3, 1e-3, 1e-6, 1e-4)):
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g[name], rtol=tol, atol=tol * max(1.0, float(np.abs(g[name]).max())) * 0.1)
+    np.testing.assert_allclose(U.propagate(T("a_xyz1"), T("a_xyz2"), T("a_p1"), T("a_p2"), de_neighbors=6).cpu().numpy(),
+                               g["b_out"], rtol=1e-5, atol=2e-6)
+    t = [T(k).requires_grad_(True) for k in ("c_xyz1", "c_xyz2", "c_p2")]
+    out = U.interpolate_features(t[0], t[1], t[2], 3, eps=1e-4)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["c_out"], rtol=1e-5, atol=2e-6)
+    (out * T("c_w")).sum().backward()
+    for v, name, tol in zip(t, ("c_gx1", "c_gx2", "c_gp2"), (1e-3, 1e-3, 1e-4)):
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g[name], rtol=tol, atol=tol * max(1.0, float(np.abs(g[name]).max())) * 0.1)
+    one = U.interpolate_features(T("c_xyz1"), T("c_xyz2")[:, :1].contiguous(), T("c_p2")[:, :1].contiguous(), 3)
+    np.testing.assert_allclose(one.cpu().numpy(), g["d_out"], rtol=0, atol=0)  # S == 1: repeated
+    with pytest.raises(ValueError):
+        U.ops.interp_forward(T("a_xyz1"), T("a_xyz2"), T("a_p2"), 33, 1e-3)
+    with pytest.raises(RuntimeError):
+        U.ops.interp_forward(T("a_xyz1").cpu(), T("a_xyz2"), T("a_p2"), 3, 1e-3)
+
+
+# ------------------------------------------------------------------ knn_points (SURVEY 8f row 4) -----
+
+@pytest.mark.parametrize("B,N1,N2,K", [(4, 20, 1024, 4), (2, 52, 1076, 4), (3, 100, 64, 8), (2, 7, 5, 5), (2, 300, 2500, 32), (1, 1, 1, 1)])
+def test_knn_points_matches_oracle(U, O, dev, B, N1, N2, K):
+    """pytorch3d convention (models/Point_MAE_pretask_dev.py:680): squared distances ascending, int64 idx, nn gather."""
+    g = torch.Generator().manual_seed(N1 + N2)
+    p1, p2 = torch.rand(B, N1, 3, generator=g) * 2 - 1, torch.rand(B, N2, 3, generator=g) * 2 - 1
+    out = U.knn_points(p1.to(dev), p2.to(dev), K=K, return_nn=True)
+    D, I = O.knn_points(p1.numpy(), p2.numpy(), K)
+    assert out.idx.dtype == torch.int64 and np.array_equal(out.idx.cpu().numpy(), I)
+    assert np.array_equal(out.dists.cpu().numpy(), D)                       # same fma spelling: bit-exact
+    want_nn = np.take_along_axis(p2.numpy()[:, None], I[..., None].repeat(3, -1), 2)
+    assert np.array_equal(out.knn.cpu().numpy(), want_nn)
+    assert U.knn_points(p1.to(dev), p2.to(dev), K=K).knn is None
+    # float64 brute force: same neighbours wherever the gap to the next candidate exceeds fp32 rounding
+    d64 = ((p1.double()[:, :, None] - p2.double()[:, None]) ** 2).sum(-1)
+    np.testing.assert_allclose(out.dists.cpu().numpy(), np.sort(d64.numpy(), -1)[..., :K], rtol=1e-5, atol=1e-7)
+
+
+def test_knn_points_autograd_and_errors(U, dev):
+    g = torch.Generator().manual_seed(5)
+    p1 = (torch.rand(2, 30, 3, generator=g)).to(dev).requires_grad_(True)
+    p2 = (torch.rand(2, 90, 3, generator=g)).to(dev).requires_grad_(True)
+    out = U.knn_points(p1, p2, K=4, return_nn=True)
+    wd, wn = torch.rand_like(out.dists), torch.rand_like(out.knn)
+    ((out.dists * wd).sum() + (out.knn * wn).sum()).backward()
+    q1, q2 = p1.detach().double().requires_grad_(True), p2.detach().double().requires_grad_(True)
+    nn64 = torch.gather(q2, 1, out.idx.reshape(2, -1, 1).expand(-1, -1, 3)).view(2, 30, 4, 3)
+    d64 = ((q1.unsqueeze(2) - nn64) ** 2).sum(-1)
+    ((d64 * wd.double()).sum() + (nn64 * wn.double()).sum()).backward()
+    torch.testing.assert_close(p1.grad.double(), q1.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(p2.grad.double(), q2.grad, rtol=1e-4, atol=1e-6)
+    with pytest.raises(ValueError):
+        U.knn_points(p1.detach(), p2.detach(), K=91)
+    with pytest.raises(NotImplementedError):
+        U.knn_points(p1.detach(), p2.detach(), K=4, lengths1=torch.tensor([30, 30]))

@@ -210,3 +210,65 @@ def test_reference_chamfer_modules_run_unmodified_over_oracle():
     loss.backward()
     assert abs(loss.item() - g["l1_loss"]) <= 1e-5 * g["l1_loss"]
     np.testing.assert_allclose(a.grad.numpy(), g["l1_g1"], rtol=2e-4, atol=1e-8)
+
+
+# ---------------------------------------------------------------- interpolation ---
+
+def _interp_case(g, tag):
+    if tag == "a":
+        return dict(xyz1=g["a_xyz1"], xyz2=g["a_xyz2"], p2=g["a_p2"], base=g["a_p1"], k=8, eps=1e-3, alpha=0.3, out=g["a_out"])
+    if tag == "b":
+        return dict(xyz1=g["a_xyz1"], xyz2=g["a_xyz2"], p2=g["a_p2"], base=g["a_p1"], k=6, eps=1e-8, alpha=0.3, out=g["b_out"])
+    return dict(xyz1=g["c_xyz1"], xyz2=g["c_xyz2"], p2=g["c_p2"], base=None, k=3, eps=1e-4, alpha=1.0, out=g["c_out"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_golden_interp_forward_reference_python(tag):
+    """oracle interp_fwd == the reference's own propagate / PointNetFeaturePropagation (run unmodified,
+    tests/golden/make_golden.py) on lattice clouds whose distances are exact in either formula."""
+    c = _interp_case(gold("golden_interp.npz"), tag)
+    out, idx, w, d = O.interp_fwd(c["xyz1"], c["xyz2"], c["p2"], c["k"], c["eps"], base=c["base"], alpha=c["alpha"])
+    np.testing.assert_allclose(out, c["out"], rtol=1e-5, atol=2e-6)
+    assert (np.diff(d, axis=-1) >= 0).all() and np.allclose(w.sum(-1), 1.0, atol=1e-6)
+
+
+def test_golden_interp_backward_reference_autograd():
+    """oracle interp_bwd == float64 autograd through the reference's own code."""
+    g = gold("golden_interp.npz")
+    out, idx, w, d = O.interp_fwd(g["a_xyz1"], g["a_xyz2"], g["a_p2"], 8, 1e-3, base=g["a_p1"], alpha=0.3)
+    gf, g1, g2 = O.interp_bwd(g["a_w"], g["a_p2"], g["a_xyz1"], g["a_xyz2"], idx, w, d, 1e-3, alpha=0.3)
+    np.testing.assert_allclose(gf, g["a_gp2"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(g1, g["a_gx1"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(g2, g["a_gx2"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(g["a_w"], g["a_gp1"], rtol=0, atol=0)  # d out / d points1 is the identity
+    out, idx, w, d = O.interp_fwd(g["c_xyz1"], g["c_xyz2"], g["c_p2"], 3, 1e-4)
+    gf, g1, g2 = O.interp_bwd(g["c_w"], g["c_p2"], g["c_xyz1"], g["c_xyz2"], idx, w, d, 1e-4)
+    np.testing.assert_allclose(gf, g["c_gp2"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(g1, g["c_gx1"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(g2, g["c_gx2"], rtol=1e-3, atol=1e-4)
+
+
+def test_interp_known_answers():
+    # target coincides with a source: that source dominates (weight -> 1 as eps -> 0)
+    xyz2 = np.array([[[0, 0, 0], [1, 0, 0], [0, 2, 0], [0, 0, 3]]], np.float32)
+    xyz1 = np.array([[[1, 0, 0], [0.5, 0, 0]]], np.float32)
+    f2 = np.array([[[10.0], [20.0], [30.0], [40.0]]], np.float32)
+    out, idx, w, d = O.interp_fwd(xyz1, xyz2, f2, 2, 1e-8)
+    assert idx[0, 0, 0] == 1 and abs(out[0, 0, 0] - 20.0) < 1e-4
+    # equidistant pair: the tie keeps the lower index first and the weights are equal
+    assert list(idx[0, 1]) == [0, 1] and np.allclose(w[0, 1], 0.5) and abs(out[0, 1, 0] - 15.0) < 1e-5
+    with pytest.raises(ValueError):
+        O.interp_fwd(xyz1, xyz2, f2, 5, 1e-8)
+
+
+@pytest.mark.skipif(not ref_lift.available(), reason="needs /root/reference")
+def test_interp_oracle_vs_live_reference_random_clouds():
+    """Random (non-lattice) clouds: indices may differ from the torch formula only on near-ties; values agree
+    to tolerance wherever they coincide (they do, at this seed)."""
+    R = ref_lift.interpolation()
+    g = torch.Generator().manual_seed(3)
+    x1, x2 = torch.rand(2, 150, 3, generator=g), torch.rand(2, 48, 3, generator=g)
+    p1, p2 = torch.randn(2, 150, 16, generator=g), torch.randn(2, 48, 16, generator=g)
+    want = R.propagate(x1, x2, p1, p2, de_neighbors=8, dist_e=1e-3).numpy()
+    out, *_ = O.interp_fwd(x1.numpy(), x2.numpy(), p2.numpy(), 8, 1e-3, base=p1.numpy(), alpha=0.3)
+    np.testing.assert_allclose(out, want, rtol=1e-4, atol=1e-4)
