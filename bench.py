@@ -97,6 +97,18 @@ class GpuWorkload:
         self.B = next(iter(host.values())).shape[0]
         self.collect = None  # when set: list collecting (label, fn, args, kwargs) of every labelled op
         self.side = [torch.cuda.Stream(device=dev) for _ in range(2)]  # independent branches of the step
+        # N > 1: the loss all-reduce runs inside the Chamfer kernels over NVLink peer memory when the peers'
+        # buffers can be mapped (parallel.PeerExchange); otherwise one NCCL all-reduce of 16 bytes
+        self.peers, self.collective = None, "none (1 GPU)"
+        self.no_exchange = os.environ.get("UPP_BENCH_DIAG_NO_EXCHANGE") == "1"  # diagnosis only: loss stays local
+        if world > 1 and self.no_exchange:
+            self.collective = "DIAGNOSTIC RUN WITHOUT THE LOSS ALL-REDUCE -- not a valid bench configuration"
+        elif world > 1:
+            try:
+                self.peers = upp_b200.parallel.PeerExchange()
+                self.collective = f"fused in the Chamfer finalize kernel over NVLink peer memory ({self.peers.how})"
+            except RuntimeError as ex:
+                self.collective = f"NCCL all_reduce of 4 floats (peer mapping unavailable: {str(ex)[:80]})"
         U = upp_b200
         self.g32_16, self.g64_32, self.g32_8 = U.Group(32, 16), U.Group(64, 32), U.Group(32, 8)
         self.g128_32 = U.Group(128, 32)
@@ -120,7 +132,7 @@ class GpuWorkload:
 
     def h2d_bytes(self):
         keys = {"upp_cls_geometry+chamfer": ("pts", "rebuild", "target"), "c5": ("pts",)}.get(self.name, tuple(self.host))
-        return sum(self.host[k].numel() * 4 for k in keys), keys
+        return sum((self.host[k].numel() + 3) // 4 * 16 for k in keys), keys
 
     # -- ops-level step --
     def run_ops(self, d):
@@ -140,9 +152,12 @@ class GpuWorkload:
                 t("group N32 G32 k16", o.group, g1[1], 32, 16)
                 t("group N972 G32 k16", o.group, keep, 32, 16)
             with torch.cuda.stream(self.side[1]):
-                d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward, d["rebuild"], d["target"], True)
-                if self.world > 1:
-                    self.par.reduce_sums(sums)
+                if self.peers is not None:
+                    d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward_sharded, d["rebuild"], d["target"], self.peers)
+                else:
+                    d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward, d["rebuild"], d["target"], True)
+                    if self.world > 1 and not self.no_exchange:
+                        self.par.reduce_sums(sums)
                 loss = (sums[2] + sums[3]) / (2.0 * nglob)
                 gd1 = (0.25 / nglob) / torch.sqrt(d1)
                 gd2 = (0.25 / nglob) / torch.sqrt(d2)
@@ -152,12 +167,12 @@ class GpuWorkload:
             i2, c2 = t("fps N1228 M1024", o.fps, cat, 1024, True)
             g4 = t("group N1024 G64 k32", o.group, c2, 64, 32)
             g5 = t("group N64 G32 k8", o.group, g4[1], 32, 8)
-            # backward chain: G5 -> G4 -> fps(1228->1024) gather -> fps(1024->256) gather
+            # backward chain: G5 -> G4 -> fps(1228->1024) gather -> fps(1024->256) gather (row-major scatter-adds)
             gc4 = t("group_bwd N64", o.group_backward, torch.zeros_like(g5[0]), d["w_c5"], g5[2], g5[3], 64)
             gx = t("group_bwd N1024", o.group_backward, d["w_nb"], gc4, g4[2], g4[3], 1024)
-            gcat = t("gather_grad N1228", o.gather_grad, gx.transpose(1, 2).contiguous(), i2, 1228)
-            gc1 = gcat[:, :, 972:].contiguous()
-            greb = t("gather_grad N1024", o.gather_grad, gc1, i1, 1024).transpose(1, 2)
+            gcat = t("fps_gather_bwd N1228", o.rows_scatter_add, gx, i2, 1228)
+            gc1 = gcat[:, 972:].contiguous()
+            greb = t("fps_gather_bwd N1024", o.rows_scatter_add, gc1, i1, 1024)
             self._join(cur)
             self.grad = ga + greb
             self.keepalive = (g1, g4, g5, d1, d2)
@@ -167,9 +182,12 @@ class GpuWorkload:
             return ce[0, 0, 0]
         if n == "c3":
             nglob = float(self.B * self.world * 2048)
-            d1, d2, j1, j2, sums = t("chamfer_fwd N2048 M2048", o.chamfer_forward, d["xyz1"], d["xyz2"], True)
-            if self.world > 1:
-                self.par.reduce_sums(sums)
+            if self.peers is not None:
+                d1, d2, j1, j2, sums = t("chamfer_fwd N2048 M2048", o.chamfer_forward_sharded, d["xyz1"], d["xyz2"], self.peers)
+            else:
+                d1, d2, j1, j2, sums = t("chamfer_fwd N2048 M2048", o.chamfer_forward, d["xyz1"], d["xyz2"], True)
+                if self.world > 1:
+                    self.par.reduce_sums(sums)
             gd1, gd2 = (0.25 / nglob) / torch.sqrt(d1), (0.25 / nglob) / torch.sqrt(d2)
             self.grad = t("chamfer_bwd N2048 M2048", o.chamfer_backward, d["xyz1"], d["xyz2"], j1, j2, gd1, gd2)
             return (sums[2] + sums[3]) / (2.0 * nglob)
@@ -197,7 +215,7 @@ class GpuWorkload:
                 self.g32_16(keep)
             with torch.cuda.stream(self.side[1]):
                 if self.world > 1:
-                    cd = self.par.sharded_chamfer(reb, d["target"], "l1", n_global_clouds=self.B * self.world)
+                    cd = self.par.sharded_chamfer(reb, d["target"], "l1", n_global_clouds=self.B * self.world, peers=self.peers)
                 else:
                     cd = self.cd_l1(reb, d["target"])
             c1, _ = U.fps(reb, 256)
@@ -213,7 +231,7 @@ class GpuWorkload:
             a = d["xyz1"].detach().requires_grad_(True)
             b = d["xyz2"].detach().requires_grad_(True)
             if self.world > 1:
-                loss = self.par.sharded_chamfer(a, b, "l1", n_global_clouds=self.B * self.world)
+                loss = self.par.sharded_chamfer(a, b, "l1", n_global_clouds=self.B * self.world, peers=self.peers)
             else:
                 loss = self.cd_l1(a, b)
             loss.backward()
@@ -254,7 +272,7 @@ def op_work(label):
         return 0.0, 4.0 * N * C + 4.0 * S * C + 12.0 * (N + S) + 12.0 * N * k
     if kind == "group_bwd":
         return 0.0, 0.0
-    if kind == "gather_grad":
+    if kind in ("gather_grad", "fps_gather_bwd"):
         return 0.0, 0.0
     return 0.0, 0.0
 
@@ -407,6 +425,7 @@ def main():
 
     host = make_inputs(args.workload, B, seed=rank)
     W = GpuWorkload(args.workload, host, dev, world)
+    config["collective"] = W.collective
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -467,9 +486,19 @@ def main():
     #      (torch.cuda.graph, static input buffers) and replayed; eager launches if capture fails.
     h2d_bytes, h2d_keys = W.h2d_bytes()
     dd = dict(W.d)
+    # the step's inputs live in ONE pinned host arena and one device arena (16-byte aligned views): a single
+    # H2D copy per step instead of one per tensor
+    offs, total = {}, 0
     for k in h2d_keys:
-        dd[k] = torch.empty_like(W.d[k])
-        dd[k].copy_(W.host[k])
+        offs[k] = total
+        total += (W.host[k].numel() + 3) // 4 * 4
+    host_arena = torch.empty(total, dtype=torch.float32).pin_memory()
+    dev_arena = torch.empty(total, dtype=torch.float32, device=dev)
+    for k in h2d_keys:
+        n = W.host[k].numel()
+        host_arena[offs[k]:offs[k] + n].copy_(W.host[k].reshape(-1))
+        dd[k] = dev_arena[offs[k]:offs[k] + n].view(W.host[k].shape)
+    dev_arena.copy_(host_arena)
     e2e_graph, e2e_loss, e2e_mode = None, None, "eager"
     if not args.no_graph:
         try:
@@ -490,8 +519,7 @@ def main():
             torch.cuda.synchronize()
 
     def e2e_step():
-        for k in h2d_keys:
-            dd[k].copy_(W.host[k], non_blocking=True)      # H2D of this step's inputs (pinned)
+        dev_arena.copy_(host_arena, non_blocking=True)     # H2D of this step's inputs (pinned, one copy)
         if e2e_graph is not None:
             e2e_graph.replay()
             return e2e_loss.item()                          # D2H of the step's result
@@ -548,6 +576,9 @@ def main():
     # max over ranks
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
+        config["ms_per_step_by_rank"] = [round(float(v[0]) / args.steps, 5) for v in per_rank]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:

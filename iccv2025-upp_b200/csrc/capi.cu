@@ -13,7 +13,7 @@ int fps_launch(const float*, int, int, int, int32_t*, float*, void*, size_t, cud
 size_t fps_workspace_bytes(int, int);
 int knn_launch(const float*, const float*, int, int, int, int, float*, int64_t*, float*, cudaStream_t);
 int chamfer_fwd_launch(const float*, const float*, int, int, int, float*, float*, int32_t*, int32_t*,
-                       float*, void*, size_t, cudaStream_t);
+                       float*, void*, size_t, const upp_peer_exchange*, cudaStream_t);
 size_t chamfer_fwd_workspace_bytes(int, int, int);
 int chamfer_bwd_launch(const float*, const float*, const int32_t*, const int32_t*, const float*,
                        const float*, int, int, int, float*, float*, cudaStream_t);
@@ -21,6 +21,7 @@ int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cuda
 int gather_grad_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int group_gather_launch(const float*, const float*, const int64_t*, int, int, int, int, float*,
                         cudaStream_t);
+int rows_scatter_add_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int group_bwd_launch(const float*, const float*, const int64_t*, const int32_t*, int, int, int, int,
                      float*, cudaStream_t);
 
@@ -89,6 +90,15 @@ int upp_gather_grad_f32(const float* grad_out, const int32_t* idx, int B, int C,
   return gather_grad_launch(grad_out, idx, B, C, N, M, grad_features, S(stream));
 }
 
+int upp_rows_scatter_add_f32(const float* grad_rows, const int32_t* idx, int B, int N, int M, int C,
+                             float* grad, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && C >= 0);
+  if (static_cast<size_t>(B) * N * C == 0) return UPP_OK;
+  UPP_REQUIRE(grad != nullptr);
+  UPP_REQUIRE(static_cast<size_t>(B) * M * C == 0 || (grad_rows && idx));
+  return rows_scatter_add_launch(grad_rows, idx, B, N, M, C, grad, S(stream));
+}
+
 int upp_knn_f32(const float* ref, const float* query, int B, int N, int Q, int k, float* dist_out,
                 int64_t* idx_out, upp_stream_t stream) {
   UPP_REQUIRE(B >= 0 && N >= 0 && Q >= 0);
@@ -116,7 +126,19 @@ int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int N, int 
   }
   UPP_REQUIRE(xyz1 && xyz2);
   return chamfer_fwd_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, partial_sums, workspace,
-                            workspace_bytes, S(stream));
+                            workspace_bytes, nullptr, S(stream));
+}
+
+int upp_chamfer_fwd_sharded_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
+                                float* dist2, int32_t* idx1, int32_t* idx2, float* global_sums, void* workspace,
+                                size_t workspace_bytes, const upp_peer_exchange* peers, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 1 && N >= 1 && M >= 1);  // every rank must contribute to the exchange: no empty shards
+  UPP_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2 && global_sums && peers);
+  UPP_REQUIRE(peers->world >= 1 && peers->world <= UPP_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world);
+  UPP_REQUIRE(peers->world == 1 || peers->seq != nullptr);
+  for (int r = 0; r < peers->world && peers->world > 1; ++r) UPP_REQUIRE(peers->slots[r] != nullptr);
+  return chamfer_fwd_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, global_sums, workspace, workspace_bytes,
+                            peers, S(stream));
 }
 
 int upp_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,

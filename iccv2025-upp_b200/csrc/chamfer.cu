@@ -460,6 +460,74 @@ __global__ void __launch_bounds__(256)
 // draws the last ticket adds the partials in index order.  Fixed partition + fixed order: the value
 // is identical run to run whichever CTA happens to be last.  The ticket word sits behind the keys and
 // is preset to 0xFFFFFFFF by the same memset node, so the last of T CTAs draws ticket T - 2 (mod 2^32).
+// ---- fused all-reduce of the 4 sums over NVLink peer memory (batch sharded across GPUs) ----------------
+// Every rank owns an exchange buffer slots[2][world][8 floats] that all ranks have mapped (CUDA IPC).  The CTA
+// that finishes a rank's local sums stores them, tagged with the call's sequence number, into slot
+// [seq & 1][rank] of EVERY rank's buffer (plain NVLink stores, release at system scope), then waits until its own
+// buffer holds the tag in all `world` slots and adds the world's contributions in RANK ORDER -- every rank
+// computes bit-identical global sums, deterministically, with no NCCL launch and no host involvement.
+// Two parities make slot reuse safe: rank r can only write call s+2 after it has finished call s+1, which needed
+// every peer's call-s+1 contribution, which a peer sends only after it has read call s.
+struct PeerXchg {
+  float* slots[UPP_MAX_PEERS];  // slots[r] = rank r's exchange buffer (device pointer valid in THIS process)
+  int rank, world;
+  unsigned* seq;                // this rank's call counter (device memory, zero before the first call)
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by ONE CTA (256 threads) after `local` (4 floats, thread 0's registers) is final.  Returns the global
+// sums in thread 0.
+__device__ __forceinline__ void peer_allreduce4(const PeerXchg& px, float (&v)[4], float (*s_x)[4]) {
+  __shared__ unsigned s_seq;
+  if (threadIdx.x == 0) {
+    s_seq = *px.seq + 1u;
+    *px.seq = s_seq;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s_x[0][q] = v[q];
+  }
+  __syncthreads();
+  const unsigned seq = s_seq;
+  const int t = threadIdx.x;
+  if (t < px.world) {
+    // send: my contribution into slot [parity][rank] of peer t
+    float* dst = px.slots[t] + ((seq & 1u) * px.world + px.rank) * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(s_x[0][0], s_x[0][1], s_x[0][2], s_x[0][3]);
+    st_release_sys_u32(reinterpret_cast<unsigned*>(dst + 4), seq);
+  }
+  __syncthreads();
+  if (t < px.world) {
+    // receive: rank t's contribution from my own buffer
+    const float* src = px.slots[px.rank] + ((seq & 1u) * px.world + t) * 8;
+    // bounded wait (~3 s of SM clocks): a peer that never arrives poisons the sums with NaN instead of hanging
+    const long long t0 = clock64();
+    bool ok = true;
+    while (ld_acquire_sys_u32(reinterpret_cast<const unsigned*>(src + 4)) != seq) {
+      if (clock64() - t0 > (6LL << 30)) { ok = false; break; }
+    }
+    const volatile float* vs = src;  // after the acquire: the payload written before the tag
+    const float nan = __int_as_float(0x7fc00000);
+    s_x[1 + t][0] = ok ? vs[0] : nan; s_x[1 + t][1] = ok ? vs[1] : nan;
+    s_x[1 + t][2] = ok ? vs[2] : nan; s_x[1 + t][3] = ok ? vs[3] : nan;
+  }
+  __syncthreads();
+  if (t == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float tot = 0.f;
+      for (int r = 0; r < px.world; ++r) tot += s_x[1 + r][q];
+      v[q] = tot;
+    }
+  }
+}
+
 __device__ __forceinline__ float2 block_sum2_256(float a, float b, float2* s_w) {
   a = warp_sum(a);
   b = warp_sum(b);
@@ -483,9 +551,10 @@ __global__ void __launch_bounds__(256)
                              float* __restrict__ distA, int32_t* __restrict__ idxA,
                              float* __restrict__ distB, int32_t* __restrict__ idxB,
                              float2* __restrict__ partials, unsigned* __restrict__ ticket,
-                             float* __restrict__ sums, int swapped) {
+                             float* __restrict__ sums, int swapped, const PeerXchg px) {
   __shared__ float2 s_w[8];
   __shared__ bool s_last;
+  __shared__ float s_x[1 + UPP_MAX_PEERS][4];
   const int side = blockIdx.z;  // 0: B (columns), 1: A (rows)
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,6 +602,7 @@ __global__ void __launch_bounds__(256)
   if (!s_last) return;
   __threadfence();
   // last CTA: side 0 = cloud B, side 1 = cloud A; output order { d1, d2, sqrt d1, sqrt d2 }
+  float loc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int sd = 0; sd < 2; ++sd) {
     float a0 = 0.f, a1 = 0.f;
     if (sd < static_cast<int>(gridDim.z)) {
@@ -543,11 +613,14 @@ __global__ void __launch_bounds__(256)
       }
     }
     const float2 tot = block_sum2_256(a0, a1, s_w);
-    if (threadIdx.x == 0) {
-      const int first = (sd == 1) != (swapped != 0);  // is this side the caller's xyz1?
-      sums[first ? 0 : 1] = tot.x;
-      sums[first ? 2 : 3] = tot.y;
-    }
+    const int first = (sd == 1) != (swapped != 0);  // is this side the caller's xyz1?
+    loc[first ? 0 : 1] = tot.x;                     // (valid in thread 0)
+    loc[first ? 2 : 3] = tot.y;
+  }
+  if (px.world > 1) peer_allreduce4(px, loc, s_x);  // sums of the WHOLE sharded batch, same bits on every rank
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sums[q] = loc[q];
   }
 }
 
@@ -733,7 +806,7 @@ static int chamfer_pick_chunks(long items0, int NB) {
 template <int R, int WC>
 static int launch_chamfer_packed(const float* a, const float* bpts, int B, int NA, int NB, float* dA,
                                  int32_t* iA, float* dB, int32_t* iB, void* ws, int force_chunks,
-                                 float* sums, bool swapped, cudaStream_t st) {
+                                 float* sums, bool swapped, const PeerXchg& px, cudaStream_t st) {
   static_assert(R <= 16, "chamfer_finalize2_kernel scans at most 16 rows per key");
   const int na8 = (NA + 7) & ~7, nb8 = (NB + 7) & ~7;
   const int rowblocks = (NA + 32 * R - 1) / (32 * R);
@@ -757,7 +830,7 @@ static int launch_chamfer_packed(const float* a, const float* bpts, int B, int N
   const bool rows_too = chunks > 1 || sums != nullptr;
   dim3 fgrid(((rows_too ? max(NA, NB) : NB) + 255) / 256, B, rows_too ? 2 : 1);
   chamfer_finalize2_kernel<<<fgrid, 256, 0, st>>>(a, bpts, NA, NB, na8, nb8, colkeys, rowkeys, R, dA, iA, dB, iB,
-                                                  sums ? partials : nullptr, ticket, sums, swapped ? 1 : 0);
+                                                  sums ? partials : nullptr, ticket, sums, swapped ? 1 : 0, px);
   count_launch();
   return launch_status();
 }
@@ -787,13 +860,26 @@ static int env_chunks() {
 
 int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                        float* dist2, int32_t* idx1, int32_t* idx2, float* sums, void* workspace,
-                       size_t workspace_bytes, cudaStream_t st) {
+                       size_t workspace_bytes, const upp_peer_exchange* peers, cudaStream_t st) {
+  PeerXchg px;
+  px.world = 1;
+  px.rank = 0;
+  px.seq = nullptr;
+  for (int r = 0; r < UPP_MAX_PEERS; ++r) px.slots[r] = nullptr;
+  if (peers != nullptr && peers->world > 1) {
+    px.world = peers->world;
+    px.rank = peers->rank;
+    px.seq = peers->seq;
+    for (int r = 0; r < peers->world; ++r) px.slots[r] = peers->slots[r];
+  }
   const char* v = getenv("UPP_CH_VARIANT");  // tuning aid
   const int variant = v ? atoi(v) : -1;
   const bool have_ws = workspace != nullptr && workspace_bytes >= chamfer_fwd_workspace_bytes(B, N, M);
   // single pass: rows = the larger cloud (fills the 32*R-row tiles), columns = the smaller one (any size);
   // two tiny clouds stay on the directed kernel
   const bool single = have_ws && max(N, M) >= 128 && (variant < 0 || variant >= 20);
+  // the fused peer all-reduce lives in the packed path's finalize kernel
+  if (px.world > 1 && !(single && (variant < 0 || variant >= 30) && sums != nullptr)) return UPP_ERR_UNSUPPORTED;
   if (single) {
     // rows = the larger cloud (more CTAs), columns = the smaller one (fewer keys)
     const bool swap = M > N;
@@ -812,14 +898,14 @@ int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M
       case 20: rc = launch_chamfer_both<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
       case 21: rc = launch_chamfer_both<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
       case 22: rc = launch_chamfer_both<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, st); break;
-      case 31: rc = launch_chamfer_packed<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
-      case 32: rc = launch_chamfer_packed<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
-      case 33: rc = launch_chamfer_packed<6, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
+      case 31: rc = launch_chamfer_packed<4, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 32: rc = launch_chamfer_packed<8, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 33: rc = launch_chamfer_packed<6, 8>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
       // measured best on B200: 8 rows per thread, 4 warps per CTA (5 CTAs / SM)
-      case 34: rc = launch_chamfer_packed<12, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
-      case 35: rc = launch_chamfer_packed<16, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
-      case 36: rc = launch_chamfer_packed<16, 2>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
-      default: rc = launch_chamfer_packed<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, st); break;
+      case 34: rc = launch_chamfer_packed<12, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 35: rc = launch_chamfer_packed<16, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 36: rc = launch_chamfer_packed<16, 2>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      default: rc = launch_chamfer_packed<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
     }
     if (rc != UPP_OK) return rc;
     if (pick >= 30) return UPP_OK;  // the packed path's finalize kernel has produced the sums too

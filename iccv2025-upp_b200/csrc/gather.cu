@@ -78,6 +78,20 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// grad[b, idx[b,j], :] += rows[b,j,:]  (row-major / channel-last; the gradient of the coordinate gather fused
+// into upp_fps_f32's centers_out, i.e. of utils/misc.py:19 without its two transposes)
+__global__ void __launch_bounds__(256)
+    rows_scatter_add_kernel(const float* __restrict__ rows, const int32_t* __restrict__ idx, int N, int M, int C,
+                            size_t total, float* __restrict__ grad) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t bj = i / C;  // b*M + j
+    const size_t b = bj / M;
+    atomicAdd(grad + (b * N + __ldg(idx + bj)) * C + c, __ldg(rows + i));
+  }
+}
+
 static int grid_for(size_t total, int per_block) {
   const size_t want = (total + per_block - 1) / per_block;
   const size_t cap = 148 * 16;
@@ -100,6 +114,17 @@ int gather_grad_launch(const float* gout, const int32_t* idx, int B, int C, int 
   if (e != cudaSuccess) return static_cast<int>(e);
   if (total == 0) return UPP_OK;
   gather_points_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(gout, idx, C, N, M, total, gfeat);
+  count_launch();
+  return launch_status();
+}
+
+int rows_scatter_add_launch(const float* rows, const int32_t* idx, int B, int N, int M, int C, float* grad,
+                            cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(grad, 0, static_cast<size_t>(B) * N * C * sizeof(float), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const size_t total = static_cast<size_t>(B) * M * C;
+  if (total == 0) return UPP_OK;
+  rows_scatter_add_kernel<<<grid_for(total, 256), 256, 0, st>>>(rows, idx, N, M, C, total, grad);
   count_launch();
   return launch_status();
 }

@@ -25,19 +25,73 @@ namespace upp {
 // sums as packed fp32x2 (FMUL2 / FADD2: bit-identical to the scalar mul-then-add of the torch expression).
 constexpr int kInterpCB = 8;  // float4 channel blocks per super-block (1024 channels)
 
+// CB x 128 channels starting at cs for one target: neighbours four at a time (weight / row pointer shuffled once),
+// CB independent LDG.128 in flight per neighbour.  GUARD: lanes past the last channel are masked (remainder block).
+template <int CB, bool GUARD>
+__device__ __forceinline__ void interp_gather_blocks(const float* __restrict__ fb, const float* __restrict__ brow,
+                                                     float* __restrict__ orow, int C, int cs, int k, float w, int li,
+                                                     float alpha) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = cs + lane * 4;
+  f32x2 acc[CB][2];
+#pragma unroll
+  for (int u = 0; u < CB; ++u) acc[u][0] = acc[u][1] = pack2(0.f, 0.f);
+  for (int j0 = 0; j0 < k; j0 += 4) {  // warp-uniform: every lane joins the shuffles
+    float wj[4];
+    const float* fj[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int jj = min(j0 + v, k - 1);
+      wj[v] = __shfl_sync(0xffffffffu, w, jj);
+      fj[v] = fb + static_cast<size_t>(__shfl_sync(0xffffffffu, li, jj)) * C + c0;
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (j0 + v < k) {  // warp-uniform
+        const f32x2 W2 = pack2(wj[v], wj[v]);
+#pragma unroll
+        for (int u = 0; u < CB; ++u) {
+          if (!GUARD || c0 + u * 128 < C) {
+            const ulonglong2 f = __ldg(reinterpret_cast<const ulonglong2*>(fj[v] + u * 128));
+            acc[u][0] = add2(acc[u][0], mul2(f.x, W2));
+            acc[u][1] = add2(acc[u][1], mul2(f.y, W2));
+          }
+        }
+      }
+    }
+  }
+  const f32x2 A2 = pack2(alpha, alpha);
+#pragma unroll
+  for (int u = 0; u < CB; ++u) {
+    const int c = c0 + u * 128;
+    if (!GUARD || c < C) {
+      ulonglong2 o;
+      o.x = mul2(A2, acc[u][0]);
+      o.y = mul2(A2, acc[u][1]);
+      if (brow) {
+        const ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(brow + c));
+        o.x = add2(p.x, o.x);
+        o.y = add2(p.y, o.y);
+      }
+      *reinterpret_cast<ulonglong2*>(orow + c) = o;
+    }
+  }
+}
+
+// `tpw` targets per warp: a CTA serves 8 * tpw consecutive targets of one cloud from ONE staging of the sources
+// (single-tile clouds, S <= 2048; larger source clouds run tpw = 1 through the tile loop) -- the per-CTA start-up
+// (barrier init, TMA round trip) otherwise dominates a warp whose own work is ~1 us.
 template <bool VEC4, int SLOTS>
-__global__ void __launch_bounds__(kKnnWarps * kWarp)
+__global__ void __launch_bounds__(kKnnWarps * kWarp, 3)
     interp_fwd_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                       const float* __restrict__ feat2, const float* __restrict__ base, float alpha, float eps,
-                      int N, int S, int C, int k, float* __restrict__ out, int32_t* __restrict__ idx_out,
+                      int N, int S, int C, int k, int tpw, float* __restrict__ out, int32_t* __restrict__ idx_out,
                       float* __restrict__ w_out, float* __restrict__ d_out) {
   extern __shared__ __align__(16) float s_ref[];  // min(S, kKnnTile) * 3 floats
   __shared__ __align__(8) uint64_t s_bar;
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int b = blockIdx.y;
-  const int n = blockIdx.x * kKnnWarps + warp;
-  const bool active = n < N;
   const float* rb = xyz2 + static_cast<size_t>(b) * S * 3;
 
   if (threadIdx.x == 0) {
@@ -46,7 +100,12 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
   }
   __syncthreads();
   unsigned parity = 0;
+  const bool single_tile = S <= kKnnTile;
+  if (single_tile) stage_points(s_ref, rb, S, &s_bar, parity);
 
+  for (int it = 0; it < tpw; ++it) {
+  const int n = (blockIdx.x * tpw + it) * kKnnWarps + warp;
+  const bool active = n < N;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   if (active) {
     const float* qp = xyz1 + (static_cast<size_t>(b) * N + n) * 3;
@@ -58,8 +117,22 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
   dist.set(qx, qy, qz);
   float ld;
   int li;
-  warp_topk_scan<DistExpanded, SLOTS>(rb, S, k, dist, active, s_ref, &s_bar, parity, ld, li);
-  if (!active) return;
+  if (single_tile) {
+    if (SLOTS <= 8 && k <= 8) {  // one block of sources, few neighbours: k warp arg-min rounds
+      ld = __int_as_float(0x7f800000);
+      li = 0;
+      if (active) warp_topk_small<DistExpanded, SLOTS>(s_ref, S, k, dist, ld, li);
+    } else {
+      TopkState st;
+      st.init();
+      if (active) warp_topk_tile<DistExpanded, SLOTS>(s_ref, S, 0, k, dist, st);
+      ld = st.ld;
+      li = st.li;
+    }
+  } else {
+    warp_topk_scan<DistExpanded, SLOTS>(rb, S, k, dist, active, s_ref, &s_bar, parity, ld, li);
+  }
+  if (!active) continue;
 
   // weights: dist_recip = 1/(d + eps); weight = dist_recip / sum(dist_recip)  (sum in neighbour order)
   const float r = lane < k ? __fdiv_rn(1.0f, __fadd_rn(ld, eps)) : 0.f;
@@ -78,51 +151,11 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
   float* orow = out + row * C;
   const float* brow = base ? base + row * C : nullptr;
   if (VEC4) {
-    for (int cs = 0; cs < C; cs += kInterpCB * 128) {  // warp-uniform trip counts: every lane joins the shuffles
-      f32x2 acc[kInterpCB][2];
-#pragma unroll
-      for (int u = 0; u < kInterpCB; ++u) acc[u][0] = acc[u][1] = pack2(0.f, 0.f);
-      for (int j0 = 0; j0 < k; j0 += 4) {
-        float wj[4];
-        const float* fj[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int jj = min(j0 + v, k - 1);
-          wj[v] = __shfl_sync(0xffffffffu, w, jj);
-          fj[v] = fb + static_cast<size_t>(__shfl_sync(0xffffffffu, li, jj)) * C + cs + lane * 4;
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          if (j0 + v < k) {  // warp-uniform
-            const f32x2 W2 = pack2(wj[v], wj[v]);
-#pragma unroll
-            for (int u = 0; u < kInterpCB; ++u) {
-              if (cs + u * 128 + lane * 4 < C) {
-                const ulonglong2 f = __ldg(reinterpret_cast<const ulonglong2*>(fj[v] + u * 128));
-                acc[u][0] = add2(acc[u][0], mul2(f.x, W2));
-                acc[u][1] = add2(acc[u][1], mul2(f.y, W2));
-              }
-            }
-          }
-        }
-      }
-      const f32x2 A2 = pack2(alpha, alpha);
-#pragma unroll
-      for (int u = 0; u < kInterpCB; ++u) {
-        const int c = cs + u * 128 + lane * 4;
-        if (c < C) {
-          ulonglong2 o;
-          o.x = mul2(A2, acc[u][0]);
-          o.y = mul2(A2, acc[u][1]);
-          if (brow) {
-            const ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(brow + c));
-            o.x = add2(p.x, o.x);
-            o.y = add2(p.y, o.y);
-          }
-          *reinterpret_cast<ulonglong2*>(orow + c) = o;
-        }
-      }
-    }
+    // full super-blocks of 8 x 128 channels, then the remainder in blocks of 128 (lane guard only there)
+    int cs = 0;
+    for (; cs + kInterpCB * 128 <= C; cs += kInterpCB * 128)
+      interp_gather_blocks<kInterpCB, false>(fb, brow, orow, C, cs, k, w, li, alpha);
+    for (; cs < C; cs += 128) interp_gather_blocks<1, true>(fb, brow, orow, C, cs, k, w, li, alpha);
   } else {
     for (int c0 = 0; c0 < C; c0 += 32) {  // warp-uniform trip count (shuffles inside)
       const int c = c0 + lane;
@@ -139,6 +172,7 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
       }
     }
   }
+  }  // targets of this warp
 }
 
 // Backward, target side (only when coordinate gradients are wanted).  With G = alpha * grad_out[b,n,:],
@@ -356,13 +390,18 @@ __global__ void __launch_bounds__(kSrcThreads)
 int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, const float* base, float alpha,
                       float eps, int B, int N, int S, int C, int k, float* out, int32_t* idx, float* weight,
                       float* distk, cudaStream_t st) {
-  dim3 grid((N + kKnnWarps - 1) / kKnnWarps, B);
+  // targets per warp: as many as keep >= 4 residency waves (3 CTAs x 148 SMs) of CTAs in the grid
+  int tpw = 1;
+  if (S <= kKnnTile)
+    for (int cand = 8; cand > 1; cand >>= 1)
+      if (static_cast<long>(B) * ((N + kKnnWarps * cand - 1) / (kKnnWarps * cand)) >= 4L * 3 * 148) { tpw = cand; break; }
+  dim3 grid((N + kKnnWarps * tpw - 1) / (kKnnWarps * tpw), B);
   const size_t smem = static_cast<size_t>(min(S, kKnnTile)) * 3 * sizeof(float);
   const bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat2) | reinterpret_cast<uintptr_t>(out) |
                                       reinterpret_cast<uintptr_t>(base)) % 16 == 0);
   const int threads = kKnnWarps * kWarp;
 #define UPP_INTERP(V_, SL_) \
-  interp_fwd_kernel<V_, SL_><<<grid, threads, smem, st>>>(xyz1, xyz2, feat2, base, alpha, eps, N, S, C, k, out, idx, weight, distk)
+  interp_fwd_kernel<V_, SL_><<<grid, threads, smem, st>>>(xyz1, xyz2, feat2, base, alpha, eps, N, S, C, k, tpw, out, idx, weight, distk)
   if (vec4) {
     if (S <= 128) UPP_INTERP(true, 4);
     else if (S <= 256) UPP_INTERP(true, 8);

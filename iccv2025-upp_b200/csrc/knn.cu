@@ -62,7 +62,14 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
   dist.set(qx, qy, qz);
   float ld;  // lane i: squared distance of the i-th nearest
   int li;    //         and its reference index
-  warp_topk_scan<DistDirect, SLOTS>(rb, N, k, dist, active, s_ref, &s_bar, parity, ld, li);
+  if (SLOTS <= 8 && k <= 8) {  // the whole cloud is one block and few neighbours are wanted: warp arg-min rounds
+    stage_points(s_ref, rb, N, &s_bar, parity);
+    ld = __int_as_float(0x7f800000);
+    li = 0;
+    if (active) warp_topk_small<DistDirect, SLOTS>(s_ref, N, k, dist, ld, li);
+  } else {
+    warp_topk_scan<DistDirect, SLOTS>(rb, N, k, dist, active, s_ref, &s_bar, parity, ld, li);
+  }
   if (active && lane < k) {
     const size_t o = (static_cast<size_t>(b) * Q + q) * k + lane;
     if (dist_out) dist_out[o] = RAW ? ld : __fsqrt_rn(ld);

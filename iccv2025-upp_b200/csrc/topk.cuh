@@ -66,81 +66,147 @@ __device__ __forceinline__ void warp_bitonic_sort(float& d, int& i, int lane) {
   }
 }
 
-// Scans the N references of one cloud (rb, AoS) for the k (<= 32) nearest to this warp's query.
-// Every thread of the CTA must call it (the tile staging uses __syncthreads); warps with
-// active == false only help staging.  On return lane j < k holds the j-th nearest (ld, li).
+// Running selection of one warp: lane i holds the i-th best so far, plus the warp-uniform k-th best.
+struct TopkState {
+  float ld;
+  int li;
+  float thr_d;
+  int thr_i;
+  bool seeded;
+  __device__ __forceinline__ void init() {
+    ld = thr_d = __int_as_float(0x7f800000);
+    li = thr_i = 0x7fffffff;
+    seeded = false;
+  }
+};
+
+// One staged tile (s_ref holds `tile` references whose first has cloud index `base`) through the selection.
 // SLOTS = distances per lane per block (block = 32 * SLOTS references): 32 for large clouds; 4 / 8 keep the
 // unrolled loops short when the whole cloud is at most 128 / 256 points.
-template <class Dist, int SLOTS = kKnnSlots>
-__device__ __forceinline__ void warp_topk_scan(const float* __restrict__ rb, int N, int k, const Dist& dist,
-                                               bool active, float* s_ref, uint64_t* s_bar, unsigned& parity,
-                                               float& ld, int& li) {
+template <class Dist, int SLOTS>
+__device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int base, int k, const Dist& dist,
+                                               TopkState& st) {
   const int lane = threadIdx.x & 31;
   const float kInf = __int_as_float(0x7f800000);
-  ld = kInf;           // lane i: distance of the i-th best so far
-  li = 0x7fffffff;     //         and its reference index
-  float thr_d = kInf;  // current k-th best (warp-uniform)
-  int thr_i = 0x7fffffff;
-  bool seeded = false;
-
-  for (int base = 0; base < N; base += kKnnTile) {
-    const int tile = min(kKnnTile, N - base);
-    if (base > 0) __syncthreads();  // everyone done reading the previous tile
-    stage_points(s_ref, rb + static_cast<size_t>(base) * 3, tile, s_bar, parity);
-    if (!active) continue;
-    for (int blk = 0; blk < tile; blk += SLOTS * kWarp) {
-      // ---- 1. distances of this block into registers; slot s <-> ref index blk + s*32 + lane ----
-      float d[SLOTS];
-      float lmin = kInf;
-      int lmin_s = 0;
+  for (int blk = 0; blk < tile; blk += SLOTS * kWarp) {
+    // ---- 1. distances of this block into registers; slot s <-> ref index blk + s*32 + lane ----
+    float d[SLOTS];
+    float lmin = kInf;
+    int lmin_s = 0;
 #pragma unroll
-      for (int s = 0; s < SLOTS; ++s) {
-        const int c = blk + s * kWarp + lane;
-        d[s] = kInf;
-        if (blk + s * kWarp < tile) {  // warp-uniform guard, then the per-lane tail
-          if (c < tile) d[s] = dist(s_ref[3 * c], s_ref[3 * c + 1], s_ref[3 * c + 2]);
-          if (d[s] < lmin) { lmin = d[s]; lmin_s = s; }  // strict '<': lowest index among equal minima
-        }
+    for (int s = 0; s < SLOTS; ++s) {
+      const int c = blk + s * kWarp + lane;
+      d[s] = kInf;
+      if (blk + s * kWarp < tile) {  // warp-uniform guard, then the per-lane tail
+        if (c < tile) d[s] = dist(s_ref[3 * c], s_ref[3 * c + 1], s_ref[3 * c + 2]);
+        if (d[s] < lmin) { lmin = d[s]; lmin_s = s; }  // strict '<': lowest index among equal minima
       }
-      // ---- 2. seed the list with the sorted lane minima (first block only) ----
-      if (!seeded) {
-        seeded = true;
-        ld = lmin;
-        li = lmin < kInf ? base + blk + lmin_s * kWarp + lane : 0x7fffffff;
-        warp_bitonic_sort(ld, li, lane);
+    }
+    // ---- 2. seed the list with the sorted lane minima (first block only) ----
+    if (!st.seeded) {
+      st.seeded = true;
+      st.ld = lmin;
+      st.li = lmin < kInf ? base + blk + lmin_s * kWarp + lane : 0x7fffffff;
+      warp_bitonic_sort(st.ld, st.li, lane);
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s)
-          if (s == lmin_s) d[s] = kInf;  // consumed
-        thr_d = __shfl_sync(0xffffffffu, ld, k - 1);
-        thr_i = __shfl_sync(0xffffffffu, li, k - 1);
-      }
-      // ---- 3. stream the register slots through the threshold filter ----
+      for (int s = 0; s < SLOTS; ++s)
+        if (s == lmin_s) d[s] = kInf;  // consumed
+      st.thr_d = __shfl_sync(0xffffffffu, st.ld, k - 1);
+      st.thr_i = __shfl_sync(0xffffffffu, st.li, k - 1);
+    }
+    // ---- 3. stream the register slots through the threshold filter ----
 #pragma unroll
-      for (int s = 0; s < SLOTS; ++s) {
-        if (blk + s * kWarp < tile) {  // warp-uniform
-          const int myi = base + blk + s * kWarp + lane;
-          unsigned m = __ballot_sync(0xffffffffu, key_less(d[s], myi, thr_d, thr_i));
-          if (m != 0) {
-            while (m) {
-              const int src = __ffs(m) - 1;
-              m &= m - 1;
-              const float cd = __shfl_sync(0xffffffffu, d[s], src);
-              const int ci = base + blk + s * kWarp + src;
-              const float ud = __shfl_up_sync(0xffffffffu, ld, 1);
-              const int ui = __shfl_up_sync(0xffffffffu, li, 1);
-              // entries greater than the candidate shift right by one; the first of them is replaced
-              const bool mine_gt = key_less(cd, ci, ld, li);
-              const bool left_gt = (lane > 0) && key_less(cd, ci, ud, ui);
-              li = mine_gt ? (left_gt ? ui : ci) : li;
-              ld = mine_gt ? (left_gt ? ud : cd) : ld;
-            }
-            thr_d = __shfl_sync(0xffffffffu, ld, k - 1);
-            thr_i = __shfl_sync(0xffffffffu, li, k - 1);
+    for (int s = 0; s < SLOTS; ++s) {
+      if (blk + s * kWarp < tile) {  // warp-uniform
+        const int myi = base + blk + s * kWarp + lane;
+        unsigned m = __ballot_sync(0xffffffffu, key_less(d[s], myi, st.thr_d, st.thr_i));
+        if (m != 0) {
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(0xffffffffu, d[s], src);
+            const int ci = base + blk + s * kWarp + src;
+            const float ud = __shfl_up_sync(0xffffffffu, st.ld, 1);
+            const int ui = __shfl_up_sync(0xffffffffu, st.li, 1);
+            // entries greater than the candidate shift right by one; the first of them is replaced
+            const bool mine_gt = key_less(cd, ci, st.ld, st.li);
+            const bool left_gt = (lane > 0) && key_less(cd, ci, ud, ui);
+            st.li = mine_gt ? (left_gt ? ui : ci) : st.li;
+            st.ld = mine_gt ? (left_gt ? ud : cd) : st.ld;
           }
+          st.thr_d = __shfl_sync(0xffffffffu, st.ld, k - 1);
+          st.thr_i = __shfl_sync(0xffffffffu, st.li, k - 1);
         }
       }
     }
   }
+}
+
+// Small problems (the whole cloud in ONE block of 32 * SLOTS references, few neighbours): k rounds of a warp
+// arg-min instead of the sort-and-stream machinery -- per round two REDUX.MIN (value on a monotone unsigned image
+// of the float, then lowest index among the lanes that hold it) and the winning lane retires its slot; ~25
+// instructions per neighbour against ~400 for seeding + streaming.  Same total order (distance, index).
+__device__ __forceinline__ unsigned float_to_ordered(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+template <class Dist, int SLOTS>
+__device__ __forceinline__ void warp_topk_small(const float* s_ref, int n, int k, const Dist& dist, float& ld,
+                                                int& li) {
+  const int lane = threadIdx.x & 31;
+  const float kInf = __int_as_float(0x7f800000);
+  float d[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int c = s * kWarp + lane;
+    d[s] = kInf;
+    if (s * kWarp < n && c < n) d[s] = dist(s_ref[3 * c], s_ref[3 * c + 1], s_ref[3 * c + 2]);
+  }
+  ld = kInf;
+  li = 0x7fffffff;
+  for (int r = 0; r < k; ++r) {
+    float lmin = d[0];
+    int ls = 0;
+#pragma unroll
+    for (int s = 1; s < SLOTS; ++s)
+      if (d[s] < lmin) { lmin = d[s]; ls = s; }  // strict '<': lowest slot == lowest index within the lane
+    const unsigned key = float_to_ordered(lmin);
+    const unsigned wmin = redux_min_u32(key);
+    const unsigned cand = key == wmin ? static_cast<unsigned>(ls * kWarp + lane) : 0xffffffffu;
+    const unsigned widx = redux_min_u32(cand);
+    if (lane == r) {
+      ld = ordered_to_float(wmin);
+      li = static_cast<int>(widx);
+    }
+    if (cand == widx) {
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s)
+        if (s == ls) d[s] = kInf;  // retired
+    }
+  }
+}
+
+// Scans the N references of one cloud (rb, AoS) for the k (<= 32) nearest to this warp's query.
+// Every thread of the CTA must call it (the tile staging uses __syncthreads); warps with
+// active == false only help staging.  On return lane j < k holds the j-th nearest (ld, li).
+template <class Dist, int SLOTS = kKnnSlots>
+__device__ __forceinline__ void warp_topk_scan(const float* __restrict__ rb, int N, int k, const Dist& dist,
+                                               bool active, float* s_ref, uint64_t* s_bar, unsigned& parity,
+                                               float& ld, int& li) {
+  TopkState st;
+  st.init();
+  for (int base = 0; base < N; base += kKnnTile) {
+    const int tile = min(kKnnTile, N - base);
+    if (base > 0) __syncthreads();  // everyone done reading the previous tile
+    stage_points(s_ref, rb + static_cast<size_t>(base) * 3, tile, s_bar, parity);
+    if (active) warp_topk_tile<Dist, SLOTS>(s_ref, tile, base, k, dist, st);
+  }
+  ld = st.ld;
+  li = st.li;
 }
 
 }  // namespace upp

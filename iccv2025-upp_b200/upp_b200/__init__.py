@@ -7,6 +7,7 @@ reference's own operator API.
     fps, Group, ChamferFunction, ChamferDistanceL1/L2/L2_split (reference Python, mirrored)
     propagate, interpolate_features                            (kNN inverse-distance feature interpolation)
     knn_points                                                 (pytorch3d.ops.knn_points convention)
+    misc.seprate_point_cloud                                   (batched crop + FPS, utils/misc.py:205-256)
     parallel                                                   (batch sharding + NCCL loss all-reduce)
 
 Everything computes in libupp_geom.so (hand-written CUDA); importing this package without the
@@ -16,7 +17,7 @@ from . import _lib
 
 _lib.load()  # fail loudly, at import, if the CUDA library is missing
 
-from . import chamfer, ops, parallel, pointnet2_utils  # noqa: E402,F401
+from . import chamfer, misc, ops, parallel, pointnet2_utils  # noqa: E402,F401
 from .knn import KNN  # noqa: E402,F401
 from .modules import (ChamferDistanceL1, ChamferDistanceL2, ChamferDistanceL2_split,  # noqa: E402,F401
                       ChamferFunction, Group, fps, interpolate_features, knn_points, propagate)

@@ -1,0 +1,67 @@
+"""Host-side mirror of the reference's utils/misc.py helpers that sit on the FPS path.
+
+  fps                   utils/misc.py:13-20      (re-exported from modules)
+  seprate_point_cloud   utils/misc.py:205-256    
+
+The reference's seprate_point_cloud walks the batch in a Python loop and, per cloud, sorts the points by
+distance to a random viewpoint, crops, and calls fps() on (1, n - num_crop, 3) and (1, num_crop, 3): 2*B
+one-CTA FPS launches per training step (tools/runner_module.py:131, tools/runner_pretask.py:179,
+tools/runner_unify_seg.py:212).  num_crop is drawn ONCE per call, so every cloud of the batch has the same two
+lengths: here the sort, the gathers and the two FPS calls run once for the whole batch (two B-CTA launches).
+The random viewpoints are drawn exactly as the reference draws them (one torch.randn(1,1,3) per cloud from the
+CPU generator, random.sample for a list of fixed points), so a seeded run selects the same crops.
+"""
+import random
+
+import torch
+import torch.nn.functional as F
+
+from .modules import fps
+
+__all__ = ["fps", "seprate_point_cloud"]
+
+
+def seprate_point_cloud(xyz, num_points, crop, fixed_points=None, padding_zeros=False, sample_points=1024,
+                        incomplete_shape=True):
+    """Same signature, return convention and RNG consumption as the reference function:
+    -> (input_data (B, n_in, 3), crop_data (B, n_crop, 3)), both contiguous; (xyz, None) when crop == num_points."""
+    _, n, c = xyz.shape
+    assert n == num_points
+    assert c == 3
+    if crop == num_points:
+        return xyz, None
+    if isinstance(crop, list):
+        num_crop = random.randint(crop[0], crop[1])
+    else:
+        num_crop = crop
+    B = xyz.shape[0]
+    centers = []
+    for _ in range(B):  # per-cloud draws, in the reference's order
+        if fixed_points is None:
+            center = F.normalize(torch.randn(1, 1, 3), p=2, dim=-1)
+        else:
+            if isinstance(fixed_points, list):
+                fixed_point = random.sample(fixed_points, 1)[0]
+            else:
+                fixed_point = fixed_points
+            center = fixed_point.reshape(1, 1, 3)
+        centers.append(center.to(xyz.device, xyz.dtype))
+    centers = torch.cat(centers, 0)                                                     # (B,1,3)
+    distance_matrix = torch.norm(centers.unsqueeze(2) - xyz.unsqueeze(1), p=2, dim=-1)  # (B,1,n)
+    idx = torch.argsort(distance_matrix, dim=-1, descending=False)[:, 0]                # (B,n)
+    take = lambda ix: torch.gather(xyz, 1, ix.unsqueeze(-1).expand(-1, -1, 3))  # noqa: E731
+    crop_data = take(idx[:, :num_crop])
+    if padding_zeros:
+        input_data = xyz.clone()
+        input_data.scatter_(1, idx[:, :num_crop].unsqueeze(-1).expand(-1, -1, 3), 0.0)
+    else:
+        input_data = take(idx[:, num_crop:])
+    if isinstance(crop, list):
+        input_data = fps(input_data, sample_points)[0]
+        crop_data = fps(crop_data, sample_points)[0]
+    else:
+        if incomplete_shape and input_data.shape[1] > sample_points:
+            input_data = fps(input_data, sample_points)[0]
+        if incomplete_shape and crop_data.shape[1] > sample_points:
+            crop_data = fps(crop_data, sample_points)[0]
+    return input_data.contiguous(), crop_data.contiguous()

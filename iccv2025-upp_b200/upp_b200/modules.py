@@ -34,9 +34,8 @@ class _FpsGather(Function):
     @staticmethod
     def backward(ctx, grad_centers, _grad_idx):
         (idx,) = ctx.saved_tensors
-        # (B,M,3) -> channel-first scatter-add -> (B,N,3)
-        g = ops.gather_grad(grad_centers.transpose(1, 2).contiguous(), idx, ctx.n)
-        return g.transpose(1, 2).contiguous(), None
+        # (B,M,3) -> scatter-add -> (B,N,3), row-major: no transposes (the reference pays two, utils/misc.py:19)
+        return ops.rows_scatter_add(grad_centers.contiguous(), idx, ctx.n), None
 
 
 def fps(data, number):

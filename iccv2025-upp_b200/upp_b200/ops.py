@@ -108,6 +108,19 @@ def gather_grad(grad_out, idx, N):
     return g
 
 
+def rows_scatter_add(grad_rows, idx, N):
+    """grad_rows (B,M,C), idx (B,M) int32 -> (B,N,C): gradient of the row-major gather rows = x[b, idx[b,j], :]
+    (what misc.fps returns as fps_data)."""
+    _need("grad_rows", grad_rows, torch.float32, 3)
+    _need("idx", idx, torch.int32, 2)
+    B, M, C = grad_rows.shape
+    g = torch.empty((B, int(N), C), dtype=torch.float32, device=grad_rows.device)
+    with _on(grad_rows):
+        rc = _lib.load().upp_rows_scatter_add_f32(_ptr(grad_rows), _ptr(idx), B, int(N), M, C, _ptr(g), _stream(grad_rows))
+    _lib.check(rc, "upp_rows_scatter_add_f32")
+    return g
+
+
 def knn(ref, query, k, want_dist=True):
     """ref (B,N,3), query (B,Q,3) -> D (B,Q,k) f32 Euclidean ascending, I (B,Q,k) int64;
     replaces KNN(k, transpose_mode=True).forward (models/Point_MAE_unify.py:69)."""
@@ -304,3 +317,27 @@ def knn_points(p1, p2, K, want_nn=False):
         rc = _lib.load().upp_knn_points_f32(_ptr(p1), _ptr(p2), B, N1, N2, K, _ptr(d), _ptr(i), _ptr(nn), _stream(p1))
     _lib.check(rc, "upp_knn_points_f32")
     return d, i, nn
+
+
+def chamfer_forward_sharded(xyz1, xyz2, peers):
+    """upp_chamfer_fwd_sharded_f32: chamfer.forward of this rank's clouds, fused with the all-reduce of its sums
+    over NVLink peer memory.  `peers` is a parallel.PeerExchange.  -> [dist1, dist2, idx1, idx2, global_sums]."""
+    _xyz("xyz1", xyz1)
+    _xyz("xyz2", xyz2)
+    B, N, _ = xyz1.shape
+    M = xyz2.shape[1]
+    dev = xyz1.device
+    d1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+    d2 = torch.empty((B, M), dtype=torch.float32, device=dev)
+    i1 = torch.empty((B, N), dtype=torch.int32, device=dev)
+    i2 = torch.empty((B, M), dtype=torch.int32, device=dev)
+    sums = torch.empty(4, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    wbytes = int(lib.upp_chamfer_fwd_workspace_bytes(B, N, M))
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    import ctypes
+    with _on(xyz1):
+        rc = lib.upp_chamfer_fwd_sharded_f32(_ptr(xyz1), _ptr(xyz2), B, N, M, _ptr(d1), _ptr(d2), _ptr(i1), _ptr(i2),
+                                             _ptr(sums), _ptr(ws), wbytes, ctypes.addressof(peers.struct), _stream(xyz1))
+    _lib.check(rc, "upp_chamfer_fwd_sharded_f32")
+    return [d1, d2, i1, i2, sums]

@@ -36,6 +36,69 @@ def shard_batch(t, rank=None, world_size=None):
     return t[lo:hi]
 
 
+class PeerExchange:
+    """Exchange buffers for the fused Chamfer-sums all-reduce (upp_chamfer_fwd_sharded_f32): every rank's buffer
+    mapped into every process, so that the kernel that finishes a rank's sums can store them straight into its
+    peers' memory over NVLink.  Mapping: torch symmetric memory (CUDA VMM handles exchanged through the process
+    group's store) first, classic CUDA IPC handles second.  Construction is a collective; raises if neither
+    mapping works on this system (callers then keep the NCCL path)."""
+
+    def __init__(self, group=None, device=None):
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised process group")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.UPP_MAX_PEERS:
+            raise RuntimeError(f"world size {self.world} > UPP_MAX_PEERS")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n = 2 * self.world * 8  # floats: slots[2 parities][world][8]
+        self._keep = []
+        try:
+            ptrs, self.how = self._map_symmetric(group), "torch symmetric memory"
+        except Exception as first:  # noqa: BLE001 -- any failure of the preferred mapping: try the classic one
+            try:
+                ptrs, self.how = self._map_ipc(group), "CUDA IPC handles"
+            except Exception as second:  # noqa: BLE001
+                raise RuntimeError(f"peer mapping unavailable (symmetric memory: {first!r}; IPC: {second!r})") from second
+        self.seq = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.struct = _lib.PeerExchangeStruct()
+        for r in range(self.world):
+            self.struct.slots[r] = ptrs[r]
+        self.struct.rank, self.struct.world, self.struct.seq = self.rank, self.world, self.seq.data_ptr()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)  # every buffer is zeroed and mapped before anyone's first call
+
+    def _map_symmetric(self, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty(self.n, dtype=torch.float32, device=self.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != buf.data_ptr():
+            raise RuntimeError("unexpected symmetric-memory handle layout")
+        self._keep += [buf, hdl]
+        return ptrs
+
+    def _map_ipc(self, group):
+        buf = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        handle = buf.untyped_storage()._share_cuda_()
+        got = [None] * self.world
+        dist.all_gather_object(got, (handle, buf.storage_offset()), group)
+        ptrs = []
+        for r, (h, off) in enumerate(got):
+            if r == self.rank:
+                ptrs.append(buf.data_ptr())
+                continue
+            st = torch.UntypedStorage._new_shared_cuda(*h)
+            peer = torch.empty(0, dtype=torch.float32, device=st.device).set_(st, off, (self.n,))
+            probe = torch.empty(1, dtype=torch.float32, device=self.device)
+            probe.copy_(peer[:1])  # makes torch enable peer access between the two devices
+            self._keep += [st, peer]
+            ptrs.append(peer.data_ptr())
+        self._keep.append(buf)
+        return ptrs
+
+
 def reduce_sums(sums, group=None):
     """SUM all-reduce of the 4-float partial-sum buffer (NCCL on GPU tensors, gloo on CPU)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -61,9 +124,13 @@ class _ShardedChamfer(Function):
     computation would produce for its clouds."""
 
     @staticmethod
-    def forward(ctx, xyz1, xyz2, kind, n_global_clouds, group):
-        d1, d2, i1, i2, sums = ops.chamfer_forward(xyz1, xyz2, want_sums=True)
-        reduce_sums(sums, group)
+    def forward(ctx, xyz1, xyz2, kind, n_global_clouds, group, peers=None):
+        if peers is not None and max(xyz1.size(1), xyz2.size(1)) >= 128 and xyz1.size(0) > 0:
+            # one kernel chain: local Chamfer + sums + all-reduce over NVLink peer memory, no NCCL launch
+            d1, d2, i1, i2, sums = ops.chamfer_forward_sharded(xyz1, xyz2, peers)
+        else:
+            d1, d2, i1, i2, sums = ops.chamfer_forward(xyz1, xyz2, want_sums=True)
+            reduce_sums(sums, group)
         n1 = float(n_global_clouds * xyz1.size(1))
         n2 = float(n_global_clouds * xyz2.size(1))
         ctx.save_for_backward(xyz1, xyz2, i1, i2, d1, d2)
@@ -80,12 +147,14 @@ class _ShardedChamfer(Function):
             g1 = grad_loss / (4.0 * ctx.n1) / torch.sqrt(d1)
             g2 = grad_loss / (4.0 * ctx.n2) / torch.sqrt(d2)
         gx1, gx2 = ops.chamfer_backward(xyz1, xyz2, i1, i2, g1, g2)
-        return gx1, gx2, None, None, None
+        return gx1, gx2, None, None, None, None
 
 
-def sharded_chamfer(xyz1_local, xyz2_local, kind="l1", n_global_clouds=None, group=None):
+def sharded_chamfer(xyz1_local, xyz2_local, kind="l1", n_global_clouds=None, group=None, peers=None):
     """Chamfer-L1 / L2 loss of the GLOBAL batch from this rank's shard of clouds.
-    Every rank returns the same scalar; gradients flow to the local clouds only."""
+    Every rank returns the same scalar; gradients flow to the local clouds only.
+    peers: a PeerExchange -> the sums are all-reduced inside the Chamfer kernels over NVLink peer memory
+    (bit-identical on every rank); None -> one NCCL all-reduce of 16 bytes."""
     if kind not in ("l1", "l2"):
         raise ValueError("kind must be 'l1' or 'l2'")
     if n_global_clouds is None:
@@ -94,4 +163,4 @@ def sharded_chamfer(xyz1_local, xyz2_local, kind="l1", n_global_clouds=None, gro
             dist.all_reduce(n, group=group)
         n_global_clouds = int(n.item())
     return _ShardedChamfer.apply(xyz1_local.contiguous(), xyz2_local.contiguous(), kind,
-                                 int(n_global_clouds), group)
+                                 int(n_global_clouds), group, peers)

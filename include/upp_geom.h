@@ -80,6 +80,13 @@ UPP_API int upp_gather_f32(const float* features, const int32_t* idx, int B, int
 UPP_API int upp_gather_grad_f32(const float* grad_out, const int32_t* idx, int B, int C, int N, int M,
                         float* grad_features, upp_stream_t stream);
 
+/* Gradient of the row-major coordinate gather fused into upp_fps_f32 (centers_out):
+ *   grad (B,N,C) is OVERWRITTEN with the scatter-add of grad_rows (B,M,C) by idx (B,M) int32.
+ * Equals gather_operation's backward (upstream gather_points_grad_kernel) applied to the transposed
+ * tensors of utils/misc.py:19, without the two transpose copies. */
+UPP_API int upp_rows_scatter_add_f32(const float* grad_rows, const int32_t* idx, int B, int N, int M, int C,
+                             float* grad, upp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Exact brute-force k nearest neighbours.
  * Replaces knn_cuda.KNN(k, transpose_mode=True).forward(ref, query)
@@ -114,6 +121,35 @@ UPP_API size_t upp_chamfer_fwd_workspace_bytes(int B, int N, int M);
 UPP_API int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                         float* dist2, int32_t* idx1, int32_t* idx2, float* partial_sums,
                         void* workspace, size_t workspace_bytes, upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Chamfer forward of a batch SHARDED across the GPUs of one node, fused with the all-reduce of its sums.
+ * Replaces, for the batch-sharded loss, chamfer.forward + torch.mean + dist_utils.reduce_tensor
+ *   (extensions/chamfer_dist/__init__.py:28-84, utils/dist_utils.py:41-48, tools/runner_pretask.py:241).
+ * Same outputs as upp_chamfer_fwd_f32 for this rank's B clouds, but global_sums (4 floats) receives
+ *   { sum dist1, sum dist2, sum sqrt(dist1), sum sqrt(dist2) } over ALL ranks' clouds: the kernel that finishes
+ * the local sums stores them into every peer's exchange buffer over NVLink (CUDA IPC-mapped peer memory), waits
+ * for the peers' contributions in its own buffer and adds them in rank order -- bit-identical on every rank, no
+ * NCCL launch, no host synchronisation, CUDA-graph capturable.  All ranks must issue their calls in the same order
+ * (as with any collective).  Each rank provides:
+ *   slots[r]  device pointer (valid in THIS process) to rank r's exchange buffer of upp_peer_exchange_bytes(world)
+ *             bytes, zero-filled once before the first call;
+ *   seq       this rank's call counter in device memory, zero before the first call.
+ * Requires the workspace (single-pass path) and max(N, M) >= 128; otherwise UPP_ERR_UNSUPPORTED (use
+ * upp_chamfer_fwd_f32 + an NCCL all-reduce of its partial sums).
+ */
+#define UPP_MAX_PEERS 16
+typedef struct upp_peer_exchange {
+  float* slots[UPP_MAX_PEERS];
+  int rank;
+  int world;
+  unsigned int* seq;
+} upp_peer_exchange;
+#define upp_peer_exchange_bytes(world) ((size_t)2 * (size_t)(world) * 8 * sizeof(float))
+UPP_API int upp_chamfer_fwd_sharded_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
+                                float* dist2, int32_t* idx1, int32_t* idx2, float* global_sums,
+                                void* workspace, size_t workspace_bytes, const upp_peer_exchange* peers,
+                                upp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Chamfer distance backward.

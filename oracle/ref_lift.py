@@ -81,3 +81,27 @@ def interpolation():
     p = lift("models/Point_MAE_unify.py", ["propagate"], env)
     fp = lift("models/Point_MAE_unify_segment.py", ["PointNetFeaturePropagation"], env)
     return types.SimpleNamespace(propagate=p.propagate, PointNetFeaturePropagation=fp.PointNetFeaturePropagation)
+
+
+def seprate_point_cloud(fps_impl):
+    """The reference's own seprate_point_cloud (utils/misc.py:205-256) bound to a stand-in for fps
+    (utils/misc.py:13-20).  The function calls .cuda() on its viewpoints: run it under `cpu_cuda()`."""
+    import random
+    import torch
+    import torch.nn.functional as F
+    return lift("utils/misc.py", ["seprate_point_cloud"],
+                {"torch": torch, "F": F, "random": random, "fps": fps_impl}).seprate_point_cloud
+
+
+class cpu_cuda:
+    """Context manager: Tensor.cuda() is the identity (lets the reference's host code run in a GPU-less container)."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self._orig

@@ -19,6 +19,10 @@ outputs are stored as small .npz files that travel to the GPU box.
 
     python tests/golden/make_golden.py            # everything
     python tests/golden/make_golden.py interp     # only golden_interp.npz
+    python tests/golden/make_golden.py crop       # only golden_seprate.npz
+
+  golden_seprate.npz         utils/misc.py:205-256 seprate_point_cloud run unmodified (Tensor.cuda patched to the
+                             identity, fps = utils/misc.py:13-20 over a float64 FPS stand-in), seeded
 """
 import os
 import sys
@@ -106,12 +110,49 @@ def make_interp():
     np.savez_compressed(os.path.join(HERE, "golden_interp.npz"), **out)
 
 
+def make_seprate():
+    """seprate_point_cloud from the reference's own code, seeded; the cases of its call sites."""
+    import random
+
+    class _P2:
+        @staticmethod
+        def furthest_point_sample(xyz, npoint):
+            return torch.from_numpy(f64.fps(xyz.numpy(), npoint).astype(np.int32))
+
+        @staticmethod
+        def gather_operation(features, idx):
+            return torch.gather(features, 2, idx.long().unsqueeze(1).expand(-1, features.shape[1], -1))
+
+    spc = ref_lift.seprate_point_cloud(ref_lift.misc_fps(_P2))
+    xyz = torch.from_numpy(lattice_cloud(5, 512, 31))
+    out = {"xyz": xyz.numpy()}
+    cases = {  # name -> kwargs (tools/runner_module.py:131, tools/runner_pretask.py:179,369, tools/runner_finetune.py:267)
+        "fixed_crop": dict(crop=128, sample_points=256),
+        "range_crop": dict(crop=[100, 200], sample_points=64),
+        "fixed_view": dict(crop=128, fixed_points=torch.Tensor([1, 1, 1]), sample_points=256),
+        "view_list": dict(crop=150, fixed_points=[torch.Tensor([1, 1, 1]), torch.Tensor([-1, 1, 0]), torch.Tensor([0, -1, 1])]),
+        "padding": dict(crop=128, padding_zeros=True, sample_points=1024),
+        "no_fps": dict(crop=128, incomplete_shape=False),
+    }
+    with ref_lift.cpu_cuda():
+        for name, kw in cases.items():
+            random.seed(11)
+            torch.manual_seed(11)
+            a, b = spc(xyz, 512, **kw)
+            out[name + "_input"], out[name + "_crop"] = a.numpy(), b.numpy()
+    np.savez_compressed(os.path.join(HERE, "golden_seprate.npz"), **out)
+
+
 def main():
     assert ref_lift.available(), "needs /root/reference"
     if sys.argv[1:] == ["interp"]:
         make_interp()
         return
+    if sys.argv[1:] == ["crop"]:
+        make_seprate()
+        return
     make_interp()
+    make_seprate()
     H = ref_lift.torch_helpers()
 
     # ---- knn_point ----

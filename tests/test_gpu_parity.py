@@ -138,6 +138,20 @@ def test_fps_centers_and_misc_fps_grad(U, O, dev):
     np.testing.assert_allclose(x.grad.cpu().numpy(), g, rtol=RTOL, atol=0)
 
 
+def test_rows_scatter_add_equals_transposed_gather_grad(U, O, dev):
+    """The row-major gradient of misc.fps's gather == gather_operation's backward on the transposed tensors."""
+    g = torch.Generator().manual_seed(21)
+    gr = torch.randn(3, 50, 3, generator=g)
+    idx = torch.randint(0, 70, (3, 50), generator=g, dtype=torch.int32)  # duplicates accumulate
+    got = U.ops.rows_scatter_add(gr.to(dev), idx.to(dev), 70)
+    want = O.gather_grad(gr.transpose(1, 2).contiguous().numpy(), idx.numpy(), 70).transpose(0, 2, 1)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+    wide = torch.randn(2, 9, 17, generator=g)
+    i2 = torch.randint(0, 12, (2, 9), generator=g, dtype=torch.int32)
+    want2 = torch.zeros(2, 12, 17).scatter_add_(1, i2.long().unsqueeze(-1).expand(-1, -1, 17), wide)
+    np.testing.assert_allclose(U.ops.rows_scatter_add(wide.to(dev), i2.to(dev), 12).cpu().numpy(), want2.numpy(), rtol=1e-6, atol=1e-6)
+
+
 def test_fps_empty(U, dev):
     assert U.ops.fps(torch.zeros(0, 16, 3, device=dev), 4).shape == (0, 4)
     assert U.ops.fps(torch.zeros(2, 16, 3, device=dev), 0).shape == (2, 0)
@@ -612,3 +626,51 @@ def test_knn_points_autograd_and_errors(U, dev):
         U.knn_points(p1.detach(), p2.detach(), K=91)
     with pytest.raises(NotImplementedError):
         U.knn_points(p1.detach(), p2.detach(), K=4, lengths1=torch.tensor([30, 30]))
+
+
+# ------------------------------------------------------------------ seprate_point_cloud ----
+
+SEPRATE_CASES = {
+    "fixed_crop": dict(crop=128, sample_points=256),
+    "range_crop": dict(crop=[100, 200], sample_points=64),
+    "fixed_view": dict(crop=128, fixed_points=torch.Tensor([1, 1, 1]), sample_points=256),
+    "view_list": dict(crop=150, fixed_points=[torch.Tensor([1, 1, 1]), torch.Tensor([-1, 1, 0]), torch.Tensor([0, -1, 1])]),
+    "padding": dict(crop=128, padding_zeros=True, sample_points=1024),
+    "no_fps": dict(crop=128, incomplete_shape=False),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SEPRATE_CASES))
+def test_golden_reference_seprate_point_cloud(U, dev, case):
+    """The batched mirror against the reference's own per-cloud loop (tests/golden/golden_seprate.npz), same seeds:
+    identical crops and identical FPS selections (2 batched FPS launches instead of 2*B batch-1 launches)."""
+    import os
+    import random
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_seprate.npz"))
+    xyz = torch.from_numpy(g["xyz"]).to(dev)
+    random.seed(11)
+    torch.manual_seed(11)
+    c0 = U.launch_count()
+    a, b = U.misc.seprate_point_cloud(xyz, 512, **SEPRATE_CASES[case])
+    assert U.launch_count() - c0 <= 2
+    assert a.is_contiguous() and b.is_contiguous()
+    assert np.array_equal(a.cpu().numpy(), g[case + "_input"])
+    assert np.array_equal(b.cpu().numpy(), g[case + "_crop"])
+    same, none = U.misc.seprate_point_cloud(xyz, 512, 512)
+    assert same is xyz and none is None
+
+
+def test_chamfer_sharded_entry_world1_equals_plain(U, dev):
+    """upp_chamfer_fwd_sharded_f32 with a one-rank exchange (no peers to wait for) == upp_chamfer_fwd_f32 + sums;
+    the N-rank exchange itself is exercised by scripts/check_multigpu.py under torchrun."""
+    from upp_b200 import _lib
+
+    class _One:
+        struct = _lib.PeerExchangeStruct()
+    _One.struct.rank, _One.struct.world, _One.struct.seq = 0, 1, None
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(3, 500, 3, generator=g).to(dev), torch.rand(3, 700, 3, generator=g).to(dev)
+    got = U.ops.chamfer_forward_sharded(a, b, _One)
+    want = U.ops.chamfer_forward(a, b, want_sums=True)
+    for x, y in zip(got, want):
+        assert torch.equal(x, y)

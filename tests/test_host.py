@@ -158,3 +158,17 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "clouds/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"] == "c1"
+
+
+def test_seprate_point_cloud_host_logic_matches_reference_golden():
+    """The crop / gather / RNG logic of the batched mirror (no FPS on these cases -> runs without a GPU)."""
+    import random
+    import upp_b200
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_seprate.npz"))
+    xyz = torch.from_numpy(g["xyz"])
+    for case, kw in (("padding", dict(crop=128, padding_zeros=True, sample_points=1024)),
+                     ("no_fps", dict(crop=128, incomplete_shape=False))):
+        random.seed(11)
+        torch.manual_seed(11)
+        a, b = upp_b200.misc.seprate_point_cloud(xyz, 512, **kw)
+        assert np.array_equal(a.numpy(), g[case + "_input"]) and np.array_equal(b.numpy(), g[case + "_crop"])
