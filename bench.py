@@ -106,7 +106,8 @@ class GpuWorkload:
         elif world > 1:
             try:
                 self.peers = upp_b200.parallel.PeerExchange()
-                self.collective = f"fused in the Chamfer finalize kernel over NVLink peer memory ({self.peers.how})"
+                self.collective = (f"fused in the Chamfer finalize kernel over NVLink peer memory ({self.peers.how}); "
+                                   "device arm: deferred wait late on the Chamfer side stream")
             except RuntimeError as ex:
                 self.collective = f"NCCL all_reduce of 4 floats (peer mapping unavailable: {str(ex)[:80]})"
         U = upp_b200
@@ -152,8 +153,8 @@ class GpuWorkload:
                 t("group N32 G32 k16", o.group, g1[1], 32, 16)
                 t("group N972 G32 k16", o.group, keep, 32, 16)
             with torch.cuda.stream(self.side[1]):
-                if self.peers is not None:
-                    d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward_sharded, d["rebuild"], d["target"], self.peers)
+                if self.peers is not None:  # deferred exchange: the kernels send now, the wait + sum closes the step
+                    d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward_sharded, d["rebuild"], d["target"], self.peers, True)
                 else:
                     d1, d2, j1, j2, sums = t("chamfer_fwd N1024 M1024", o.chamfer_forward, d["rebuild"], d["target"], True)
                     if self.world > 1 and not self.no_exchange:
@@ -166,6 +167,15 @@ class GpuWorkload:
             cat = torch.cat([keep, c1], 1)
             i2, c2 = t("fps N1228 M1024", o.fps, cat, 1024, True)
             g4 = t("group N1024 G64 k32", o.group, c2, 64, 32)
+            if self.peers is not None:
+                # close the deferred exchange on the Chamfer side stream, but only once the critical path has come this
+                # far: the peers have had ~0.23 ms to deliver, and the wait + loss arithmetic overlaps the chain's tail
+                late = torch.cuda.Event()
+                late.record(torch.cuda.current_stream())
+                with torch.cuda.stream(self.side[1]):
+                    self.side[1].wait_event(late)
+                    sums = o.peer_allreduce_finish(self.peers, self.dev)
+                    loss = (sums[2] + sums[3]) / (2.0 * nglob)
             g5 = t("group N64 G32 k8", o.group, g4[1], 32, 8)
             # backward chain: G5 -> G4 -> fps(1228->1024) gather -> fps(1024->256) gather (row-major scatter-adds)
             gc4 = t("group_bwd N64", o.group_backward, torch.zeros_like(g5[0]), d["w_c5"], g5[2], g5[3], 64)
@@ -183,13 +193,15 @@ class GpuWorkload:
         if n == "c3":
             nglob = float(self.B * self.world * 2048)
             if self.peers is not None:
-                d1, d2, j1, j2, sums = t("chamfer_fwd N2048 M2048", o.chamfer_forward_sharded, d["xyz1"], d["xyz2"], self.peers)
+                d1, d2, j1, j2, sums = t("chamfer_fwd N2048 M2048", o.chamfer_forward_sharded, d["xyz1"], d["xyz2"], self.peers, True)
             else:
                 d1, d2, j1, j2, sums = t("chamfer_fwd N2048 M2048", o.chamfer_forward, d["xyz1"], d["xyz2"], True)
                 if self.world > 1:
                     self.par.reduce_sums(sums)
             gd1, gd2 = (0.25 / nglob) / torch.sqrt(d1), (0.25 / nglob) / torch.sqrt(d2)
             self.grad = t("chamfer_bwd N2048 M2048", o.chamfer_backward, d["xyz1"], d["xyz2"], j1, j2, gd1, gd2)
+            if self.peers is not None:
+                sums = o.peer_allreduce_finish(self.peers, self.dev)
             return (sums[2] + sums[3]) / (2.0 * nglob)
         if n == "c4":
             _, c = t("fps N8192 M1024", o.fps, d["pts"], 1024, True)

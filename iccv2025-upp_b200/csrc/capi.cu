@@ -15,6 +15,7 @@ int knn_launch(const float*, const float*, int, int, int, int, float*, int64_t*,
 int chamfer_fwd_launch(const float*, const float*, int, int, int, float*, float*, int32_t*, int32_t*,
                        float*, void*, size_t, const upp_peer_exchange*, cudaStream_t);
 size_t chamfer_fwd_workspace_bytes(int, int, int);
+int peer_finish_launch(const upp_peer_exchange*, float*, cudaStream_t);
 int chamfer_bwd_launch(const float*, const float*, const int32_t*, const int32_t*, const float*,
                        const float*, int, int, int, float*, float*, cudaStream_t);
 int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
@@ -139,6 +140,14 @@ int upp_chamfer_fwd_sharded_f32(const float* xyz1, const float* xyz2, int B, int
   for (int r = 0; r < peers->world && peers->world > 1; ++r) UPP_REQUIRE(peers->slots[r] != nullptr);
   return chamfer_fwd_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, global_sums, workspace, workspace_bytes,
                             peers, S(stream));
+}
+
+int upp_peer_allreduce_finish_f32(const upp_peer_exchange* peers, float* global_sums, upp_stream_t stream) {
+  UPP_REQUIRE(peers && global_sums);
+  UPP_REQUIRE(peers->world >= 2 && peers->world <= UPP_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world);
+  UPP_REQUIRE(peers->seq != nullptr);
+  for (int r = 0; r < peers->world; ++r) UPP_REQUIRE(peers->slots[r] != nullptr);
+  return peer_finish_launch(peers, global_sums, S(stream));
 }
 
 int upp_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,

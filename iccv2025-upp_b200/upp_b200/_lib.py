@@ -28,6 +28,7 @@ _SIGNATURES = {
     "upp_chamfer_fwd_workspace_bytes": [_i, _i, _i],
     "upp_chamfer_fwd_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "upp_chamfer_fwd_sharded_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp],
+    "upp_peer_allreduce_finish_f32": [_vp, _vp, _vp],
     "upp_chamfer_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "upp_group_f32": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "upp_group_bwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
@@ -50,7 +51,7 @@ UPP_MAX_PEERS = 16
 class PeerExchangeStruct(ctypes.Structure):
     """upp_peer_exchange of include/upp_geom.h."""
     _fields_ = [("slots", ctypes.c_void_p * UPP_MAX_PEERS), ("rank", ctypes.c_int), ("world", ctypes.c_int),
-                ("seq", ctypes.c_void_p)]
+                ("seq", ctypes.c_void_p), ("defer", ctypes.c_int)]
 
 _lib = None
 

@@ -319,9 +319,23 @@ def knn_points(p1, p2, K, want_nn=False):
     return d, i, nn
 
 
-def chamfer_forward_sharded(xyz1, xyz2, peers):
+def peer_allreduce_finish(peers, device):
+    """upp_peer_allreduce_finish_f32: second half of a deferred exchange -> global sums (4 floats)."""
+    import ctypes
+    sums = torch.empty(4, dtype=torch.float32, device=device)
+    with _on(sums):
+        rc = _lib.load().upp_peer_allreduce_finish_f32(ctypes.addressof(peers.struct), _ptr(sums), _stream(sums))
+    _lib.check(rc, "upp_peer_allreduce_finish_f32")
+    return sums
+
+
+def chamfer_forward_sharded(xyz1, xyz2, peers, defer=False):
     """upp_chamfer_fwd_sharded_f32: chamfer.forward of this rank's clouds, fused with the all-reduce of its sums
-    over NVLink peer memory.  `peers` is a parallel.PeerExchange.  -> [dist1, dist2, idx1, idx2, global_sums]."""
+    over NVLink peer memory.  `peers` is a parallel.PeerExchange.  -> [dist1, dist2, idx1, idx2, global_sums].
+    defer=True: the kernels only SEND (the 5th output holds the LOCAL sums); call peer_allreduce_finish(peers, device)
+    later on the same stream -- where the loss value is consumed -- for the global sums."""
+    if hasattr(peers.struct, "defer"):
+        peers.struct.defer = 1 if defer else 0
     _xyz("xyz1", xyz1)
     _xyz("xyz2", xyz2)
     B, N, _ = xyz1.shape

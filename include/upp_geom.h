@@ -144,12 +144,21 @@ typedef struct upp_peer_exchange {
   int rank;
   int world;
   unsigned int* seq;
+  int defer; /* 0: the call returns the global sums; 1: the call only SENDS (global_sums receives this rank's local
+                sums) and upp_peer_allreduce_finish_f32, launched later on the same stream, waits and adds */
 } upp_peer_exchange;
 #define upp_peer_exchange_bytes(world) ((size_t)2 * (size_t)(world) * 8 * sizeof(float))
 UPP_API int upp_chamfer_fwd_sharded_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                                 float* dist2, int32_t* idx1, int32_t* idx2, float* global_sums,
                                 void* workspace, size_t workspace_bytes, const upp_peer_exchange* peers,
                                 upp_stream_t stream);
+
+/* Second half of a deferred exchange (peers->defer was 1 in the last upp_chamfer_fwd_sharded_f32 call on this
+ * stream): waits for every rank's contribution of that call and writes the rank-ordered sum to global_sums (4 floats).
+ * Launch it where the loss VALUE is consumed (end of the step): a kernel that waits on its peers early in the step
+ * stalls the work queued behind it on the same hardware queue; by the end of the step the peers have delivered.
+ * Exactly one finish per deferred call, before the next sharded call. */
+UPP_API int upp_peer_allreduce_finish_f32(const upp_peer_exchange* peers, float* global_sums, upp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Chamfer distance backward.

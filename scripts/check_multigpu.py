@@ -93,8 +93,16 @@ def main():
             ref = upp_b200.ops.chamfer_forward(sx, sy, want_sums=True)[4]
             dist.all_reduce(ref)
             torch.testing.assert_close(out[4], ref, rtol=1e-6, atol=0)
+        # deferred exchange: send inside the Chamfer kernels, wait + sum in a later launch
+        for it in range(4):
+            sx.copy_(al + 0.03 * it)
+            loc = upp_b200.ops.chamfer_forward_sharded(sx, sy, peers, defer=True)[4].clone()
+            glob = upp_b200.ops.peer_allreduce_finish(peers, dev)
+            ref = loc.clone()
+            dist.all_reduce(ref)
+            torch.testing.assert_close(glob, ref, rtol=1e-6, atol=0)
         if rank == 0:
-            print(f"fused peer all-reduce ok via {peers.how}: == NCCL (1e-6), bit-identical across ranks, graph replay x6")
+            print(f"fused peer all-reduce ok via {peers.how}: == NCCL (1e-6), bit-identical across ranks, graph replay x6, deferred finish x4")
     # Group is per cloud: a shard's result equals the same rows of the full batch
     x = (torch.rand(B, 1024, 3, generator=g) * 2 - 1).to(dev)
     nb_f, ce_f = upp_b200.Group(64, 32)(x)
