@@ -296,10 +296,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.first = [], None, 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -309,6 +309,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """Samples from here on (the last one taken before included) are the ones reported."""
+        self.first = max(0, len(self.rows) - 1)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -316,7 +320,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -477,10 +481,17 @@ def main():
             return static_loss
         return W.run_ops(W.d)
 
+    # nvidia-smi is started BEFORE the warm-up and left to settle: launching it right in front of the timed region
+    # perturbs the rank that owns it (measured at 2 GPUs: rank 0 lagged ~14 us per step over a 30-step region, and
+    # every peer waited for it in the loss exchange)
+    sampler = ClockSampler(local_rank) if rank == 0 and os.environ.get("UPP_BENCH_DIAG_NO_SAMPLER") != "1" else None
+    if sampler is not None:
+        time.sleep(0.5)
     for _ in range(args.warmup):
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.mark()
     evs = []
     for _ in range(args.steps):
         flush.zero_()

@@ -103,6 +103,8 @@ __device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int
       }
     }
     // ---- 2. seed the list with the sorted lane minima (first block only) ----
+    // (Seeding with the 32 smallest of the 128 per-lane GROUP minima -- four row sorts + three top-32 merges, ~4x
+    //  fewer survivors below -- was measured on B200 and lost: kNN 64q x 1024 went from 15.4 to 19.5 us.)
     if (!st.seeded) {
       st.seeded = true;
       st.ld = lmin;
