@@ -235,8 +235,9 @@ class GpuWorkload:
             nb4, ce4 = self.g64_32(c2)
             _, ce5 = self.g32_8(ce4)
             self._join(cur)
-            loss = cd + 1e-9 * ((nb4 * d["w_nb"]).sum() + (ce5 * d["w_c5"]).sum())
-            loss.backward()
+            # backward through the public autograd Functions, seeded with the downstream gradients directly (what the
+            # encoder would hand back for the neighbourhoods / centres) instead of a synthetic scalar head
+            torch.autograd.backward([cd, nb4, ce5], [None, d["w_nb"], d["w_c5"]])
             self.grad = reb.grad
             return cd.detach()
         if n == "c3":
@@ -287,6 +288,16 @@ def op_work(label):
     if kind in ("gather_grad", "fps_gather_bwd"):
         return 0.0, 0.0
     return 0.0, 0.0
+
+
+def traffic_for(label):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the op's dominant kernel, per launch, from the committed
+    `ncu --set full` captures (profiles/traffic.json: label -> {bytes, kernel, source}); None when not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(label)
+    except (OSError, ValueError):
+        return None
+    return t["bytes"] if t else None
 
 
 # ----------------------------------------------------------------------------- clocks --------
@@ -630,7 +641,7 @@ def main():
                 "peak": round(fp32_peak, 2) if fp32_bound else hbm_peak,
                 "unit": "TFLOP/s" if fp32_bound else "GB/s",
                 "frac": round((top["tflops"] / fp32_peak) if fp32_bound else (top["gbs"] / hbm_peak), 5),
-                "traffic": None,
+                "traffic": traffic_for(top["op"]),
                 "peak_source": (f"computed 148 SM x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no fp32 figure; "
                                 "K=3 distances are not a tensor-core contraction)") if fp32_bound
                 else ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"),
