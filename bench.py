@@ -647,6 +647,18 @@ def main():
                 else ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"),
                 "hbm_gbs": top["gbs"], "hbm_frac": round(top["gbs"] / hbm_peak, 5),
                 "note": "FPS is a serial chain of M-1 block arg-max rounds: latency-bound, see DESIGN.md" if top["op"].startswith(("fps", "group")) else ""}
+    if top["op"].startswith("fps") and int(top["op"].split()[1][1:]) <= 2048:
+        # the bound that actually binds FPS: (M-1) dependent rounds, each a chain of fixed instruction latencies
+        # (LDS centre 29 + sub/mul/fma/fma 16 + FMNMX 4 + 3 x VIMNMX3 12 + REDUX 23 + vote/compare 12 + STS/BAR 15 +
+        #  LDS slots 29 + select 12 + address 4 = 156 cycles, + ~45 cycles of packed-FMA issue that cannot overlap it;
+        #  cycle counts from /opt/skills/guides/B300_MICROARCH.md and scripts/microbench*.cu)
+        v = {x[0]: int(x[1:]) for x in top["op"].split()[1:] if x[1:].isdigit()}
+        rounds = max(v["M"] - 1, 1)
+        floor_us = 201.0 / sm_max
+        roofline["latency_model"] = {"rounds": rounds, "us_per_round": round(top["ms"] * 1e3 / rounds, 4),
+                                     "chain_floor_us_per_round": round(floor_us, 4),
+                                     "frac_of_chain_floor": round(floor_us / (top["ms"] * 1e3 / rounds), 3),
+                                     "busy_sms": min(B, N_SM)}
 
     line = {"metric": METRIC, "value": clouds / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -8,6 +8,7 @@ reference's own operator API.
     propagate, interpolate_features                            (kNN inverse-distance feature interpolation)
     knn_points                                                 (pytorch3d.ops.knn_points convention)
     misc.seprate_point_cloud                                   (batched crop + FPS, utils/misc.py:205-256)
+    metrics.f_score / chamfer_distance_l1 / _l2                (utils/metrics.py:70-111 on the Chamfer kernels)
     parallel                                                   (batch sharding + NCCL loss all-reduce)
 
 Everything computes in libupp_geom.so (hand-written CUDA); importing this package without the
@@ -17,7 +18,7 @@ from . import _lib
 
 _lib.load()  # fail loudly, at import, if the CUDA library is missing
 
-from . import chamfer, misc, ops, parallel, pointnet2_utils  # noqa: E402,F401
+from . import chamfer, metrics, misc, ops, parallel, pointnet2_utils  # noqa: E402,F401
 from .knn import KNN  # noqa: E402,F401
 from .modules import (ChamferDistanceL1, ChamferDistanceL2, ChamferDistanceL2_split,  # noqa: E402,F401
                       ChamferFunction, Group, fps, interpolate_features, knn_points, propagate)

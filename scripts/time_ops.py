@@ -66,7 +66,7 @@ def main():
         shapes = [(32, 1228, 1024), (32, 1024, 256), (32, 64, 512), (32, 32, 512), (128, 1024, 512), (32, 2048, 512), (32, 1843, 1536),
                   (32, 1536, 512), (1, 2048, 1024), (512, 1024, 256), (32, 256, 256), (32, 128, 256), (32, 512, 256), (32, 384, 256)]
         if args.only == "big":
-            shapes = [(128, 8192, 1024), (1, 6144, 1024), (32, 4096, 512), (32, 3000, 512), (32, 2500, 512)]
+            shapes = [(128, 8192, 1024), (1, 6144, 1024), (32, 4096, 512), (32, 3000, 512), (32, 2500, 512), (128, 8192, 128)]
             args.only = ""
         for (B, N, M) in shapes:
             x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
@@ -81,11 +81,11 @@ def main():
                     if search == 2:  # deferred tree search: the instantiated large-cloud combinations
                         if nw == 8 and p2 > 8:
                             p2 += p2 % 2
-                        if not ((nw == 8 and 3 <= p2 <= 16) or (nw == 16 and 3 <= p2 <= 8) or (nw == 32 and 2 <= p2 <= 4)):
+                        if not ((nw == 4 and 3 <= p2 <= 8) or (nw == 8 and 3 <= p2 <= 16) or (nw == 16 and 3 <= p2 <= 8) or (nw == 32 and 2 <= p2 <= 4)):
                             continue
                     elif p2 > (4 if nw == 32 else 8):
                         continue
-                    for s2 in ((0,) if nw <= 2 else (1,) if nw == 32 else (0, 1)):
+                    for s2 in ((0,) if nw <= 2 or (nw == 4 and search == 2) else (1,) if nw == 32 else (0, 1)):
                         os.environ["UPP_FPS_NW"], os.environ["UPP_FPS_P2"], os.environ["UPP_FPS_S2"] = str(nw), str(p2), str(s2)
                         os.environ["UPP_FPS_SEARCH"] = str(search)
                         ok = bool(torch.equal(ops.fps(x, M), want))
@@ -93,6 +93,18 @@ def main():
                             lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
             for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_S2", "UPP_FPS_SEARCH"):
                 os.environ.pop(k, None)
+            if N > 2048:  # Morton-bucketed kernel with box-distance skipping
+                os.environ["UPP_FPS_BUCKET"] = "1"
+                for nw, p2 in ((32, (N + 2047) // 2048), (16, (N + 1023) // 1024), (8, (N + 511) // 512)):
+                    p2 = {7: 8, 9: 12, 10: 12, 11: 12, 13: 16, 14: 16, 15: 16}.get(p2, p2) if nw == 8 else (8 if nw == 16 and p2 == 7 else p2)
+                    if (nw, p2) not in ((32, 2), (32, 3), (32, 4), (16, 3), (16, 4), (16, 5), (16, 6), (16, 8), (8, 8), (8, 12), (8, 16)):
+                        continue
+                    os.environ["UPP_FPS_NW"], os.environ["UPP_FPS_P2"] = str(nw), str(p2)
+                    ok = bool(torch.equal(ops.fps(x, M), want))
+                    rec(f"fps2-sweep B{B} N{N} M{M} bucket nw{nw} p2={p2}", lambda: ops.fps(x, M),
+                        lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
+                for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_BUCKET"):
+                    os.environ.pop(k, None)
         return
     if args.sweep_chamfer:
         for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 1024, 1024), (64, 32, 1024), (8, 2048, 2048)]:

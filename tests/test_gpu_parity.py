@@ -55,6 +55,12 @@ FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
     "v2_tree_nw8_p5": {"UPP_FPS_NW": "8", "UPP_FPS_P2": "5", "UPP_FPS_S2": "0", "UPP_FPS_SEARCH": "2"},
     "v2_tree_nw16_p8": {"UPP_FPS_NW": "16", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
     "v2_tree_nw32_p4": {"UPP_FPS_NW": "32", "UPP_FPS_P2": "4", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
+    # Morton-bucketed kernel with box-distance skipping (large clouds); forced shapes also run it on small clouds
+    "bucket_auto": {"UPP_FPS_BUCKET": "1"},
+    "bucket_nw16_p3": {"UPP_FPS_BUCKET": "1", "UPP_FPS_NW": "16", "UPP_FPS_P2": "3"},
+    "bucket_nw16_p8": {"UPP_FPS_BUCKET": "1", "UPP_FPS_NW": "16", "UPP_FPS_P2": "8"},
+    "bucket_nw8_p16": {"UPP_FPS_BUCKET": "1", "UPP_FPS_NW": "8", "UPP_FPS_P2": "16"},
+    "bucket_nw32_p2": {"UPP_FPS_BUCKET": "1", "UPP_FPS_NW": "32", "UPP_FPS_P2": "2"},
     "v1": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "0"},                       # round-1a strided kernels
     "v1_w4": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "1"},
 }
@@ -674,3 +680,23 @@ def test_chamfer_sharded_entry_world1_equals_plain(U, dev):
     want = U.ops.chamfer_forward(a, b, want_sums=True)
     for x, y in zip(got, want):
         assert torch.equal(x, y)
+
+
+def test_metrics_f_score_and_cd_x1000(U, dev):
+    """utils/metrics.py:70-111 semantics against float64 brute force (what open3d computes), per cloud then averaged."""
+    g = torch.Generator().manual_seed(17)
+    gt = torch.rand(3, 400, 3, generator=g) * 0.2
+    pred = gt[:, torch.randperm(400, generator=g)[:300]] + 0.004 * torch.randn(3, 300, 3, generator=g)
+    d = torch.cdist(pred.double(), gt.double())
+    fs = []
+    for b in range(3):
+        p, r = (d[b].min(1)[0] < 0.01).double().mean(), (d[b].min(0)[0] < 0.01).double().mean()
+        fs.append(2 * r * p / (r + p) if r + p else 0.0)
+    got = U.metrics.f_score(pred.to(dev), gt.to(dev))
+    assert got.dim() == 0 and abs(got.item() - float(sum(fs) / 3)) < 2e-3  # a point within fp32 rounding of th may flip
+    far = U.metrics.f_score(pred.to(dev), (gt + 5.0).to(dev))
+    assert far.item() == 0.0
+    l1 = ((d.min(2)[0].mean() + d.min(1)[0].mean()) / 2 * 1000).item()
+    l2 = (((d ** 2).min(2)[0].mean() + (d ** 2).min(1)[0].mean()) * 1000).item()
+    assert abs(U.metrics.chamfer_distance_l1(pred.to(dev), gt.to(dev)).item() - l1) <= 1e-5 * l1
+    assert abs(U.metrics.chamfer_distance_l2(pred.to(dev), gt.to(dev)).item() - l2) <= 1e-5 * l2
