@@ -505,211 +505,6 @@ __global__ void __launch_bounds__(NW * 32)
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Large clouds (2048 < N <= 8192): spatially BUCKETED FPS with exact results.
-// A new sample only lowers the running min-distance of points near it, and ever fewer as sampling goes on -- yet
-// the kernels above touch all N points every round (N = 8192: the round is ALU/issue bound at ~1070 cycles).
-// Here the cloud is first sorted along a Morton curve inside the CTA (bitonic sort of (code << 32 | index) keys in
-// shared memory, once, ~10 us), so that each WARP owns a spatially compact bucket of 32*P points with a bounding
-// box.  Per round a warp first tests its box against the new centre c: if the squared distance from c to the box
-// exceeds the bucket's largest running min-distance, no point of the bucket can change (d(p,c) >= lb^2 > md[p]),
-// the cached warp winner stays valid and the warp only re-posts it.  Only buckets near c recompute.  The test is
-// conservative in fp32 (margin 2^-20 >> the rounding of either side), so md[] -- and therefore every selected
-// index -- is bit-identical to the plain algorithm.  Ties are resolved by the lowest ORIGINAL index explicitly
-// (sorted position no longer implies index order): REDUX.MIN over the original indices of the tied candidates.
-__device__ __forceinline__ unsigned morton_expand10(unsigned v) {  // 10 bits -> every third bit
-  v &= 0x3ffu;
-  v = (v | (v << 16)) & 0x030000ffu;
-  v = (v | (v << 8)) & 0x0300f00fu;
-  v = (v | (v << 4)) & 0x030c30c3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
-}
-
-template <int NW, int P2>
-__global__ void __launch_bounds__(NW * 32)
-    fps_bucket_kernel(const float* __restrict__ xyz, int N, int NPAD, int M, int32_t* __restrict__ idx_out,
-                      float* __restrict__ centers_out) {
-  constexpr int P = 2 * P2;
-  constexpr int NT = NW * 32;
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  float* s_xyz = reinterpret_cast<float*>(s_raw);                                  // 3*N floats (AoS, original order)
-  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_raw + ((static_cast<size_t>(N) * 12 + 15) & ~static_cast<size_t>(15)));  // NPAD keys
-  __shared__ __align__(16) int2 s_slot[2][32];
-  __shared__ float s_box[6][32];
-  __shared__ __align__(8) uint64_t s_bar;
-
-  const int t = threadIdx.x;
-  const int lane = t & 31;
-  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const int b = blockIdx.x;
-  const float* p = xyz + static_cast<size_t>(b) * N * 3;
-  int32_t* out = idx_out + static_cast<size_t>(b) * M;
-  float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
-
-  if (t == 0) {
-    mbar_init(&s_bar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  unsigned parity = 0;
-  stage_points(s_xyz, p, N, &s_bar, parity);
-
-  // ---- cloud bounding box -> 10-bit Morton codes -> sort (code << 32 | original index) ----
-  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-  for (int i = t; i < N; i += NT)
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float v = s_xyz[3 * i + a];
-      lo[a] = fminf(lo[a], v);
-      hi[a] = fmaxf(hi[a], v);
-    }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-    }
-    if (lane == 0) { s_box[a][warp] = lo[a]; s_box[3 + a][warp] = hi[a]; }
-  }
-  __syncthreads();
-  float scale[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    float l = s_box[a][0], h = s_box[3 + a][0];
-    for (int w = 1; w < NW; ++w) { l = fminf(l, s_box[a][w]); h = fmaxf(h, s_box[3 + a][w]); }
-    lo[a] = l;
-    scale[a] = h > l ? 1023.0f / (h - l) : 0.f;
-  }
-  for (int i = t; i < NPAD; i += NT) {
-    unsigned long long key = ~0ull;  // padding sorts to the end
-    if (i < N) {
-      unsigned code = 0;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const int q = min(1023, max(0, __float2int_rn((s_xyz[3 * i + a] - lo[a]) * scale[a])));
-        code |= morton_expand10(static_cast<unsigned>(q)) << a;
-      }
-      key = (static_cast<unsigned long long>(code) << 32) | static_cast<unsigned>(i);
-    }
-    s_key[i] = key;
-  }
-  __syncthreads();
-  for (unsigned k = 2; k <= static_cast<unsigned>(NPAD); k <<= 1)
-    for (unsigned j = k >> 1; j > 0; j >>= 1) {
-      for (unsigned e = t; e < static_cast<unsigned>(NPAD) / 2; e += NT) {
-        const unsigned i = ((e & ~(j - 1)) << 1) | (e & (j - 1));
-        const unsigned l = i | j;
-        const unsigned long long a = s_key[i], c = s_key[l];
-        if ((a > c) == ((i & k) == 0)) { s_key[i] = c; s_key[l] = a; }
-      }
-      __syncthreads();
-    }
-  const unsigned* s_perm = reinterpret_cast<const unsigned*>(s_key);  // s_perm[2*pos] = original index at sorted position pos
-
-  // ---- this thread's P consecutive sorted points into registers; this warp's bounding box ----
-  const int base = t * P;
-  f32x2 X[P2], Y[P2], Z[P2];
-  float md[P];
-  float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-#pragma unroll
-  for (int r = 0; r < P2; ++r) {
-    float c[2][3];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int pos = base + 2 * r + h;
-      if (pos < N) {
-        const unsigned o = s_perm[2 * pos];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          c[h][a] = s_xyz[3 * o + a];
-          blo[a] = fminf(blo[a], c[h][a]);
-          bhi[a] = fmaxf(bhi[a], c[h][a]);
-        }
-        md[2 * r + h] = fps_initial_md(c[h][0], c[h][1], c[h][2]);
-      } else {
-        c[h][0] = c[h][1] = c[h][2] = 0.f;
-        md[2 * r + h] = kOutOfRange;
-      }
-    }
-    X[r] = pack2(c[0][0], c[1][0]);
-    Y[r] = pack2(c[0][1], c[1][1]);
-    Z[r] = pack2(c[0][2], c[1][2]);
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      blo[a] = fminf(blo[a], __shfl_xor_sync(0xffffffffu, blo[a], o));
-      bhi[a] = fmaxf(bhi[a], __shfl_xor_sync(0xffffffffu, bhi[a], o));
-    }
-
-  float cx = s_xyz[0], cy = s_xyz[1], cz = s_xyz[2];
-  if (t == 0) out[0] = 0;
-  int wkey = __float_as_int(1e10f);   // cached warp maximum (float bits of md) ...
-  unsigned worig = 0xffffffffu;       // ... and the lowest original index attaining it
-
-  for (int j = 1; j < M; ++j) {
-    // squared distance from the centre to this warp's box vs the bucket's largest running min-distance
-    const float ex = fmaxf(fmaxf(blo[0] - cx, cx - bhi[0]), 0.f);
-    const float ey = fmaxf(fmaxf(blo[1] - cy, cy - bhi[1]), 0.f);
-    const float ez = fmaxf(fmaxf(blo[2] - cz, cz - bhi[2]), 0.f);
-    const float lb2 = ex * ex + ey * ey + ez * ez;
-    // (round 1 always updates: it replaces the initial 1e10 by real distances and gives warps that own no point
-    //  -- capacity beyond N -- their negative key; 0.99999905 = 1 - 2^-20)
-    const bool skip = j > 1 && (wkey < 0 || lb2 * 0.99999905f > __int_as_float(wkey));  // warp-uniform
-    if (!skip) {
-      const f32x2 CX = pack2(cx, cx), CY = pack2(cy, cy), CZ = pack2(cz, cz);
-      f32x2 D[P2];
-#pragma unroll
-      for (int r = 0; r < P2; ++r) D[r] = sub2(Y[r], CY);
-#pragma unroll
-      for (int r = 0; r < P2; ++r) D[r] = mul2(D[r], D[r]);
-#pragma unroll
-      for (int r = 0; r < P2; ++r) { const f32x2 dx = sub2(X[r], CX); D[r] = fma2(dx, dx, D[r]); }
-#pragma unroll
-      for (int r = 0; r < P2; ++r) { const f32x2 dz = sub2(Z[r], CZ); D[r] = fma2(dz, dz, D[r]); }
-      int best = INT_MIN;
-#pragma unroll
-      for (int r = 0; r < P2; ++r) {
-        float d0, d1;
-        unpack2(D[r], d0, d1);
-        md[2 * r] = fminf(md[2 * r], d0);
-        md[2 * r + 1] = fminf(md[2 * r + 1], d1);
-        best = max(best, max(__float_as_int(md[2 * r]), __float_as_int(md[2 * r + 1])));
-      }
-      wkey = redux_max_s32(best);
-      unsigned cand = 0xffffffffu;  // lowest original index among this thread's points holding the warp maximum
-      if (best == wkey) {
-#pragma unroll
-        for (int r = 0; r < P; ++r)
-          if (__float_as_int(md[r]) == wkey && base + r < N) cand = min(cand, s_perm[2 * (base + r)]);
-      }
-      worig = redux_min_u32(cand);
-    }
-    int2* slot = s_slot[j & 1];
-    if (lane == 0) slot[warp] = make_int2(wkey, static_cast<int>(worig));
-    __syncthreads();
-    const int2 sv = (lane < NW) ? slot[lane] : make_int2(INT_MIN, -1);
-    const int bmax = redux_max_s32(sv.x);
-    const unsigned sel = redux_min_u32(sv.x == bmax ? static_cast<unsigned>(sv.y) : 0xffffffffu);
-    cx = s_xyz[3 * sel];
-    cy = s_xyz[3 * sel + 1];
-    cz = s_xyz[3 * sel + 2];
-    if (t == 0) out[j] = static_cast<int>(sel);
-  }
-  if (cen) {
-    __syncthreads();
-    for (int j = t; j < M; j += NT) {
-      const int sel = out[j];
-      cen[3 * j] = s_xyz[3 * sel];
-      cen[3 * j + 1] = s_xyz[3 * sel + 1];
-      cen[3 * j + 2] = s_xyz[3 * sel + 2];
-    }
-  }
-}
-
 // Any-N fallback: min-distance array in a global workspace (L2-resident), xyz re-read from
 // global memory every iteration.  Same selection rule, same two-stage arg-max.
 template <int THREADS>
@@ -928,31 +723,6 @@ static int dispatch_fps_blk_big(FpsBlkConfig c, const float* xyz, int B, int N, 
   return UPP_ERR_UNSUPPORTED;
 }
 
-template <int NW, int P2>
-static int launch_fps_bucket(const float* xyz, int B, int N, int M, int32_t* idx, float* centers, cudaStream_t st) {
-  int npad = 1;
-  while (npad < N) npad <<= 1;
-  const size_t need = ((static_cast<size_t>(N) * 12 + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(npad) * 8;
-  const size_t smem = fps_smem_request(need, B);
-  auto kern = fps_bucket_kernel<NW, P2>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return static_cast<int>(e);
-  kern<<<B, NW * 32, smem, st>>>(xyz, N, npad, M, idx, centers);
-  count_launch();
-  return launch_status();
-}
-
-// nw in {16, 32}; p2 = point pairs per thread (capacity nw * 64 * p2 >= N)
-static int dispatch_fps_bucket(int nw, int p2, const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
-                               cudaStream_t st) {
-#define UPP_BKT(NW_, P2_) \
-  if (nw == NW_ && p2 == P2_) return launch_fps_bucket<NW_, P2_>(xyz, B, N, M, idx, centers, st);
-  UPP_BKT(32, 2) UPP_BKT(32, 3) UPP_BKT(32, 4) UPP_BKT(16, 3) UPP_BKT(16, 4) UPP_BKT(16, 5) UPP_BKT(16, 6) UPP_BKT(16, 8)
-  UPP_BKT(8, 8) UPP_BKT(8, 12) UPP_BKT(8, 16)
-#undef UPP_BKT
-  return UPP_ERR_UNSUPPORTED;
-}
-
 static bool fps_blk_valid(FpsBlkConfig c, int N) {
   const bool nw_ok = c.nw == 1 || c.nw == 2 || c.nw == 4 || c.nw == 8 || c.nw == 16 || c.nw == 32;
   if (c.search == 2) {  // the combinations dispatch_fps_blk_big instantiates
@@ -995,16 +765,11 @@ int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* cente
                                  env_int("UPP_FPS_SEARCH", 0)};
     const bool use_forced = forced.nw > 0 && forced.p2 > 0 && fps_blk_valid(forced, N);  // tuning aid
     if (use_forced) c = forced;
-    const int bucket = env_int("UPP_FPS_BUCKET", 0);  // tuning aid: 1 = bucketed kernel (UPP_FPS_NW / UPP_FPS_P2 pick its shape)
-    if (bucket == 1 && N > 64 && N <= kFpsMaxRegPoints) {
-      const int nw = forced.nw > 0 ? forced.nw : 32;
-      const int p2 = forced.p2 > 0 ? forced.p2 : (N + nw * 64 - 1) / (nw * 64);
-      if (static_cast<long>(nw) * 64 * p2 >= N) {
-        const int rc = dispatch_fps_bucket(nw, p2, xyz, B, N, M, idx, centers, st);
-        if (rc != UPP_ERR_UNSUPPORTED) return rc;
-      }
-    }
     if (!use_forced && N > 2048) {
+      // (A Morton-bucketed variant -- cloud sorted along a Z-curve in the CTA, one spatial bucket per warp, buckets whose
+      //  box is farther from the new centre than their largest running min-distance skipped, exact results -- was
+      //  built and measured: 0.63 us per round at N = 8192 against 0.54 here; with 32 buckets per cloud too few are
+      //  skipped and the per-warp reduction overhead of 32 warps dominates.  profiles/r01d_sweep_fps_big_bucket_experiment.jsonl)
       // large clouds: 8 fat warps (B200 sweep, us per round v1 -> here): N 2500 0.335 -> 0.255, 3000 0.335 -> 0.270,
       // 4096 0.388 -> 0.367, 6144 0.475 -> 0.452, 8192 0.570 -> 0.544 (deferred tree search from 18 points per thread)
       const int p2 = (N + 511) / 512;

@@ -93,18 +93,6 @@ def main():
                             lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
             for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_S2", "UPP_FPS_SEARCH"):
                 os.environ.pop(k, None)
-            if N > 2048:  # Morton-bucketed kernel with box-distance skipping
-                os.environ["UPP_FPS_BUCKET"] = "1"
-                for nw, p2 in ((32, (N + 2047) // 2048), (16, (N + 1023) // 1024), (8, (N + 511) // 512)):
-                    p2 = {7: 8, 9: 12, 10: 12, 11: 12, 13: 16, 14: 16, 15: 16}.get(p2, p2) if nw == 8 else (8 if nw == 16 and p2 == 7 else p2)
-                    if (nw, p2) not in ((32, 2), (32, 3), (32, 4), (16, 3), (16, 4), (16, 5), (16, 6), (16, 8), (8, 8), (8, 12), (8, 16)):
-                        continue
-                    os.environ["UPP_FPS_NW"], os.environ["UPP_FPS_P2"] = str(nw), str(p2)
-                    ok = bool(torch.equal(ops.fps(x, M), want))
-                    rec(f"fps2-sweep B{B} N{N} M{M} bucket nw{nw} p2={p2}", lambda: ops.fps(x, M),
-                        lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
-                for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_BUCKET"):
-                    os.environ.pop(k, None)
         return
     if args.sweep_chamfer:
         for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 1024, 1024), (64, 32, 1024), (8, 2048, 2048)]:

@@ -55,12 +55,6 @@ FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
     "v2_tree_nw8_p5": {"UPP_FPS_NW": "8", "UPP_FPS_P2": "5", "UPP_FPS_S2": "0", "UPP_FPS_SEARCH": "2"},
     "v2_tree_nw16_p8": {"UPP_FPS_NW": "16", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
     "v2_tree_nw32_p4": {"UPP_FPS_NW": "32", "UPP_FPS_P2": "4", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
-    # Morton-bucketed kernel with box-distance skipping (large clouds); forced shapes also run it on small clouds
-    "bucket_auto": {"UPP_FPS_BUCKET": "1"},
-    "bucket_nw16_p3": {"UPP_FPS_BUCKET": "1", "UPP_FPS_NW": "16", "UPP_FPS_P2": "3"},
-    "bucket_nw16_p8": {"UPP_FPS_BUCKET": "1", "UPP_FPS_NW": "16", "UPP_FPS_P2": "8"},
-    "bucket_nw8_p16": {"UPP_FPS_BUCKET": "1", "UPP_FPS_NW": "8", "UPP_FPS_P2": "16"},
-    "bucket_nw32_p2": {"UPP_FPS_BUCKET": "1", "UPP_FPS_NW": "32", "UPP_FPS_P2": "2"},
     "v1": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "0"},                       # round-1a strided kernels
     "v1_w4": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "1"},
 }
