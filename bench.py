@@ -68,7 +68,9 @@ def make_inputs(workload, B, seed):
         return {"pts": unit_sphere(torch.randn(B, 8192, 3, generator=g) * 0.35).contiguous()}
     if workload == "c5":
         return {"pts": unit_sphere(torch.randn(B, 2048, 3, generator=g) * 0.35).contiguous(),
-                "feat": torch.randn(B, 128, 1152, generator=g)}  # (B,128,1152) group features to propagate
+                "feat": torch.randn(B, 128, 1152, generator=g),  # (B,128,1152) group features to propagate
+                # what the segmentation head hands back for the propagated features (device-resident, like the features)
+                "w_up": torch.randn(B, 2048, 1152, generator=g)}
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -80,8 +82,8 @@ DESCR = {
     "c1": "Point-MAE Group divider FPS 64 + kNN k=32, B=32, N=1024 (BASELINE configs[0])",
     "c3": "Chamfer L1 fwd+bwd B=64, 2048 vs 2048 (BASELINE configs[2])",
     "c4": "ShapeNet55-scale grouping FPS 8192->1024 then Group(64,32), B=128 (BASELINE configs[3])",
-    "c5": "ShapeNetPart Group(128,32) on 2048 points + kNN feature propagation 2048<-128, 3-NN, 1152-d, B=32 "
-          "(BASELINE configs[4], geometry part)",
+    "c5": "ShapeNetPart Group(128,32) on 2048 points + kNN feature propagation 2048<-128, 3-NN, 1152-d, forward and "
+          "feature-gradient backward, B=32 (BASELINE configs[4], geometry part)",
 }
 
 
@@ -213,7 +215,8 @@ class GpuWorkload:
             return ce[0, 0, 0]
         if n == "c5":
             nb, ce, _, _ = t("group N2048 G128 k32", o.group, d["pts"], 128, 32)
-            up = t("interp N2048 S128 C1152 k3", o.interp_forward, d["pts"], ce, d["feat"], 3, 1e-4)[0]
+            up, j, w, _ = t("interp N2048 S128 C1152 k3", o.interp_forward, d["pts"], ce, d["feat"], 3, 1e-4)
+            self.grad = t("interp_bwd N2048 S128 C1152 k3", o.interp_backward, d["w_up"], j, w, 128)[0]
             self.keepalive = (nb, up)
             return up[0, 0, 0]
         raise SystemExit(n)
@@ -278,8 +281,11 @@ class GpuWorkload:
             return ce[0, 0, 0]
         if n == "c5":
             nb, ce = self.g128_32(d["pts"])
-            up = U.interpolate_features(d["pts"], ce, d["feat"], 3, eps=1e-4)
-            return up[0, 0, 0]
+            feat = d["feat"].detach().requires_grad_(True)
+            up = U.interpolate_features(d["pts"], ce, feat, 3, eps=1e-4)
+            up.backward(d["w_up"])
+            self.grad = feat.grad
+            return up.detach()[0, 0, 0]
         raise SystemExit(n)
 
 
@@ -303,6 +309,9 @@ def op_work(label):
     if kind == "interp":  # HBM: out written once, features + coordinates read once (the k re-reads hit L2)
         N, S, C, k = v["N"], v["S"], v["C"], v["k"]
         return 0.0, 4.0 * N * C + 4.0 * S * C + 12.0 * (N + S) + 12.0 * N * k
+    if kind == "interp_bwd":  # grad_out read once, grad_feat2 written once, the selection read once
+        N, S, C, k = v["N"], v["S"], v["C"], v["k"]
+        return 0.0, 4.0 * N * C + 4.0 * S * C + 8.0 * N * k
     if kind == "group_bwd":
         return 0.0, 0.0
     if kind in ("gather_grad", "fps_gather_bwd"):
@@ -398,7 +407,10 @@ def cpu_step(workload, host):
         return float(T.group(c, 64, 32)[1][0, 0, 0])
     if workload == "c5":
         _, ce = T.group(host["pts"], 128, 32)
-        return float(T.interpolate(host["pts"], ce, host["feat"], 3, 1e-4)[0, 0, 0])
+        feat = host["feat"].clone().requires_grad_(True)
+        up = T.interpolate(host["pts"], ce, feat, 3, 1e-4)
+        up.backward(host["w_up"])
+        return float(up.detach()[0, 0, 0])
     raise SystemExit(workload)
 
 

@@ -7,6 +7,32 @@
 namespace upp {
 
 static std::atomic<unsigned long long> g_launches{0};
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup: the library keeps linking against
+// cudart only (no libcuda at build time, and none needed on the CPU-only build box).
+int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+                     uint32_t box_inner, uint32_t box_rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<encode_fn>(fn);
+  }();
+  if (encode == nullptr) return UPP_ERR_UNSUPPORTED;
+  const cuuint64_t gdim[2] = {inner, rows};
+  const cuuint64_t gstride[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {box_inner, box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box,
+                            estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? UPP_OK : UPP_ERR_INVALID_ARG;
+}
+
 void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
 
 int fps_launch(const float*, int, int, int, int32_t*, float*, void*, size_t, cudaStream_t);
@@ -31,7 +57,8 @@ int interp_fwd_launch(const float*, const float*, const float*, const float*, fl
                       int, float*, int32_t*, float*, float*, cudaStream_t);
 int interp_bwd_launch(const float*, const int32_t*, const float*, const float*, const float*, const float*,
                       const float*, float, float, int, int, int, int, int, float*, float*, float*, float*,
-                      cudaStream_t);
+                      void*, size_t, cudaStream_t);
+size_t interp_bwd_workspace_bytes(int, int, int, int, int);
 
 }  // namespace upp
 
@@ -212,10 +239,14 @@ int upp_interp_fwd_f32(const float* xyz1, const float* xyz2, const float* feat2,
                            static_cast<cudaStream_t>(stream));  // (the size S shadows the helper here)
 }
 
+size_t upp_interp_bwd_workspace_bytes(int B, int N, int S, int C, int k) {
+  return interp_bwd_workspace_bytes(B, N, S, C, k);
+}
+
 int upp_interp_bwd_f32(const float* grad_out, const int32_t* idx, const float* weight, const float* dist,
                        const float* feat2, const float* xyz1, const float* xyz2, float alpha, float eps, int B,
                        int N, int S, int C, int k, float* grad_feat2, float* grad_xyz1, float* grad_xyz2,
-                       float* gd_workspace, upp_stream_t stream) {
+                       float* gd_workspace, void* workspace, size_t workspace_bytes, upp_stream_t stream) {
   UPP_REQUIRE(B >= 0 && N >= 0 && S >= 0 && C >= 0);
   UPP_REQUIRE(k >= 1 && k <= 32);
   if (B == 0 || S == 0) return UPP_OK;
@@ -223,7 +254,8 @@ int upp_interp_bwd_f32(const float* grad_out, const int32_t* idx, const float* w
   UPP_REQUIRE(N == 0 || (grad_out && idx && weight));
   if (gd_workspace) UPP_REQUIRE(N == 0 || (dist && feat2 && xyz1 && xyz2));
   return interp_bwd_launch(grad_out, idx, weight, dist, feat2, xyz1, xyz2, alpha, eps, B, N, S, C, k, grad_feat2,
-                           grad_xyz1, grad_xyz2, gd_workspace, static_cast<cudaStream_t>(stream));
+                           grad_xyz1, grad_xyz2, gd_workspace, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

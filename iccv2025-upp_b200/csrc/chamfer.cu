@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(WC * 32)
 //     grid can be cut to a whole number of SM-waves (the R8W8 profile ran 1.15 waves).  With more
 //     than one chunk the row side also merges through RED.MIN.U64 keys (distance bits << 32 | column
 //     group) and chamfer_finalize_kernel resolves both sides; with one chunk rows are written directly.
-template <int R, int WC>
-__global__ void __launch_bounds__(WC * 32)
+template <int R, int WC, int MINB = 0>
+__global__ void __launch_bounds__(WC * 32, MINB)
     chamfer_fwd_packed_kernel(const float* __restrict__ xyzA, const float* __restrict__ xyzB, int NA,
                               int NB, int NA8, int NB8, int chunk, float* __restrict__ distA,
                               int32_t* __restrict__ idxA, unsigned long long* __restrict__ rowbest,
@@ -816,8 +816,8 @@ size_t chamfer_fwd_workspace_bytes(int B, int N, int M) {
 // residency wave (5 x 148 items) and then fill whole waves.  B200 sweep (scripts/time_ops.py
 // --sweep-chamfer): B32 1024x1024 1 chunk 33.8 us -> 4 chunks 27.6; B64 2048x2048 1 chunk 107.5 -> 4 chunks
 // 93.2; B64 2048x8192 (2048 items already) best with 1.  Chunks stay >= 256 columns and a multiple of 64.
-static int chamfer_pick_chunks(long items0, int NB) {
-  const long wave = 5 * 148;
+static int chamfer_pick_chunks(long items0, int NB, int per_sm = 5) {
+  const long wave = static_cast<long>(per_sm) * 148;
   const int cap = NB / 256 < 1 ? 1 : (NB / 256 > 32 ? 32 : NB / 256);
   long cmin = (wave + items0 - 1) / items0;
   if (cmin < 1) cmin = 1;
@@ -832,14 +832,14 @@ static int chamfer_pick_chunks(long items0, int NB) {
   return best;
 }
 
-template <int R, int WC>
+template <int R, int WC, int MINB = 0>
 static int launch_chamfer_packed(const float* a, const float* bpts, int B, int NA, int NB, float* dA,
                                  int32_t* iA, float* dB, int32_t* iB, void* ws, int force_chunks,
                                  float* sums, bool swapped, const PeerXchg& px, cudaStream_t st) {
   static_assert(R <= 16, "chamfer_finalize2_kernel scans at most 16 rows per key");
   const int na8 = (NA + 7) & ~7, nb8 = (NB + 7) & ~7;
   const int rowblocks = (NA + 32 * R - 1) / (32 * R);
-  int chunks = force_chunks > 0 ? force_chunks : chamfer_pick_chunks(static_cast<long>(B) * rowblocks, NB);
+  int chunks = force_chunks > 0 ? force_chunks : chamfer_pick_chunks(static_cast<long>(B) * rowblocks, NB, MINB > 1 ? MINB : 5);
   int chunk = ((NB + chunks - 1) / chunks + 63) & ~63;
   chunks = (NB + chunk - 1) / chunk;
   // workspace: [col keys B*nb8][row keys B*na8][ticket, 16 B][partials]; keys and ticket preset to 0xFF
@@ -852,7 +852,7 @@ static int launch_chamfer_packed(const float* a, const float* bpts, int B, int N
   cudaError_t e = cudaMemsetAsync(ws, 0xFF, preset, st);
   if (e != cudaSuccess) return static_cast<int>(e);
   dim3 grid(rowblocks, B, chunks);
-  chamfer_fwd_packed_kernel<R, WC><<<grid, WC * 32, 0, st>>>(a, bpts, NA, NB, na8, nb8, chunk, dA, iA, rowkeys, colkeys);
+  chamfer_fwd_packed_kernel<R, WC, MINB><<<grid, WC * 32, 0, st>>>(a, bpts, NA, NB, na8, nb8, chunk, dA, iA, rowkeys, colkeys);
   count_launch();
   int rc = launch_status();
   if (rc != UPP_OK) return rc;
@@ -936,6 +936,10 @@ int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M
       case 34: rc = launch_chamfer_packed<12, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
       case 35: rc = launch_chamfer_packed<16, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
       case 36: rc = launch_chamfer_packed<16, 2>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 37: rc = launch_chamfer_packed<8, 4, 6>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 38: rc = launch_chamfer_packed<8, 4, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 39: rc = launch_chamfer_packed<8, 4, 3>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 40: rc = launch_chamfer_packed<8, 8, 3>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
       default: rc = launch_chamfer_packed<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
     }
     if (rc != UPP_OK) return rc;

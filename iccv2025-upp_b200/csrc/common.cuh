@@ -1,5 +1,6 @@
 // common.cuh -- shared device helpers for libupp_geom (sm_100a only).
 #pragma once
+#include <cuda.h>  // CUtensorMap: types only -- the encoder is fetched from the driver at run time (no libcuda link)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -127,6 +128,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+
+// 2-D TMA tile load (cp.async.bulk.tensor -> SASS UTMALDG): the box of `map` whose first element is
+// (c_inner, c_row) lands densely in shared memory (row after row, dst 128-byte aligned) and completes
+// box-bytes on `bar`; elements outside the tensor arrive as zeros and still count.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c_inner, int c_row,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_row), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// Host: row-major fp32 matrix (rows x inner, row pitch in bytes a multiple of 16, base 16-byte aligned)
+// as a tensor map with a (box_rows x box_inner) box, no swizzle, zero fill.  Returns UPP_OK or an error code.
+int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+                     uint32_t box_inner, uint32_t box_rows);
 
 // Stage `npts` xyz triples (AoS, 12 B each) from global into shared memory.
 // The 16-byte-aligned body goes through one TMA bulk copy issued by thread 0; a misaligned

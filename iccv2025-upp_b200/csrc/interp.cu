@@ -175,6 +175,231 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp, 3)
   }  // targets of this warp
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide features (seg feature propagation: 2048 <- 128 sources, 1152 channels): TWO launches.
+// The one-launch kernel above gathers the k source rows from L2 per target and is bound by that
+// latency (ncu: 52 % long-scoreboard stalls, 3.0 TB/s of output).  Here
+//   1. the selection runs alone: interp_select_kernel (k <= 4: one THREAD per target scanning the
+//      staged sources with a branch-free sorted insertion -- the warp-per-target selection costs
+//      ~700 issue cycles per target for k = 3, 40 us at the seg shape) or interp_fwd_kernel with
+//      C = 0; both write idx / weight / dist only;
+//   2. interp_blend_kernel streams the output: a CTA owns (cloud, 128-channel chunk, span of
+//      targets), stages its S x 128-channel slice of the source features ONCE in shared memory (one
+//      2-D TMA tile load), turns the span's (idx, weight) pairs into {row offset, weight} records in
+//      shared memory 128 targets at a time (the next batch is in flight in registers while this one
+//      is blended), and every warp blends target after target from shared memory: one float4 per
+//      lane, per neighbour one broadcast LDS.64 + one LDS.128, one streaming 512-byte store per
+//      target.  The only long-latency traffic left is the output write, which is what bounds the op.
+// Arithmetic is the fused kernel's (products and sums in neighbour order -- ptxas contracts each
+// mul.f32x2 + add.f32x2 pair to FFMA2 in both kernels -- then alpha, then base): bit-identical output.
+// ---- explicit shared-window loads (32-bit addresses; see interp_bwd_stream_kernel) ----
+__device__ __forceinline__ uint2 lds_u64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+
+__device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
+  ulonglong2 v;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a));
+  return v;
+}
+
+constexpr int kBlendCh = 128;
+constexpr int kBlendWarps = 8;
+constexpr int kBlendMaxS = 192;   // 96 KB of staged features: two CTAs per SM (three up to S = 136)
+constexpr int kBlendSub = 128;    // targets per record batch
+
+// Thread-per-target selection for k = K <= 4 (single staged tile of sources, S <= kKnnTile).  Sources are
+// visited in index order and a candidate only moves ahead of strictly larger distances, so equal distances
+// keep the lower source index first: the order of the warp kernels (stable sort by distance).  Distances are
+// DistExpanded's, operation for operation (|b|^2 is computed once per source while staging).
+template <int K>
+__global__ void __launch_bounds__(128)
+    interp_select_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2, float eps, int N, int S,
+                         int32_t* __restrict__ idx_out, float* __restrict__ w_out, float* __restrict__ d_out) {
+  extern __shared__ __align__(16) float s_sel[];  // [S x {x, y, z, |b|^2}] then the AoS staging area (3 S floats)
+  __shared__ __align__(8) uint64_t s_bar;
+  float4* s4 = reinterpret_cast<float4*>(s_sel);
+  float* s_ref = s_sel + 4 * S;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned parity = 0;
+  stage_points(s_ref, xyz2 + static_cast<size_t>(b) * S * 3, S, &s_bar, parity);
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float x = s_ref[3 * s], y = s_ref[3 * s + 1], z = s_ref[3 * s + 2];
+    s4[s] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t row = static_cast<size_t>(b) * N + n;
+  const float qx = __ldg(xyz1 + row * 3), qy = __ldg(xyz1 + row * 3 + 1), qz = __ldg(xyz1 + row * 3 + 2);
+  const float s1 = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz));
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) { bd[j] = __int_as_float(0x7f800000); bi[j] = 0; }
+#pragma unroll 4
+  for (int s = 0; s < S; ++s) {
+    const float4 r = s4[s];  // same address in every lane: one broadcast LDS.128
+    const float dot = __fmaf_rn(qz, r.z, __fmaf_rn(qy, r.y, __fmul_rn(qx, r.x)));
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), s1), r.w);
+    bool lt[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) lt[j] = d < bd[j];
+#pragma unroll
+    for (int j = K - 1; j >= 0; --j) {
+      if (j > 0 && lt[j - 1]) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; }
+      else if (lt[j]) { bd[j] = d; bi[j] = s; }
+    }
+  }
+  // weights: dist_recip = 1/(d + eps); weight = dist_recip / sum(dist_recip)  (sum in neighbour order)
+  float r[K], norm = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    r[j] = __fdiv_rn(1.0f, __fadd_rn(bd[j], eps));
+    norm = __fadd_rn(norm, r[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    idx_out[row * K + j] = bi[j];
+    w_out[row * K + j] = __fdiv_rn(r[j], norm);
+    if (d_out) d_out[row * K + j] = bd[j];
+  }
+}
+
+// K = 0: any k <= 32 (neighbour loop not unrolled, no register prefetch of the next record batch).
+template <int K>
+__global__ void __launch_bounds__(kBlendWarps * kWarp)
+    interp_blend_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ base, float alpha,
+                        const int32_t* __restrict__ idx, const float* __restrict__ weight, int N, int S, int C,
+                        int krt, int span, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char s_blend[];  // [S x 512 B features][kBlendSub * k records of 8 B]
+  __shared__ __align__(8) uint64_t s_bar;
+  const int k = K > 0 ? K : krt;
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int chunk = blockIdx.x, b = blockIdx.z;
+  const int n0 = blockIdx.y * span;
+  const int n1 = min(N, n0 + span);
+  uint2* s_rec = reinterpret_cast<uint2*>(s_blend + static_cast<size_t>(S) * (kBlendCh * 4));
+
+  if (t == 0) {
+    tma_prefetch_desc(&fmap);
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&s_bar, static_cast<unsigned>(S) * (kBlendCh * 4u));
+    tma_load_2d(s_blend, &fmap, chunk * kBlendCh, b * S, &s_bar);
+  }
+  // records of one batch: entry e of the batch <-> flat (target, j) position, contiguous in idx / weight
+  constexpr int PE = K > 0 ? (kBlendSub * K + kBlendWarps * kWarp - 1) / (kBlendWarps * kWarp) : 1;
+  uint2 pre[PE];
+  auto fetch = [&](int s0) {
+    const int cnt = (min(n1, s0 + kBlendSub) - s0) * k;
+    const size_t p0 = (static_cast<size_t>(b) * N + s0) * k;
+#pragma unroll
+    for (int u = 0; u < PE; ++u) {
+      const int e = t + u * (kBlendWarps * kWarp);
+      pre[u] = e < cnt ? make_uint2(static_cast<unsigned>(__ldg(idx + p0 + e)) * (kBlendCh * 4u),
+                                    __float_as_uint(__ldg(weight + p0 + e)))
+                       : make_uint2(0u, 0u);
+    }
+  };
+  auto commit = [&]() {
+#pragma unroll
+    for (int u = 0; u < PE; ++u) {
+      const int e = t + u * (kBlendWarps * kWarp);
+      if (e < kBlendSub * k) s_rec[e] = pre[u];
+    }
+  };
+  if (K > 0) {
+    fetch(n0);
+    commit();
+  }
+  __syncthreads();  // barrier init visible to every thread; first record batch in place
+  mbar_wait(&s_bar, 0);
+
+  const uint32_t feat = smem_u32(s_blend) + lane * 16u;
+  const f32x2 A2 = pack2(alpha, alpha);
+  const int col = chunk * kBlendCh + lane * 4;
+  for (int s0 = n0; s0 < n1; s0 += kBlendSub) {
+    const int cnt = min(n1, s0 + kBlendSub) - s0;
+    if (K > 0) {
+      if (s0 + kBlendSub < n1) fetch(s0 + kBlendSub);  // next batch: loads in flight under this batch's blend
+    } else {
+      __syncthreads();
+      for (int e = t; e < cnt * k; e += kBlendWarps * kWarp) {
+        const size_t p = (static_cast<size_t>(b) * N + s0) * k + e;
+        s_rec[e] = make_uint2(static_cast<unsigned>(__ldg(idx + p)) * (kBlendCh * 4u), __float_as_uint(__ldg(weight + p)));
+      }
+      __syncthreads();
+    }
+    // two targets per warp and trip: 2k independent LDS.128 in flight
+    for (int tl = warp; tl < cnt; tl += 2 * kBlendWarps) {
+      const bool two = tl + kBlendWarps < cnt;
+      const int tb = two ? tl + kBlendWarps : tl;
+      const uint2* ra = s_rec + tl * k;
+      const uint2* rb = s_rec + tb * k;
+      f32x2 a0 = pack2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+      for (int j = 0; j < (K > 0 ? K : 1); ++j) {
+        for (int jj = j; jj < k; jj += (K > 0 ? k : 1)) {  // K > 0: exactly one trip (unrolled); K == 0: the run-time loop
+          const uint2 ea = ra[jj], eb = rb[jj];
+          const ulonglong2 fa = lds_v2u64(feat + ea.x), fb = lds_v2u64(feat + eb.x);
+          const f32x2 WA = pack2(__uint_as_float(ea.y), __uint_as_float(ea.y));
+          const f32x2 WB = pack2(__uint_as_float(eb.y), __uint_as_float(eb.y));
+          a0 = add2(a0, mul2(fa.x, WA));
+          a1 = add2(a1, mul2(fa.y, WA));
+          b0 = add2(b0, mul2(fb.x, WB));
+          b1 = add2(b1, mul2(fb.y, WB));
+        }
+      }
+      ulonglong2 oa, ob;
+      oa.x = mul2(A2, a0);
+      oa.y = mul2(A2, a1);
+      ob.x = mul2(A2, b0);
+      ob.y = mul2(A2, b1);
+      const size_t rowa = static_cast<size_t>(b) * N + s0 + tl;
+      const size_t rowb = static_cast<size_t>(b) * N + s0 + tb;
+      if (base) {
+        const ulonglong2 pa = __ldg(reinterpret_cast<const ulonglong2*>(base + rowa * C + col));
+        const ulonglong2 pb = __ldg(reinterpret_cast<const ulonglong2*>(base + rowb * C + col));
+        oa.x = add2(pa.x, oa.x);
+        oa.y = add2(pa.y, oa.y);
+        ob.x = add2(pb.x, ob.x);
+        ob.y = add2(pb.y, ob.y);
+      }
+      __stcs(reinterpret_cast<ulonglong2*>(out + rowa * C + col), oa);
+      if (two) __stcs(reinterpret_cast<ulonglong2*>(out + rowb * C + col), ob);
+    }
+    if (K > 0 && s0 + kBlendSub < n1) {
+      __syncthreads();  // every warp is done with this batch's records
+      commit();
+      __syncthreads();
+    }
+  }
+}
+
 // Backward, target side (only when coordinate gradients are wanted).  With G = alpha * grad_out[b,n,:],
 // dot_j = <G, f_j>, m = sum_j w_j dot_j, r_j = 1/(d_j + eps):
 //   d loss / d d_j = -(r_j w_j)(dot_j - m)                      (w_j = r_j / sum r  =>  r_j^2 / sum r = r_j w_j)
@@ -387,9 +612,236 @@ __global__ void __launch_bounds__(kSrcThreads)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward for wide features, feature gradient only (no coordinate terms): STREAM grad_out once.
+// interp_bwd_source_kernel reads every grad_out row k times through L2 (one CTA per source point
+// gathering its matches: 207 us at the seg shape, 1.5 TB/s).  Here a CTA owns (cloud, 128-channel
+// chunk) and pulls that chunk of ALL N grad_out rows through a 3-stage TMA pipeline exactly once,
+// 64 targets per tile; warp w keeps the accumulators of sources 16w .. 16w+15 in registers (one float4
+// per lane and source) and adds weight * row for the tile's matches of each of its sources, in list
+// order.  Which matches those are comes from a per-tile CSR block built once per call (and shared by
+// all channel chunks) by interp_csr_kernel: a stable counting sort of the tile's (target, j) entries
+// by source.  Per source the additions happen in ascending (n, j) order, tile after tile: the same
+// sequence of fmaf as the source-side kernel's -- deterministic, no atomics, bit-identical to it.
+constexpr int kBsTile = 64;                 // targets per streamed tile
+constexpr int kBsSrc = 128;                 // sources covered: 8 warps x 16 register accumulators
+constexpr int kBsWarps = 8;                 // consumer warps (+ 1 producer warp)
+constexpr int kBsStages = 3;
+constexpr int kBsMaxK = 8;                  // entries per tile kBsTile * k <= 512
+constexpr unsigned kBsOffBytes = 272;       // 129 uint16 offsets, padded to a multiple of 16 B
+constexpr unsigned kBsRowBytes = kBlendCh * 4;
+constexpr unsigned kBsStagePad = 16;         // the entry prefetch reads one slot past the last entry
+
+__host__ __device__ inline unsigned bs_block_bytes(int k) { return kBsOffBytes + static_cast<unsigned>(kBsTile) * k * 8u; }
+
+// stage = [tile][CSR block][pad for the entry prefetch], rounded to the 128-byte alignment TMA tile loads need
+__host__ __device__ inline unsigned bs_stage_bytes(int k) {
+  return (kBsTile * kBsRowBytes + bs_block_bytes(k) + kBsStagePad + 127u) & ~127u;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One warp per (cloud, tile): block = [uint16 off[129] (pad)][entries sorted by (source, list position)],
+// entry = {byte offset of the target's row inside the staged tile, weight bits}.
+__global__ void __launch_bounds__(256)
+    interp_csr_kernel(const int32_t* __restrict__ idx, const float* __restrict__ weight, int B, int N, int k,
+                      int tiles, unsigned char* __restrict__ csr) {
+  __shared__ int s_cnt[8][kBsSrc];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long wg = static_cast<long>(blockIdx.x) * 8 + warp;
+  if (wg >= static_cast<long>(B) * tiles) return;  // whole warps leave; no CTA barrier below
+  const int b = static_cast<int>(wg / tiles), tile = static_cast<int>(wg % tiles);
+  int* cnt = s_cnt[warp];
+#pragma unroll
+  for (int i = 0; i < kBsSrc / 32; ++i) cnt[lane + 32 * i] = 0;
+  __syncwarp();
+  const int nt = min(kBsTile, N - tile * kBsTile);
+  const int E = nt * k;
+  const size_t p0 = (static_cast<size_t>(b) * N + static_cast<size_t>(tile) * kBsTile) * k;
+  for (int e = lane; e < E; e += 32) atomicAdd(&cnt[__ldg(idx + p0 + e)], 1);
+  __syncwarp();
+  // exclusive prefix over the 128 sources: four consecutive counts per lane + a warp scan
+  int c[4], tot = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { c[i] = cnt[4 * lane + i]; tot += c[i]; }
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  unsigned char* blk = csr + static_cast<size_t>(wg) * bs_block_bytes(k);
+  uint16_t* off = reinterpret_cast<uint16_t*>(blk);
+  uint2* ent = reinterpret_cast<uint2*>(blk + kBsOffBytes);
+  int run = incl - tot;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    off[4 * lane + i] = static_cast<uint16_t>(run);
+    cnt[4 * lane + i] = run;  // becomes the placement cursor
+    run += c[i];
+  }
+  if (lane == 31) off[kBsSrc] = static_cast<uint16_t>(run);
+  __syncwarp();
+  const unsigned below = (1u << lane) - 1u;
+  for (int e0 = 0; e0 < E; e0 += 32) {  // rounds in list order, lanes in list order: a stable sort
+    const int e = e0 + lane;
+    const bool valid = e < E;
+    const int s = valid ? __ldg(idx + p0 + e) : -1 - lane;
+    const unsigned m = __match_any_sync(0xffffffffu, s);
+    const int rank = __popc(m & below);
+    const int pos = valid ? cnt[s] + rank : 0;
+    __syncwarp();
+    if (valid && rank == 0) cnt[s] += __popc(m);
+    __syncwarp();
+    if (valid) ent[pos] = make_uint2(static_cast<unsigned>(e / k) * kBsRowBytes, __float_as_uint(__ldg(weight + p0 + e)));
+  }
+}
+
+__global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
+    interp_bwd_stream_kernel(const __grid_constant__ CUtensorMap gmap, const unsigned char* __restrict__ csr, float alpha,
+                             int N, int S, int C, int k, int tiles, float* __restrict__ gfeat2) {
+  extern __shared__ __align__(128) unsigned char s_stage[];  // kBsStages x [tile 64 x 512 B][CSR block]
+  __shared__ __align__(8) uint64_t s_full[kBsStages], s_empty[kBsStages];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const unsigned blk_bytes = bs_block_bytes(k);
+  const unsigned stage_bytes = bs_stage_bytes(k);
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kBsStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kBsWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kBsWarps) {  // ---- producer: one 2-D TMA tile (64 rows x 512 B) + the tile's CSR block per stage ----
+    if (lane == 0) {
+      tma_prefetch_desc(&gmap);
+      const unsigned char* csrc = csr + static_cast<size_t>(b) * tiles * blk_bytes;
+      for (int t = 0; t < tiles; ++t) {
+        const int st = t % kBsStages;
+        unsigned char* dst = s_stage + static_cast<size_t>(st) * stage_bytes;
+        if (t >= kBsStages) mbar_wait(&s_empty[st], static_cast<unsigned>(t / kBsStages - 1) & 1u);
+        // rows past this cloud's N (next cloud's, or zero fill past the tensor) are loaded but never referenced
+        mbar_expect_tx(&s_full[st], kBsTile * kBsRowBytes + blk_bytes);
+        tma_load_2d(dst, &gmap, chunk * kBlendCh, b * N + t * kBsTile, &s_full[st]);
+        bulk_g2s(dst + kBsTile * kBsRowBytes, csrc + static_cast<size_t>(t) * blk_bytes, blk_bytes, &s_full[st]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps ----
+  // Shared memory is addressed with explicit 32-bit shared-window addresses (ld.shared): the generic-pointer form made
+  // the compiler rebuild the stage address in front of every one of the 16 per-source loops.
+  float4 acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t stage0 = smem_u32(s_stage);
+  for (int t = 0; t < tiles; ++t) {
+    const int st = t % kBsStages;
+    const uint32_t tile = stage0 + static_cast<uint32_t>(st) * stage_bytes;
+    const uint32_t blk = tile + kBsTile * kBsRowBytes;
+    mbar_wait(&s_full[st], static_cast<unsigned>(t / kBsStages) & 1u);
+    // this warp's 17 offsets (warp-uniform): two LDS.128 + one LDS.U16
+    const uint4 oa = lds_u128(blk + 32u * warp);
+    const uint4 ob = lds_u128(blk + 32u * warp + 16u);
+    const unsigned olast = lds_u16(blk + 32u * warp + 32u);
+    const unsigned ow[9] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w, olast};
+    uint32_t ent = blk + kBsOffBytes;
+    uint32_t rowp = tile + lane * 16u;
+    asm volatile("" : "+r"(ent), "+r"(rowp));  // opaque: kept in registers, not rebuilt from %tid / the shared window per source
+    // one cursor over the warp's contiguous entry range; the next entry is always already in flight
+    unsigned m = ow[0] & 0xffffu;
+    uint2 en = lds_u64(ent + m * 8u);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const unsigned end = (i & 1) ? (ow[(i >> 1) + 1] & 0xffffu) : (ow[i >> 1] >> 16);
+#pragma unroll 1
+      for (; m < end; ++m) {
+        const uint2 cur = en;
+        en = lds_u64(ent + (m + 1u) * 8u);  // may be the slot after the last entry: the stage is padded for it
+        const float4 g = lds_f128(rowp + cur.x);
+        const float w = __uint_as_float(cur.y);
+        acc[i].x = __fmaf_rn(w, g.x, acc[i].x);
+        acc[i].y = __fmaf_rn(w, g.y, acc[i].y);
+        acc[i].z = __fmaf_rn(w, g.z, acc[i].z);
+        acc[i].w = __fmaf_rn(w, g.w, acc[i].w);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[st]);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int s = 16 * warp + i;
+    if (s < S) {
+      float4 o;
+      o.x = __fmul_rn(alpha, acc[i].x);
+      o.y = __fmul_rn(alpha, acc[i].y);
+      o.z = __fmul_rn(alpha, acc[i].z);
+      o.w = __fmul_rn(alpha, acc[i].w);
+      *reinterpret_cast<float4*>(gfeat2 + (static_cast<size_t>(b) * S + s) * C + chunk * kBlendCh + lane * 4) = o;
+    }
+  }
+}
+
+// UPP_INTERP_PATH (tuning / test aid): 0 = never take the wide-feature paths, 1 = take them whenever the
+// shape allows, unset = when the shape allows AND the problem is large enough to pay for the extra launch.
+static int interp_path_env() {
+  const char* v = getenv("UPP_INTERP_PATH");
+  return v ? atoi(v) : -1;
+}
+
+static bool aligned16(const void* a, const void* b = nullptr, const void* c = nullptr) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) % 16) == 0;
+}
+
+// fewest target spans per (cloud, chunk) whose CTA count fills whole residency waves (within 3 % of the best fill)
+static int blend_pick_spans(long items0, int N, long wave) {
+  int best = 1;
+  double best_eff = 0.0;
+  const int smax = N / 128 < 1 ? 1 : (N / 128 > 64 ? 64 : N / 128);
+  for (int sp = 1; sp <= smax; ++sp) {
+    const long items = items0 * sp;
+    const double eff = static_cast<double>(items) / (static_cast<double>(wave) * ((items + wave - 1) / wave));
+    if (eff > best_eff + 0.03) { best_eff = eff; best = sp; }
+  }
+  return best;
+}
+
 int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, const float* base, float alpha,
                       float eps, int B, int N, int S, int C, int k, float* out, int32_t* idx, float* weight,
                       float* distk, cudaStream_t st) {
+  const bool vec4 = (C % 4 == 0) && aligned16(feat2, out, base);
+  // wide features: selection alone, then the shared-memory blend (interp_blend_kernel)
+  const int env = interp_path_env();
+  const bool blend_ok = vec4 && C > 0 && C % kBlendCh == 0 && S <= kBlendMaxS && B <= 65535;
+  const bool blend_big = static_cast<size_t>(B) * N * C >= (static_cast<size_t>(8) << 20) && N >= 256;
+  const bool two_phase = blend_ok && (env == 1 || (env < 0 && blend_big));
+  const int csel = two_phase ? 0 : C;
+  // UPP_INTERP_SELECT (test aid): 0 = never the thread-per-target selection, 1 = whenever k <= 4 and S <= 1024
+  const char* sv = getenv("UPP_INTERP_SELECT");
+  const int senv = sv ? atoi(sv) : -1;
+  const bool thread_select = two_phase && k <= 4 && S <= 1024 && senv != 0 &&
+                             (senv == 1 || static_cast<long>(B) * N >= 4096);
+  if (thread_select) {
+    dim3 sgrid((N + 127) / 128, B);
+    const size_t ssm = static_cast<size_t>(S) * 7 * sizeof(float);
+#define UPP_SELECT(K_) interp_select_kernel<K_><<<sgrid, 128, ssm, st>>>(xyz1, xyz2, eps, N, S, idx, weight, distk)
+    if (k == 1) UPP_SELECT(1);
+    else if (k == 2) UPP_SELECT(2);
+    else if (k == 3) UPP_SELECT(3);
+    else UPP_SELECT(4);
+#undef UPP_SELECT
+  } else {
   // targets per warp: as many as keep >= 4 residency waves (3 CTAs x 148 SMs) of CTAs in the grid
   int tpw = 1;
   if (S <= kKnnTile)
@@ -397,11 +849,9 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
       if (static_cast<long>(B) * ((N + kKnnWarps * cand - 1) / (kKnnWarps * cand)) >= 4L * 3 * 148) { tpw = cand; break; }
   dim3 grid((N + kKnnWarps * tpw - 1) / (kKnnWarps * tpw), B);
   const size_t smem = static_cast<size_t>(min(S, kKnnTile)) * 3 * sizeof(float);
-  const bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat2) | reinterpret_cast<uintptr_t>(out) |
-                                      reinterpret_cast<uintptr_t>(base)) % 16 == 0);
   const int threads = kKnnWarps * kWarp;
 #define UPP_INTERP(V_, SL_) \
-  interp_fwd_kernel<V_, SL_><<<grid, threads, smem, st>>>(xyz1, xyz2, feat2, base, alpha, eps, N, S, C, k, tpw, out, idx, weight, distk)
+  interp_fwd_kernel<V_, SL_><<<grid, threads, smem, st>>>(xyz1, xyz2, feat2, base, alpha, eps, N, S, csel, k, tpw, out, idx, weight, distk)
   if (vec4) {
     if (S <= 128) UPP_INTERP(true, 4);
     else if (S <= 256) UPP_INTERP(true, 8);
@@ -412,20 +862,57 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
     else UPP_INTERP(false, 32);
   }
 #undef UPP_INTERP
+  }
+  count_launch();
+  int rc = launch_status();
+  if (rc != UPP_OK || !two_phase) return rc;
+
+  const int chunks = C / kBlendCh;
+  const size_t bsmem = static_cast<size_t>(S) * kBlendCh * sizeof(float) + static_cast<size_t>(kBlendSub) * k * 8;
+  const long per_sm = bsmem <= 74 * 1024 ? 3 : 2;
+  const int spans = blend_pick_spans(static_cast<long>(chunks) * B, N, per_sm * 148);
+  int span = ((N + spans - 1) / spans + 15) & ~15;  // whole trips of 8 warps x 2 targets
+  dim3 bgrid(chunks, (N + span - 1) / span, B);
+  CUtensorMap fmap;  // feat2 as (B*S rows) x C, box = S rows x 128 channels
+  rc = make_tmap_2d_f32(&fmap, feat2, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * S,
+                        static_cast<uint64_t>(C) * sizeof(float), kBlendCh, static_cast<uint32_t>(S));
+  if (rc != UPP_OK) return rc;
+#define UPP_BLEND(K_)                                                                                                    \
+  do {                                                                                                                   \
+    if (bsmem > 40 * 1024) {                                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(interp_blend_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                           static_cast<int>(bsmem));                                                     \
+      if (e != cudaSuccess) return static_cast<int>(e);                                                                  \
+    }                                                                                                                    \
+    interp_blend_kernel<K_><<<bgrid, kBlendWarps * kWarp, bsmem, st>>>(fmap, base, alpha, idx, weight, N, S, C, k, span, \
+                                                                      out);                                             \
+  } while (0)
+  if (k == 3) UPP_BLEND(3);
+  else if (k == 4) UPP_BLEND(4);
+  else if (k == 8) UPP_BLEND(8);
+  else UPP_BLEND(0);
+#undef UPP_BLEND
   count_launch();
   return launch_status();
+}
+
+// Workspace of the streamed backward (one CSR block per cloud and 64-target tile); 0 when the shape has no such path.
+size_t interp_bwd_workspace_bytes(int B, int N, int S, int C, int k) {
+  if (B <= 0 || N <= 0 || C <= 0 || C % kBlendCh != 0 || S > kBsSrc || k > kBsMaxK || B > 65535) return 0;
+  const size_t tiles = (static_cast<size_t>(N) + kBsTile - 1) / kBsTile;
+  return static_cast<size_t>(B) * tiles * bs_block_bytes(k);
 }
 
 int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight, const float* distk,
                       const float* feat2, const float* xyz1, const float* xyz2, float alpha, float eps, int B,
                       int N, int S, int C, int k, float* gfeat2, float* gxyz1, float* gxyz2, float* gd_ws,
-                      cudaStream_t st) {
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
   const bool want_xyz = gd_ws != nullptr;
   if (want_xyz) {
     const size_t rows = static_cast<size_t>(B) * N;
     const size_t want = (rows + 7) / 8;
     const int blocks = static_cast<int>(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-    const bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(feat2)) % 16 == 0);
+    const bool vec4 = (C % 4 == 0) && aligned16(gout, feat2);
     if (vec4)
       interp_bwd_target_kernel<true><<<blocks, 256, 0, st>>>(gout, feat2, xyz1, xyz2, idx, weight, distk, alpha, eps, N,
                                                              S, C, k, rows, gd_ws, gxyz1);
@@ -436,16 +923,46 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
     int rc = launch_status();
     if (rc != UPP_OK) return rc;
   }
-  dim3 grid(S, B);
-  const float* gdp = want_xyz ? gd_ws : nullptr;
-  float* g2p = want_xyz ? gxyz2 : nullptr;
+  // wide features: the feature gradient streams grad_out once (interp_bwd_stream_kernel); the source-side kernel
+  // then only carries the coordinate terms (C = 0: list scan, no feature rows)
+  const int env = interp_path_env();
+  const size_t need = interp_bwd_workspace_bytes(B, N, S, C, k);
+  const bool stream_ok = need > 0 && ws != nullptr && ws_bytes >= need && aligned16(gout, gfeat2, ws);
+  const bool stream_big = static_cast<long>(C / kBlendCh) * B >= 120 && N >= 512;
+  const bool streamed = stream_ok && (env == 1 || (env < 0 && stream_big));
+  const int csrc = streamed ? 0 : C;
+  if (!streamed || want_xyz) {
+    dim3 grid(S, B);
+    const float* gdp = want_xyz ? gd_ws : nullptr;
+    float* g2p = want_xyz ? gxyz2 : nullptr;
 #define UPP_SRC(G_) \
-  interp_bwd_source_kernel<G_><<<grid, kSrcThreads, 0, st>>>(gout, idx, weight, gdp, xyz1, xyz2, alpha, N, S, C, k, gfeat2, g2p)
-  if (C > 1024) UPP_SRC(1);       // 256 threads x 8 channels per pass
-  else if (C > 512) UPP_SRC(2);
-  else if (C > 256) UPP_SRC(4);
-  else UPP_SRC(8);                // 32 threads x 8 channels = 256 channels per group
+  interp_bwd_source_kernel<G_><<<grid, kSrcThreads, 0, st>>>(gout, idx, weight, gdp, xyz1, xyz2, alpha, N, S, csrc, k, gfeat2, g2p)
+    if (csrc > 1024) UPP_SRC(1);       // 256 threads x 8 channels per pass
+    else if (csrc > 512) UPP_SRC(2);
+    else if (csrc > 256) UPP_SRC(4);
+    else UPP_SRC(8);                // 32 threads x 8 channels = 256 channels per group
 #undef UPP_SRC
+    count_launch();
+    int rc = launch_status();
+    if (rc != UPP_OK || !streamed) return rc;
+  }
+  const int tiles = (N + kBsTile - 1) / kBsTile;
+  const long warps = static_cast<long>(B) * tiles;
+  interp_csr_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>(idx, weight, B, N, k, tiles,
+                                                                            static_cast<unsigned char*>(ws));
+  count_launch();
+  int rc = launch_status();
+  if (rc != UPP_OK) return rc;
+  const size_t ssmem = static_cast<size_t>(kBsStages) * bs_stage_bytes(k);
+  CUtensorMap gmap;  // grad_out as (B*N rows) x C, box = 64 rows x 128 channels
+  rc = make_tmap_2d_f32(&gmap, gout, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * N,
+                        static_cast<uint64_t>(C) * sizeof(float), kBlendCh, kBsTile);
+  if (rc != UPP_OK) return rc;
+  cudaError_t e = cudaFuncSetAttribute(interp_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(ssmem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  interp_bwd_stream_kernel<<<dim3(C / kBlendCh, B), (kBsWarps + 1) * kWarp, ssmem, st>>>(
+      gmap, static_cast<const unsigned char*>(ws), alpha, N, S, C, k, tiles, gfeat2);
   count_launch();
   return launch_status();
 }

@@ -34,13 +34,15 @@ _SIGNATURES = {
     "upp_group_bwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "upp_knn_points_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "upp_interp_fwd_f32": [_vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
-    "upp_interp_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "upp_interp_bwd_workspace_bytes": [_i, _i, _i, _i, _i],
+    "upp_interp_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
 }
 _RESTYPES = {
     "upp_error_string": ctypes.c_char_p,
     "upp_launch_count": ctypes.c_ulonglong,
     "upp_fps_workspace_bytes": _sz,
     "upp_chamfer_fwd_workspace_bytes": _sz,
+    "upp_interp_bwd_workspace_bytes": _sz,
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -287,10 +287,13 @@ def interp_backward(grad_out, idx, weight, S, alpha=1.0, xyz_terms=None):
         g1 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
         g2 = torch.empty((B, int(S), 3), dtype=torch.float32, device=dev)
         gd = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws_bytes = int(lib.upp_interp_bwd_workspace_bytes(B, N, int(S), C, k))  # 0: no streamed path for this shape
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     with _on(grad_out):
-        rc = _lib.load().upp_interp_bwd_f32(_ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(dist), _ptr(points2),
-                                            _ptr(xyz1), _ptr(xyz2), float(alpha), float(eps), B, N, int(S), C, k,
-                                            _ptr(gp2), _ptr(g1), _ptr(g2), _ptr(gd), _stream(grad_out))
+        rc = lib.upp_interp_bwd_f32(_ptr(grad_out), _ptr(idx), _ptr(weight), _ptr(dist), _ptr(points2),
+                                    _ptr(xyz1), _ptr(xyz2), float(alpha), float(eps), B, N, int(S), C, k,
+                                    _ptr(gp2), _ptr(g1), _ptr(g2), _ptr(gd), _ptr(ws), ws_bytes, _stream(grad_out))
     _lib.check(rc, "upp_interp_bwd_f32")
     return gp2, g1, g2
 

@@ -230,11 +230,16 @@ UPP_API int upp_interp_fwd_f32(const float* xyz1, const float* xyz2, const float
  * Coordinate gradients (through the weights) are produced when gd_workspace (B*N*k floats) is given:
  * grad_xyz1 (B,N,3) and grad_xyz2 (B,S,3) are then OVERWRITTEN (either may be NULL) and dist, feat2,
  * xyz1, xyz2 must be the forward's; with gd_workspace == NULL those five pointers are ignored.
- * (The gradient w.r.t. base is grad_out itself.) */
+ * (The gradient w.r.t. base is grad_out itself.)
+ * workspace (nullable): upp_interp_bwd_workspace_bytes(B,N,S,C,k) bytes of 16-byte-aligned scratch; when given
+ * (and the size query is non-zero: C a multiple of 128, S <= 128, k <= 8) large problems take the streamed
+ * feature-gradient kernel, which reads grad_out once instead of k times.  Results are the same either way. */
+UPP_API size_t upp_interp_bwd_workspace_bytes(int B, int N, int S, int C, int k);
 UPP_API int upp_interp_bwd_f32(const float* grad_out, const int32_t* idx, const float* weight, const float* dist,
                        const float* feat2, const float* xyz1, const float* xyz2, float alpha, float eps,
                        int B, int N, int S, int C, int k, float* grad_feat2, float* grad_xyz1,
-                       float* grad_xyz2, float* gd_workspace, upp_stream_t stream);
+                       float* grad_xyz2, float* gd_workspace, void* workspace, size_t workspace_bytes,
+                       upp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Introspection used by bench.py / tests: number of kernel launches the library has issued

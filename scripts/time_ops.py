@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--sweep-fps", action="store_true")
     ap.add_argument("--sweep-chamfer", action="store_true")
+    ap.add_argument("--sweep-chamfer2", action="store_true")
     ap.add_argument("--sweep-fps2", action="store_true", help="v2 FPS kernel: warps x point-pairs x stage-2 variant")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -93,6 +94,20 @@ def main():
                             lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
             for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_S2", "UPP_FPS_SEARCH"):
                 os.environ.pop(k, None)
+        return
+    if args.sweep_chamfer2:  # residency variants of the packed kernel (register cap -> CTAs per SM)
+        for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192)]:
+            a = torch.rand(B, N, 3, generator=g).to(dev)
+            b = torch.rand(B, M, 3, generator=g).to(dev)
+            for v, name in [(-1, "default R8W4 83 regs 5/SM"), (37, "R8W4 80 regs 6/SM"), (38, "R8W4 <=128 regs 4/SM"),
+                            (39, "R8W4 <=168 regs 3/SM"), (40, "R8W8 <=80 regs 3/SM")]:
+                for ch in (0, 1, 2, 4):
+                    os.environ["UPP_CH_VARIANT"] = str(v)
+                    os.environ["UPP_CH_CHUNKS"] = str(ch)
+                    rec(f"chamfer-sweep2 {name} chunks={ch or 'auto'} B{B} N{N} M{M} +sums", lambda: ops.chamfer_forward(a, b, True),
+                        lambda us: {"tflops_8NM": round(8.0 * N * M * B / us / 1e6, 2)})
+            os.environ.pop("UPP_CH_CHUNKS", None)
+            os.environ.pop("UPP_CH_VARIANT", None)
         return
     if args.sweep_chamfer:
         for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 1024, 1024), (64, 32, 1024), (8, 2048, 2048)]:
@@ -151,13 +166,20 @@ def main():
         x2 = (torch.rand(B, S, 3, generator=g) * 2 - 1).to(dev)
         p2, go = torch.randn(B, S, C, generator=g).to(dev), torch.randn(B, N, C, generator=g).to(dev)
         hbm = 4.0 * B * (N * C + S * C)
-        rec(f"interp_fwd B{B} N{N} S{S} C{C} k{k}", lambda: ops.interp_forward(x1, x2, p2, k, 1e-4),
-            lambda us: {"gbs": round(hbm / us / 1e3, 1)})
         out, idx, w, d = ops.interp_forward(x1, x2, p2, k, 1e-4)
-        rec(f"interp_bwd_feat B{B} N{N} S{S} C{C} k{k}", lambda: ops.interp_backward(go, idx, w, S),
-            lambda us: {"gbs": round(hbm / us / 1e3, 1)})
-        rec(f"interp_bwd_feat+xyz B{B} N{N} S{S} C{C} k{k}",
-            lambda: ops.interp_backward(go, idx, w, S, xyz_terms=(d, p2, x1, x2, 1e-4)), lambda us: {"gbs": round(hbm / us / 1e3, 1)})
+        # default dispatch, then the one-launch / source-side kernels (0) and the wide-feature kernels (1) forced
+        for path, tag in ((None, ""), ("0", " [UPP_INTERP_PATH=0]"), ("1", " [UPP_INTERP_PATH=1]")):
+            if path is None:
+                os.environ.pop("UPP_INTERP_PATH", None)
+            else:
+                os.environ["UPP_INTERP_PATH"] = path
+            rec(f"interp_fwd B{B} N{N} S{S} C{C} k{k}{tag}", lambda: ops.interp_forward(x1, x2, p2, k, 1e-4),
+                lambda us: {"gbs": round(hbm / us / 1e3, 1)})
+            rec(f"interp_bwd_feat B{B} N{N} S{S} C{C} k{k}{tag}", lambda: ops.interp_backward(go, idx, w, S),
+                lambda us: {"gbs": round(hbm / us / 1e3, 1)})
+            rec(f"interp_bwd_feat+xyz B{B} N{N} S{S} C{C} k{k}{tag}",
+                lambda: ops.interp_backward(go, idx, w, S, xyz_terms=(d, p2, x1, x2, 1e-4)), lambda us: {"gbs": round(hbm / us / 1e3, 1)})
+        os.environ.pop("UPP_INTERP_PATH", None)
     if args.only and "interp" in args.only:
         return
     try:

@@ -562,6 +562,80 @@ def test_interp_backward_matches_oracle_and_is_deterministic(U, O, dev, B, N, S,
         assert torch.equal(a, gp2) and torch.equal(b1, g1) and torch.equal(b2, g2)
 
 
+WIDE_SHAPES = [  # shapes the wide-feature kernels accept: C a multiple of 128, few sources
+    (2, 2048, 128, 1152, 3),  # seg feature propagation (BASELINE configs[4])
+    (3, 64, 32, 384, 8),      # Block propagate
+    (2, 333, 150, 256, 5),    # ragged target count, S > 128 (blend only; the streamed backward declines)
+    (1, 130, 128, 128, 8),    # one channel chunk, S and k at the streamed backward's limits, N % 64 != 0
+    (2, 17, 5, 128, 1),
+]
+
+
+@pytest.mark.parametrize("B,N,S,C,k", WIDE_SHAPES)
+@pytest.mark.parametrize("with_base", [False, True])
+def test_interp_forward_two_phase_is_bit_identical(U, O, dev, monkeypatch, B, N, S, C, k, with_base):
+    """Selection + shared-memory blend (interp_blend_kernel, forced by UPP_INTERP_PATH=1) against the one-launch
+    kernel (UPP_INTERP_PATH=0): same arithmetic in the same order, so bit-equal; and against the oracle."""
+    g = torch.Generator().manual_seed(N * 7 + C)
+    x1, x2 = torch.rand(B, N, 3, generator=g) * 2 - 1, torch.rand(B, S, 3, generator=g) * 2 - 1
+    p2 = torch.randn(B, S, C, generator=g)
+    base = torch.randn(B, N, C, generator=g).to(dev) if with_base else None
+    alpha, eps = (0.3, 1e-3) if with_base else (1.0, 1e-4)
+    got = {}
+    # "1s": the selection by the thread-per-target kernel (k <= 4), "1": by the warp-per-target kernel
+    for tag, path, select in (("0", "0", "0"), ("1", "1", "0"), ("1s", "1", "1")):
+        monkeypatch.setenv("UPP_INTERP_PATH", path)
+        monkeypatch.setenv("UPP_INTERP_SELECT", select)
+        n0 = U.launch_count()
+        got[tag] = U.ops.interp_forward(x1.to(dev), x2.to(dev), p2.to(dev), k, eps, base=base, alpha=alpha)
+        assert U.launch_count() - n0 == (1 if path == "0" else 2)
+    for tag in ("1", "1s"):
+        for a, b in zip(got["0"], got[tag]):
+            assert torch.equal(a, b), tag
+    o_out, o_idx, o_w, o_d = O.interp_fwd(x1.numpy(), x2.numpy(), p2.numpy(), k, eps,
+                                          base=base.cpu().numpy() if with_base else None, alpha=alpha)
+    assert np.array_equal(got["1"][1].cpu().numpy(), o_idx)
+    np.testing.assert_allclose(got["1"][0].cpu().numpy(), o_out, rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,N,S,C,k", WIDE_SHAPES)
+def test_interp_backward_streamed_matches_source_side_kernel(U, O, dev, monkeypatch, B, N, S, C, k):
+    """CSR + streamed feature gradient (UPP_INTERP_PATH=1) against the source-side kernel (=0): per source the same
+    fmaf sequence in (n, j) order -- bit-equal where the source-side kernel runs one thread group (C > 1024),
+    1e-5 otherwise -- deterministic, with and without the coordinate terms, and against the oracle."""
+    g = torch.Generator().manual_seed(S * 3 + C)
+    x1, x2 = torch.rand(B, N, 3, generator=g) * 2 - 1, torch.rand(B, S, 3, generator=g) * 2 - 1
+    p2, go = torch.randn(B, S, C, generator=g), torch.randn(B, N, C, generator=g)
+    eps, alpha = 1e-3, 0.3
+    out, idx, w, d = U.ops.interp_forward(x1.to(dev), x2.to(dev), p2.to(dev), k, eps, alpha=alpha)
+    terms = (d, p2.to(dev), x1.to(dev), x2.to(dev), eps)
+    res = {}
+    for path in ("0", "1"):
+        monkeypatch.setenv("UPP_INTERP_PATH", path)
+        n0 = U.launch_count()
+        res[path, "feat"] = U.ops.interp_backward(go.to(dev), idx, w, S, alpha=alpha)
+        n1 = U.launch_count()
+        res[path, "xyz"] = U.ops.interp_backward(go.to(dev), idx, w, S, alpha=alpha, xyz_terms=terms)
+        streamed = path == "1" and S <= 128 and k <= 8
+        assert n1 - n0 == (2 if streamed else 1) and U.launch_count() - n1 == (4 if streamed else 2)
+    ref, new = res["0", "feat"][0], res["1", "feat"][0]
+    if C > 1024:
+        assert torch.equal(ref, new)
+    else:
+        scale = max(1.0, float(ref.abs().max()))
+        np.testing.assert_allclose(new.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-6 * scale)
+    assert torch.equal(res["1", "xyz"][0], new)                       # same feature gradient with the coordinate terms
+    for i in (1, 2):                                                   # coordinate terms: same kernels either way
+        assert torch.equal(res["1", "xyz"][i], res["0", "xyz"][i])
+    monkeypatch.setenv("UPP_INTERP_PATH", "1")
+    for _ in range(2):
+        assert torch.equal(U.ops.interp_backward(go.to(dev), idx, w, S, alpha=alpha)[0], new)
+    o_gp2, _, _ = O.interp_bwd(go.numpy(), p2.numpy(), x1.numpy(), x2.numpy(), idx.cpu().numpy(),
+                               w.cpu().numpy(), d.cpu().numpy(), eps, alpha=alpha)
+    scale = max(1.0, float(np.abs(o_gp2).max()))
+    np.testing.assert_allclose(new.cpu().numpy(), o_gp2, rtol=1e-4, atol=1e-5 * scale)
+
+
 def test_golden_reference_propagate_and_feature_propagation(U, dev):
     """The reference's own propagate / PointNetFeaturePropagation outputs and float64 autograd gradients
     (tests/golden/golden_interp.npz) against the drop-in functions, autograd included."""
