@@ -225,18 +225,37 @@ constexpr int kBlendWarps = 8;
 constexpr int kBlendMaxS = 192;   // 96 KB of staged features: two CTAs per SM (three up to S = 136)
 constexpr int kBlendSub = 128;    // targets per record batch
 
-// Thread-per-target selection for k = K <= 4 (single staged tile of sources, S <= kKnnTile).  Sources are
-// visited in index order and a candidate only moves ahead of strictly larger distances, so equal distances
-// keep the lower source index first: the order of the warp kernels (stable sort by distance).  Distances are
-// DistExpanded's, operation for operation (|b|^2 is computed once per source while staging).
+// Selection for k = K <= 4 without a warp per target: FOUR threads per target (adjacent lanes), each scanning one
+// contiguous quarter of the staged sources (single tile, S <= 1024) with a branch-free sorted insertion, then two
+// shuffle-xor merge rounds.  Sources are visited in index order, a candidate only moves ahead of strictly larger
+// distances, and on equal distances a merge keeps the entry of the lower quarter first: equal distances keep the
+// lower source index, the order of the warp kernels (a stable sort by distance).  Distances are DistExpanded's,
+// operation for operation (|b|^2 is computed once per source while staging).  Quarter q lives at s4[q * (Q + 1) ...]:
+// the one-slot skew keeps the four broadcast LDS.128 of a warp in different banks.
 template <int K>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void topk_insert(float (&bd)[K], int (&bi)[K], float d, int s, bool ties_first) {
+  bool lt[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) lt[j] = ties_first ? d <= bd[j] : d < bd[j];
+#pragma unroll
+  for (int j = K - 1; j >= 0; --j) {
+    if (j > 0 && lt[j - 1]) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; }
+    else if (lt[j]) { bd[j] = d; bi[j] = s; }
+  }
+}
+
+constexpr int kSelThreads = 128;
+
+// TPT = threads per target (1, 2 or 4): the sources are cut into TPT contiguous parts.
+template <int K, int TPT>
+__global__ void __launch_bounds__(kSelThreads)
     interp_select_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2, float eps, int N, int S,
                          int32_t* __restrict__ idx_out, float* __restrict__ w_out, float* __restrict__ d_out) {
-  extern __shared__ __align__(16) float s_sel[];  // [S x {x, y, z, |b|^2}] then the AoS staging area (3 S floats)
+  extern __shared__ __align__(16) float s_sel[];  // [TPT x (Q + 1) x {x, y, z, |b|^2}] then the AoS staging area (3 S floats)
   __shared__ __align__(8) uint64_t s_bar;
+  const int Q = (S + TPT - 1) / TPT;
   float4* s4 = reinterpret_cast<float4*>(s_sel);
-  float* s_ref = s_sel + 4 * S;
+  float* s_ref = s_sel + 4 * TPT * (Q + 1);
   const int b = blockIdx.y;
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
@@ -247,32 +266,45 @@ __global__ void __launch_bounds__(128)
   stage_points(s_ref, xyz2 + static_cast<size_t>(b) * S * 3, S, &s_bar, parity);
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     const float x = s_ref[3 * s], y = s_ref[3 * s + 1], z = s_ref[3 * s + 2];
-    s4[s] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    const int q = s / Q;
+    s4[q * (Q + 1) + (s - q * Q)] =
+        make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
   }
   __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const size_t row = static_cast<size_t>(b) * N + n;
+  const int q = threadIdx.x % TPT;
+  const int n = blockIdx.x * (kSelThreads / TPT) + threadIdx.x / TPT;
+  const bool active = n < N;
+  const size_t row = static_cast<size_t>(b) * N + (active ? n : N - 1);
   const float qx = __ldg(xyz1 + row * 3), qy = __ldg(xyz1 + row * 3 + 1), qz = __ldg(xyz1 + row * 3 + 2);
   const float s1 = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz));
   float bd[K];
   int bi[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) { bd[j] = __int_as_float(0x7f800000); bi[j] = 0; }
+  const int sbeg = q * Q;
+  const int cnt = min(Q, S - sbeg);  // <= 0 for an empty quarter
+  const float4* sq = s4 + q * (Q + 1);
 #pragma unroll 4
-  for (int s = 0; s < S; ++s) {
-    const float4 r = s4[s];  // same address in every lane: one broadcast LDS.128
+  for (int j = 0; j < cnt; ++j) {
+    const float4 r = sq[j];
     const float dot = __fmaf_rn(qz, r.z, __fmaf_rn(qy, r.y, __fmul_rn(qx, r.x)));
     const float d = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), s1), r.w);
-    bool lt[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) lt[j] = d < bd[j];
-#pragma unroll
-    for (int j = K - 1; j >= 0; --j) {
-      if (j > 0 && lt[j - 1]) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; }
-      else if (lt[j]) { bd[j] = d; bi[j] = s; }
-    }
+    topk_insert<K>(bd, bi, d, sbeg + j, false);
   }
+#pragma unroll
+  for (int x = 1; x < TPT; x <<= 1) {  // merge with the partner part's sorted list; the lower part wins ties
+    float pd[K];
+    int pi[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      pd[j] = __shfl_xor_sync(0xffffffffu, bd[j], x);
+      pi[j] = __shfl_xor_sync(0xffffffffu, bi[j], x);
+    }
+    const bool partner_lower = (q & x) != 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) topk_insert<K>(bd, bi, pd[j], pi[j], partner_lower);
+  }
+  if (!active || q != 0) return;
   // weights: dist_recip = 1/(d + eps); weight = dist_recip / sum(dist_recip)  (sum in neighbour order)
   float r[K], norm = 0.f;
 #pragma unroll
@@ -660,7 +692,19 @@ __global__ void __launch_bounds__(256)
   const int nt = min(kBsTile, N - tile * kBsTile);
   const int E = nt * k;
   const size_t p0 = (static_cast<size_t>(b) * N + static_cast<size_t>(tile) * kBsTile) * k;
-  for (int e = lane; e < E; e += 32) atomicAdd(&cnt[__ldg(idx + p0 + e)], 1);
+  // the tile's whole list in registers first (one exposed memory latency instead of one per round)
+  constexpr int kRounds = kBsTile * kBsMaxK / 32;
+  int si[kRounds];
+  float sw[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int e = r * 32 + lane;
+    si[r] = (r * 32 < E && e < E) ? __ldg(idx + p0 + e) : -1 - lane;  // distinct negatives: invalid lanes match nobody
+    sw[r] = (r * 32 < E && e < E) ? __ldg(weight + p0 + e) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r)
+    if (r * 32 < E && si[r] >= 0) atomicAdd(&cnt[si[r]], 1);
   __syncwarp();
   // exclusive prefix over the 128 sources: four consecutive counts per lane + a warp scan
   int c[4], tot = 0;
@@ -686,17 +730,20 @@ __global__ void __launch_bounds__(256)
   if (lane == 31) off[kBsSrc] = static_cast<uint16_t>(run);
   __syncwarp();
   const unsigned below = (1u << lane) - 1u;
-  for (int e0 = 0; e0 < E; e0 += 32) {  // rounds in list order, lanes in list order: a stable sort
-    const int e = e0 + lane;
-    const bool valid = e < E;
-    const int s = valid ? __ldg(idx + p0 + e) : -1 - lane;
-    const unsigned m = __match_any_sync(0xffffffffu, s);
-    const int rank = __popc(m & below);
-    const int pos = valid ? cnt[s] + rank : 0;
-    __syncwarp();
-    if (valid && rank == 0) cnt[s] += __popc(m);
-    __syncwarp();
-    if (valid) ent[pos] = make_uint2(static_cast<unsigned>(e / k) * kBsRowBytes, __float_as_uint(__ldg(weight + p0 + e)));
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {  // rounds in list order, lanes in list order: a stable sort
+    if (r * 32 < E) {                  // warp-uniform
+      const int e = r * 32 + lane;
+      const int s = si[r];
+      const bool valid = s >= 0;
+      const unsigned m = __match_any_sync(0xffffffffu, s);
+      const int rank = __popc(m & below);
+      const int pos = valid ? cnt[s] + rank : 0;
+      __syncwarp();
+      if (valid && rank == 0) cnt[s] += __popc(m);
+      __syncwarp();
+      if (valid) ent[pos] = make_uint2(static_cast<unsigned>(e / k) * kBsRowBytes, __float_as_uint(sw[r]));
+    }
   }
 }
 
@@ -741,9 +788,9 @@ __global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
   // ---- consumer warps ----
   // Shared memory is addressed with explicit 32-bit shared-window addresses (ld.shared): the generic-pointer form made
   // the compiler rebuild the stage address in front of every one of the 16 per-source loops.
-  float4 acc[16];
+  f32x2 acc[16][2];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = pack2(0.f, 0.f);
   const uint32_t stage0 = smem_u32(s_stage);
   for (int t = 0; t < tiles; ++t) {
     const int st = t % kBsStages;
@@ -758,7 +805,9 @@ __global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
     uint32_t ent = blk + kBsOffBytes;
     uint32_t rowp = tile + lane * 16u;
     asm volatile("" : "+r"(ent), "+r"(rowp));  // opaque: kept in registers, not rebuilt from %tid / the shared window per source
-    // one cursor over the warp's contiguous entry range; the next entry is always already in flight
+    // one cursor over the warp's contiguous entry range; the next entry is always already in flight.  (Also keeping
+    // the next grad_out row in flight -- two entries + one row ahead -- was measured slower: 66 vs 56 us, the loop is
+    // issue-bound, not latency-bound, and the deeper pipeline costs three more instructions per match.)
     unsigned m = ow[0] & 0xffffu;
     uint2 en = lds_u64(ent + m * 8u);
 #pragma unroll
@@ -768,27 +817,24 @@ __global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
       for (; m < end; ++m) {
         const uint2 cur = en;
         en = lds_u64(ent + (m + 1u) * 8u);  // may be the slot after the last entry: the stage is padded for it
-        const float4 g = lds_f128(rowp + cur.x);
-        const float w = __uint_as_float(cur.y);
-        acc[i].x = __fmaf_rn(w, g.x, acc[i].x);
-        acc[i].y = __fmaf_rn(w, g.y, acc[i].y);
-        acc[i].z = __fmaf_rn(w, g.z, acc[i].z);
-        acc[i].w = __fmaf_rn(w, g.w, acc[i].w);
+        const ulonglong2 g = lds_v2u64(rowp + cur.x);
+        const f32x2 W2 = pack2(__uint_as_float(cur.y), __uint_as_float(cur.y));
+        acc[i][0] = fma2(W2, g.x, acc[i][0]);  // per half == fmaf(w, g, acc): the source-side kernel's arithmetic
+        acc[i][1] = fma2(W2, g.y, acc[i][1]);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[st]);
   }
+  const f32x2 A2 = pack2(alpha, alpha);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int s = 16 * warp + i;
     if (s < S) {
-      float4 o;
-      o.x = __fmul_rn(alpha, acc[i].x);
-      o.y = __fmul_rn(alpha, acc[i].y);
-      o.z = __fmul_rn(alpha, acc[i].z);
-      o.w = __fmul_rn(alpha, acc[i].w);
-      *reinterpret_cast<float4*>(gfeat2 + (static_cast<size_t>(b) * S + s) * C + chunk * kBlendCh + lane * 4) = o;
+      ulonglong2 o;
+      o.x = mul2(A2, acc[i][0]);
+      o.y = mul2(A2, acc[i][1]);
+      *reinterpret_cast<ulonglong2*>(gfeat2 + (static_cast<size_t>(b) * S + s) * C + chunk * kBlendCh + lane * 4) = o;
     }
   }
 }
@@ -833,13 +879,25 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   const bool thread_select = two_phase && k <= 4 && S <= 1024 && senv != 0 &&
                              (senv == 1 || static_cast<long>(B) * N >= 4096);
   if (thread_select) {
-    dim3 sgrid((N + 127) / 128, B);
-    const size_t ssm = static_cast<size_t>(S) * 7 * sizeof(float);
-#define UPP_SELECT(K_) interp_select_kernel<K_><<<sgrid, 128, ssm, st>>>(xyz1, xyz2, eps, N, S, idx, weight, distk)
-    if (k == 1) UPP_SELECT(1);
-    else if (k == 2) UPP_SELECT(2);
-    else if (k == 3) UPP_SELECT(3);
-    else UPP_SELECT(4);
+    const char* tv = getenv("UPP_INTERP_TPT");  // tuning aid: threads per target (1, 2, 4)
+    const int tpt = tv ? atoi(tv) : 1;
+#define UPP_SELECT(K_, T_)                                                                                          \
+  do {                                                                                                             \
+    dim3 sgrid((N + kSelThreads / T_ - 1) / (kSelThreads / T_), B);                                                \
+    const size_t ssm = (static_cast<size_t>((S + T_ - 1) / T_ + 1) * 4 * T_ + static_cast<size_t>(S) * 3) * sizeof(float); \
+    interp_select_kernel<K_, T_><<<sgrid, kSelThreads, ssm, st>>>(xyz1, xyz2, eps, N, S, idx, weight, distk);      \
+  } while (0)
+#define UPP_SELECT_K(T_)            \
+  do {                              \
+    if (k == 1) UPP_SELECT(1, T_);  \
+    else if (k == 2) UPP_SELECT(2, T_); \
+    else if (k == 3) UPP_SELECT(3, T_); \
+    else UPP_SELECT(4, T_);         \
+  } while (0)
+    if (tpt == 4) UPP_SELECT_K(4);
+    else if (tpt == 2) UPP_SELECT_K(2);
+    else UPP_SELECT_K(1);
+#undef UPP_SELECT_K
 #undef UPP_SELECT
   } else {
   // targets per warp: as many as keep >= 4 residency waves (3 CTAs x 148 SMs) of CTAs in the grid

@@ -583,19 +583,22 @@ def test_interp_forward_two_phase_is_bit_identical(U, O, dev, monkeypatch, B, N,
     alpha, eps = (0.3, 1e-3) if with_base else (1.0, 1e-4)
     got = {}
     # "1s": the selection by the thread-per-target kernel (k <= 4), "1": by the warp-per-target kernel
-    for tag, path, select in (("0", "0", "0"), ("1", "1", "0"), ("1s", "1", "1")):
+    # (1s1 / 1s2 / 1s4: with 1, 2 or 4 threads per target)
+    for tag, path, select, tpt in (("0", "0", "0", "1"), ("1", "1", "0", "1"), ("1s1", "1", "1", "1"), ("1s2", "1", "1", "2"),
+                                   ("1s4", "1", "1", "4")):
         monkeypatch.setenv("UPP_INTERP_PATH", path)
         monkeypatch.setenv("UPP_INTERP_SELECT", select)
+        monkeypatch.setenv("UPP_INTERP_TPT", tpt)
         n0 = U.launch_count()
         got[tag] = U.ops.interp_forward(x1.to(dev), x2.to(dev), p2.to(dev), k, eps, base=base, alpha=alpha)
         assert U.launch_count() - n0 == (1 if path == "0" else 2)
-    for tag in ("1", "1s"):
+    for tag in ("1", "1s1", "1s2", "1s4"):
         for a, b in zip(got["0"], got[tag]):
             assert torch.equal(a, b), tag
     o_out, o_idx, o_w, o_d = O.interp_fwd(x1.numpy(), x2.numpy(), p2.numpy(), k, eps,
                                           base=base.cpu().numpy() if with_base else None, alpha=alpha)
-    assert np.array_equal(got["1"][1].cpu().numpy(), o_idx)
-    np.testing.assert_allclose(got["1"][0].cpu().numpy(), o_out, rtol=RTOL, atol=1e-6)
+    assert np.array_equal(got["1s4"][1].cpu().numpy(), o_idx)
+    np.testing.assert_allclose(got["1s4"][0].cpu().numpy(), o_out, rtol=RTOL, atol=1e-6)
 
 
 @pytest.mark.parametrize("B,N,S,C,k", WIDE_SHAPES)
