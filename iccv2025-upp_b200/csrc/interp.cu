@@ -22,7 +22,8 @@ namespace upp {
 // out[b,n,:] = (base ? base[b,n,:] : 0) + alpha * sum_j w_j feat2[b, idx_j, :]
 // Gather: channels in super-blocks of 8 x 128 (one float4 per lane and block, 8 independent LDG.128 in flight per
 // neighbour), neighbours four at a time with their weight / row pointer shuffled once per super-block; products and
-// sums as packed fp32x2 (FMUL2 / FADD2: bit-identical to the scalar mul-then-add of the torch expression).
+// sums as packed fp32x2 (written mul.f32x2 then add.f32x2; ptxas contracts each pair to one FFMA2 -- SASS-verified -- so a
+// term is rounded once where torch's mul-then-sum rounds twice: the parity tests hold the output to 1e-5 relative).
 constexpr int kInterpCB = 8;  // float4 channel blocks per super-block (1024 channels)
 
 // CB x 128 channels starting at cs for one target: neighbours four at a time (weight / row pointer shuffled once),
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp, 3)
 //      lane, per neighbour one broadcast LDS.64 + one LDS.128, one streaming 512-byte store per
 //      target.  The only long-latency traffic left is the output write, which is what bounds the op.
 // Arithmetic is the fused kernel's (products and sums in neighbour order -- ptxas contracts each
-// mul.f32x2 + add.f32x2 pair to FFMA2 in both kernels -- then alpha, then base): bit-identical output.
+// mul.f32x2 + add.f32x2 pair to FFMA2 in both kernels, SASS-verified -- then alpha, then base): bit-identical output.
 // ---- explicit shared-window loads (32-bit addresses; see interp_bwd_stream_kernel) ----
 __device__ __forceinline__ uint2 lds_u64(uint32_t a) {
   uint2 v;
