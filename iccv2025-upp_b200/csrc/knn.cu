@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp)
   }
 }
 
+// (Measured and dropped, profiles/r01e_experiment_knn_split_warps.txt: 2 or 4 warps per query, each scanning a
+//  contiguous part of the cloud and merging the sorted 32-lists with bitonic merges, bit-identical results --
+//  64 q x 1024 at B = 32 went from 15.4 to 21.0 / 21.5 us, 128 q x 2048 from 29.7 to 42 / 52 us: the cost is the
+//  per-warp seed sort and the serial insertion chain, which parts do not shorten, not the scan of the references.)
+
 // k > 32 : selection by repeated extraction (no storage): round r finds the smallest
 // (distance, index) key strictly greater than the previous round's.  O(k*N/32) per query;
 // the reference never needs it (k in {8,16,32}), it keeps the ABI total.
