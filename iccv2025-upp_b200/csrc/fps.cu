@@ -505,6 +505,139 @@ __global__ void __launch_bounds__(NW * 32)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster FPS: ONE cloud per thread-block CLUSTER of CS CTAs (SURVEY.md 8e "cluster-split FPS for small
+// per-GPU batches").  With few large clouds -- seprate_point_cloud's B x 6144 -> 1024 (utils/misc.py:241-249),
+// or C4's 8192-point clouds once the batch is sharded over 8 GPUs (16 clouds on 148 SMs) -- one CTA per cloud
+// leaves most SMs idle while each round costs ~900-1050 cycles of distance updates.  Here CTA r of the cluster
+// owns the contiguous slice [r * Nc, (r + 1) * Nc) of the cloud (blocked ownership as in fps_blk_kernel: a lower
+// rank / warp / lane / slot is a lower point index), every CTA stages the WHOLE cloud once (coordinate look-up
+// of any winner), and a round is
+//   distance update + in-thread max -> REDUX.MAX (key) -> REDUX.MIN (lowest index among the lanes holding it)
+//   -> lanes 0..CS-1 of every warp push the warp's {key, index} into slot [rank * NW + warp] of EVERY CTA of the
+//      cluster with st.async (distributed shared memory, completes bytes on the destination's mbarrier)
+//   -> every thread waits on its own CTA's mbarrier, lane i reads entry i (CS * NW <= 32 entries),
+//      REDUX.MAX + REDUX.MIN pick the cluster winner -> its coordinates come from the local copy of the cloud.
+// No intra-CTA barrier and no cluster barrier inside the loop: two entry buffers / two mbarriers alternate by
+// round parity (a CTA can only send round j+2 after it has received every CTA's round j+1, i.e. after every
+// CTA has consumed round j).  Same selection rule as every other FPS kernel here, bit-identical indices.
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, unsigned rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, int lo, int hi, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+               "r"(lo), "r"(hi), "r"(remote_bar)
+               : "memory");
+}
+
+template <int CS, int NW, int P2>
+__global__ void __launch_bounds__(NW * 32, 1)
+    fps_cluster_kernel(const float* __restrict__ xyz, int N, int M, int Nc, int32_t* __restrict__ idx_out,
+                       float* __restrict__ centers_out) {
+  static_assert(CS * NW <= 32, "one entry per lane in the cluster stage");
+  constexpr int P = 2 * P2;
+  extern __shared__ __align__(16) float s_xyz[];  // 3*N floats: the whole cloud (AoS, as in global memory)
+  __shared__ __align__(8) int2 s_x[2][32];        // {key, index} of every warp of the cluster, by round parity
+  __shared__ __align__(8) uint64_t s_bar, s_xbar[2];
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x / CS;
+  const float* p = xyz + static_cast<size_t>(b) * N * 3;
+  int32_t* out = idx_out + static_cast<size_t>(b) * M;
+  float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
+
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_init(&s_xbar[0], 1);
+    mbar_init(&s_xbar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers exist before anyone sends to them
+  unsigned parity = 0;
+  stage_points(s_xyz, p, N, &s_bar, parity);
+
+  const int lo = static_cast<int>(rank) * Nc;
+  const int hi = min(N, lo + Nc);
+  const int base = lo + t * P;
+  f32x2 X[P2], Y[P2], Z[P2];
+  float md[P];
+#pragma unroll
+  for (int r = 0; r < P2; ++r) {
+    float c[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = base + 2 * r + h;
+      if (i < hi) {
+        c[h][0] = s_xyz[3 * i];
+        c[h][1] = s_xyz[3 * i + 1];
+        c[h][2] = s_xyz[3 * i + 2];
+        md[2 * r + h] = fps_initial_md(c[h][0], c[h][1], c[h][2]);
+      } else {
+        c[h][0] = c[h][1] = c[h][2] = 0.f;
+        md[2 * r + h] = kOutOfRange;
+      }
+    }
+    X[r] = pack2(c[0][0], c[1][0]);
+    Y[r] = pack2(c[0][1], c[1][1]);
+    Z[r] = pack2(c[0][2], c[1][2]);
+  }
+  // lane r < CS of every warp sends to CTA r: destination entry / barrier addresses for both parities
+  const unsigned dst = lane < CS ? lane : 0;
+  const int my_entry = static_cast<int>(rank) * NW + warp;
+  const uint32_t r_entry0 = map_to_cta(smem_u32(&s_x[0][my_entry]), dst);
+  const uint32_t r_entry1 = map_to_cta(smem_u32(&s_x[1][my_entry]), dst);
+  const uint32_t r_bar0 = map_to_cta(smem_u32(&s_xbar[0]), dst);
+  const uint32_t r_bar1 = map_to_cta(smem_u32(&s_xbar[1]), dst);
+
+  float cx = s_xyz[0], cy = s_xyz[1], cz = s_xyz[2];
+  if (t == 0 && rank == 0) {
+    out[0] = 0;
+    if (cen) { cen[0] = cx; cen[1] = cy; cen[2] = cz; }
+  }
+  for (int j = 1; j < M; ++j) {
+    const int h = j & 1;
+    if (t == 0) mbar_expect_tx(&s_xbar[h], CS * NW * 8u);  // this round's CS * NW entries of 8 bytes
+    const f32x2 CX = pack2(cx, cx), CY = pack2(cy, cy), CZ = pack2(cz, cz);
+    int best, ls = 0;
+    fps_span<P2, 0, P2, true>(X, Y, Z, md, CX, CY, CZ, best, ls);
+    const int wbest = redux_max_s32(best);
+    const unsigned widx = redux_min_u32(best == wbest ? static_cast<unsigned>(base + ls) : 0xffffffffu);
+    if (lane < CS) st_async_b64(h ? r_entry1 : r_entry0, wbest, static_cast<int>(widx), h ? r_bar1 : r_bar0);
+    mbar_wait(&s_xbar[h], static_cast<unsigned>((j - 1) >> 1) & 1u);  // buffer h is on its ((j - 1) / 2)-th use
+    const int2 e = lane < CS * NW ? s_x[h][lane] : make_int2(INT_MIN, INT_MAX);
+    const int cbest = redux_max_s32(e.x);
+    const int sel = static_cast<int>(redux_min_u32(e.x == cbest ? static_cast<unsigned>(e.y) : 0xffffffffu));
+    cx = s_xyz[3 * sel];
+    cy = s_xyz[3 * sel + 1];
+    cz = s_xyz[3 * sel + 2];
+    if (t == 0 && rank == 0) out[j] = sel;
+  }
+  cluster_sync_all();  // nobody leaves while a peer may still be sending to it
+  if (cen && rank == 0) {
+    __syncthreads();  // thread 0's out[] stores are visible to the block
+    for (int j = 1 + t; j < M; j += NW * 32) {
+      const int sel = out[j];
+      cen[3 * j] = s_xyz[3 * sel];
+      cen[3 * j + 1] = s_xyz[3 * sel + 1];
+      cen[3 * j + 2] = s_xyz[3 * sel + 2];
+    }
+  }
+}
+
 // Any-N fallback: min-distance array in a global workspace (L2-resident), xyz re-read from
 // global memory every iteration.  Same selection rule, same two-stage arg-max.
 template <int THREADS>
@@ -723,6 +856,70 @@ static int dispatch_fps_blk_big(FpsBlkConfig c, const float* xyz, int B, int N, 
   return UPP_ERR_UNSUPPORTED;
 }
 
+template <int CS, int NW, int P2>
+static int launch_fps_cluster(const float* xyz, int B, int N, int M, int Nc, int32_t* idx, float* centers,
+                              cudaStream_t st) {
+  // as for one CTA per cloud: while every CTA can have an SM of its own, keep throughput kernels off that SM --
+  // up to 4 CTAs per cluster (measured: a cluster of 8 CTAs asking for the whole 227 KB each is not placed at all)
+  const size_t need = static_cast<size_t>(N) * 3 * sizeof(float);
+  const size_t smem = CS <= 4 ? fps_smem_request(need, B * CS) : need;
+  auto kern = fps_cluster_kernel<CS, NW, P2>;
+  if (smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(B) * CS);
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, N, M, Nc, idx, centers);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  count_launch();
+  return launch_status();
+}
+
+// Cluster size for a batch of B clouds of N points, from the B200 sweep (scripts/time_ops.py --sweep-fps-cluster,
+// profiles/r01e_sweep_fps_cluster.jsonl; us per round, one CTA per cloud -> cluster):
+//   B32 N6144 0.453 -> 0.282 (4)   B32 N4096 0.359 -> 0.254 (4)   B16 N8192 0.543 -> 0.299 (8)   B8 N8192 0.542 -> 0.283 (8)
+//   B64 N8192 0.543 -> 0.364 (4, two CTAs per SM)   B32 N2048 0.193 -> 0.231 (slower: the ~300-cycle exchange dominates)
+// so: clouds of >= 4096 points; 8 CTAs when they all get an SM of their own and the cloud is > 6144 points, else 4
+// CTAs while every cluster is still resident at two CTAs per SM.  Two-CTA clusters (slices of up to 4096 points,
+// 32 points per thread) lose to one CTA per cloud and are never chosen.
+// UPP_FPS_CLUSTER: 0 = never, 2/4/8 = force that size (tuning / tests).  Returns 0 for "one CTA per cloud".
+static int fps_pick_cluster(int B, int N) {
+  const int forced = env_int("UPP_FPS_CLUSTER", -1);
+  if (forced == 0 || N > kFpsMaxRegPoints) return 0;
+  int cs = 0;
+  if (forced == 2 || forced == 4 || forced == 8) cs = forced;
+  else if (N >= 4096) cs = (B * 8 <= kNumSMs && N > 6144) ? 8 : (B * 4 <= 2 * kNumSMs ? 4 : 0);
+  while (cs > 1 && N / cs < 256) cs >>= 1;  // a slice is at least 256 points
+  return cs >= 2 ? cs : 0;
+}
+
+static int dispatch_fps_cluster(int cs, const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
+                                cudaStream_t st) {
+  const int nc = (((N + cs - 1) / cs) + 1) & ~1;  // slice length: whole point pairs
+  // 4 warps per CTA; point pairs per thread sized to the slice (instantiated: 1, 2, 3, 4, 6, 8, 12, 16)
+  const int want = (nc + 255) / 256;
+  const int p2 = want <= 4 ? want : (want <= 6 ? 6 : (want <= 8 ? 8 : (want <= 12 ? 12 : 16)));
+  if (p2 > 16 || static_cast<long>(p2) * 256 < nc) return UPP_ERR_UNSUPPORTED;
+#define UPP_CL(CS_, P2_) \
+  if (cs == CS_ && p2 == P2_) return launch_fps_cluster<CS_, 4, P2_>(xyz, B, N, M, nc, idx, centers, st);
+#define UPP_CL_ROW(CS_) UPP_CL(CS_, 1) UPP_CL(CS_, 2) UPP_CL(CS_, 3) UPP_CL(CS_, 4) UPP_CL(CS_, 6) UPP_CL(CS_, 8) UPP_CL(CS_, 12) UPP_CL(CS_, 16)
+  UPP_CL_ROW(2) UPP_CL_ROW(4) UPP_CL_ROW(8)
+#undef UPP_CL_ROW
+#undef UPP_CL
+  return UPP_ERR_UNSUPPORTED;
+}
+
 static bool fps_blk_valid(FpsBlkConfig c, int N) {
   const bool nw_ok = c.nw == 1 || c.nw == 2 || c.nw == 4 || c.nw == 8 || c.nw == 16 || c.nw == 32;
   if (c.search == 2) {  // the combinations dispatch_fps_blk_big instantiates
@@ -757,6 +954,10 @@ FpsBlkConfig fps_pick_blk(int N, int B) {
 
 int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (const int cs = fps_pick_cluster(B, N)) {  // few large clouds: one cloud per cluster of CTAs
+    if (dispatch_fps_cluster(cs, xyz, B, N, M, idx, centers, st) == UPP_OK) return UPP_OK;
+    (void)cudaGetLastError();  // a cluster that cannot be placed (or an uninstantiated shape): one CTA per cloud below
+  }
   if (N <= kFpsMaxRegPoints && env_int("UPP_FPS_IMPL", 2) != 1) {
     // v2 (blocked ownership, packed fp32x2) everywhere the register-resident scheme reaches; the v1 kernels
     // below stay for A/B timing (UPP_FPS_IMPL=1) and as a parity cross-check.

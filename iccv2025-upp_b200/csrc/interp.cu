@@ -872,7 +872,11 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   const int env = interp_path_env();
   const bool blend_ok = vec4 && C > 0 && C % kBlendCh == 0 && S <= kBlendMaxS && B <= 65535;
   const bool blend_big = static_cast<size_t>(B) * N * C >= (static_cast<size_t>(8) << 20) && N >= 256;
-  const bool two_phase = blend_ok && (env == 1 || (env < 0 && blend_big));
+  bool two_phase = blend_ok && (env == 1 || (env < 0 && blend_big));
+  CUtensorMap fmap;  // feat2 as (B*S rows) x C, box = S rows x 128 channels
+  if (two_phase && make_tmap_2d_f32(&fmap, feat2, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * S,
+                                    static_cast<uint64_t>(C) * sizeof(float), kBlendCh, static_cast<uint32_t>(S)) != UPP_OK)
+    two_phase = false;  // no tensor-map encoder in this driver: the one-launch kernel serves every shape
   const int csel = two_phase ? 0 : C;
   // UPP_INTERP_SELECT (test aid): 0 = never the thread-per-target selection, 1 = whenever k <= 4 and S <= 1024
   const char* sv = getenv("UPP_INTERP_SELECT");
@@ -932,10 +936,6 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   const int spans = blend_pick_spans(static_cast<long>(chunks) * B, N, per_sm * 148);
   int span = ((N + spans - 1) / spans + 15) & ~15;  // whole trips of 8 warps x 2 targets
   dim3 bgrid(chunks, (N + span - 1) / span, B);
-  CUtensorMap fmap;  // feat2 as (B*S rows) x C, box = S rows x 128 channels
-  rc = make_tmap_2d_f32(&fmap, feat2, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * S,
-                        static_cast<uint64_t>(C) * sizeof(float), kBlendCh, static_cast<uint32_t>(S));
-  if (rc != UPP_OK) return rc;
 #define UPP_BLEND(K_)                                                                                                    \
   do {                                                                                                                   \
     if (bsmem > 40 * 1024) {                                                                                             \
@@ -988,7 +988,11 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
   const size_t need = interp_bwd_workspace_bytes(B, N, S, C, k);
   const bool stream_ok = need > 0 && ws != nullptr && ws_bytes >= need && aligned16(gout, gfeat2, ws);
   const bool stream_big = static_cast<long>(C / kBlendCh) * B >= 120 && N >= 512;
-  const bool streamed = stream_ok && (env == 1 || (env < 0 && stream_big));
+  bool streamed = stream_ok && (env == 1 || (env < 0 && stream_big));
+  CUtensorMap gmap;  // grad_out as (B*N rows) x C, box = 64 rows x 128 channels
+  if (streamed && make_tmap_2d_f32(&gmap, gout, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * N,
+                                   static_cast<uint64_t>(C) * sizeof(float), kBlendCh, kBsTile) != UPP_OK)
+    streamed = false;  // no tensor-map encoder in this driver: the source-side kernel serves every shape
   const int csrc = streamed ? 0 : C;
   if (!streamed || want_xyz) {
     dim3 grid(S, B);
@@ -1013,10 +1017,6 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
   int rc = launch_status();
   if (rc != UPP_OK) return rc;
   const size_t ssmem = static_cast<size_t>(kBsStages) * bs_stage_bytes(k);
-  CUtensorMap gmap;  // grad_out as (B*N rows) x C, box = 64 rows x 128 channels
-  rc = make_tmap_2d_f32(&gmap, gout, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * N,
-                        static_cast<uint64_t>(C) * sizeof(float), kBlendCh, kBsTile);
-  if (rc != UPP_OK) return rc;
   cudaError_t e = cudaFuncSetAttribute(interp_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(ssmem));
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -2,6 +2,7 @@
 
   fps                   utils/misc.py:13-20      (re-exported from modules)
   seprate_point_cloud   utils/misc.py:205-256    
+  random_dropping       utils/misc.py:308-315    (KITTI fine-tuning: FPS to a random size, zero-padded to 2048)
 
 The reference's seprate_point_cloud walks the batch in a Python loop and, per cloud, sorts the points by
 distance to a random viewpoint, crops, and calls fps() on (1, n - num_crop, 3) and (1, num_crop, 3): 2*B
@@ -18,7 +19,7 @@ import torch.nn.functional as F
 
 from .modules import fps
 
-__all__ = ["fps", "seprate_point_cloud"]
+__all__ = ["fps", "seprate_point_cloud", "random_dropping"]
 
 
 def seprate_point_cloud(xyz, num_points, crop, fixed_points=None, padding_zeros=False, sample_points=1024,
@@ -65,3 +66,16 @@ def seprate_point_cloud(xyz, num_points, crop, fixed_points=None, padding_zeros=
         if incomplete_shape and crop_data.shape[1] > sample_points:
             crop_data = fps(crop_data, sample_points)[0]
     return input_data.contiguous(), crop_data.contiguous()
+
+
+def random_dropping(pc, e):
+    """utils/misc.py:308-315, same RNG draw (one torch.randint from the CPU generator): FPS down to a random number of
+    points in [1, max(64, 768 // (e // 50 + 1))), zero rows appended up to 2048 points (the rows ChamferDistance's
+    ignore_zeros drops again).  As written the reference passes fps()'s (data, idx) TUPLE on to .size() and raises
+    (its fps, utils/misc.py:13-20, returns both; the function predates that); the evident intent -- the sampled
+    points -- is what this mirror implements."""
+    up_num = max(64, 768 // (e // 50 + 1))
+    random_num = int(torch.randint(1, up_num, (1, 1))[0, 0])
+    pc = fps(pc, random_num)[0]
+    padding = torch.zeros(pc.size(0), 2048 - pc.size(1), 3, device=pc.device, dtype=pc.dtype)
+    return torch.cat([pc, padding], dim=1)

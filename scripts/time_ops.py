@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--sweep-fps", action="store_true")
     ap.add_argument("--sweep-chamfer", action="store_true")
     ap.add_argument("--sweep-chamfer2", action="store_true")
+    ap.add_argument("--sweep-fps-cluster", action="store_true")
     ap.add_argument("--sweep-fps2", action="store_true", help="v2 FPS kernel: warps x point-pairs x stage-2 variant")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -94,6 +95,22 @@ def main():
                             lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "matches_v1": ok})
             for k in ("UPP_FPS_NW", "UPP_FPS_P2", "UPP_FPS_S2", "UPP_FPS_SEARCH"):
                 os.environ.pop(k, None)
+        return
+    if args.sweep_fps_cluster:  # one cloud per cluster of CTAs against one CTA per cloud (UPP_FPS_CLUSTER=0)
+        for (B, N, M) in [(32, 6144, 1024), (32, 4096, 1024), (16, 8192, 1024), (8, 8192, 1024), (1, 6144, 1024),
+                          (32, 2048, 1024), (64, 8192, 1024), (16, 4096, 512)]:
+            x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+            want = None
+            for cs in ("0", "2", "4", "8", None):
+                if cs is None:
+                    os.environ.pop("UPP_FPS_CLUSTER", None)
+                else:
+                    os.environ["UPP_FPS_CLUSTER"] = cs
+                got = ops.fps(x, M)
+                want = got if want is None else want
+                rec(f"fps-cluster B{B} N{N} M{M} cluster={cs or 'auto'}", lambda: ops.fps(x, M),
+                    lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "same_as_single_cta": bool(torch.equal(got, want))})
+            os.environ.pop("UPP_FPS_CLUSTER", None)
         return
     if args.sweep_chamfer2:  # residency variants of the packed kernel (register cap -> CTAs per SM)
         for (B, N, M) in [(64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192)]:

@@ -55,6 +55,10 @@ FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
     "v2_tree_nw8_p5": {"UPP_FPS_NW": "8", "UPP_FPS_P2": "5", "UPP_FPS_S2": "0", "UPP_FPS_SEARCH": "2"},
     "v2_tree_nw16_p8": {"UPP_FPS_NW": "16", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
     "v2_tree_nw32_p4": {"UPP_FPS_NW": "32", "UPP_FPS_P2": "4", "UPP_FPS_S2": "1", "UPP_FPS_SEARCH": "2"},
+    # one cloud per cluster of 2 / 4 / 8 CTAs (DSMEM exchange; slices of >= 256 points, else the heuristic's choice)
+    "cluster2": {"UPP_FPS_CLUSTER": "2"},
+    "cluster4": {"UPP_FPS_CLUSTER": "4"},
+    "cluster8": {"UPP_FPS_CLUSTER": "8"},
     "v1": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "0"},                       # round-1a strided kernels
     "v1_w4": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "1"},
 }
@@ -114,6 +118,17 @@ def test_fps_duplicates_all_skipped_and_m_gt_n(U, O, dev):
     assert np.array_equal(got, O.fps(tiny.numpy(), 8))
     small = cube(2, 10, 5)
     assert np.array_equal(U.ops.fps(small.to(dev), 25).cpu().numpy(), O.fps(small.numpy(), 25))
+
+
+@pytest.mark.parametrize("B,N,M", [(16, 8192, 300), (32, 6144, 200), (37, 4096, 64), (18, 4099, 64), (148, 4096, 16)])
+def test_fps_cluster_heuristic_batches(U, O, dev, B, N, M):
+    """Batches the heuristic itself sends to the cluster kernel (B * CS <= 148 SMs, N >= 4096) and its edges, with the
+    fused centre gather, against the oracle."""
+    xyz = unit_sphere(torch.randn(B, N, 3, generator=torch.Generator().manual_seed(B + N)) * 0.3)
+    idx, centers = U.ops.fps(xyz.to(dev), M, True)
+    want = O.fps(xyz.numpy(), M)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert torch.equal(centers.cpu(), torch.gather(xyz, 1, torch.from_numpy(want).long()[..., None].expand(-1, -1, 3)))
 
 
 def test_fps_large_n_workspace_path(U, O, dev):
@@ -735,6 +750,18 @@ def test_golden_reference_seprate_point_cloud(U, dev, case):
     assert np.array_equal(b.cpu().numpy(), g[case + "_crop"])
     same, none = U.misc.seprate_point_cloud(xyz, 512, 512)
     assert same is xyz and none is None
+
+
+def test_random_dropping_mirror(U, dev):
+    """utils/misc.py:308-315: FPS to a random size (same CPU-generator draw), zero rows up to 2048 points."""
+    xyz = cube(3, 2048, 4).to(dev)
+    for e in (0, 120, 400):
+        torch.manual_seed(5 + e)
+        out = U.misc.random_dropping(xyz, e)
+        torch.manual_seed(5 + e)
+        n = int(torch.randint(1, max(64, 768 // (e // 50 + 1)), (1, 1))[0, 0])
+        assert tuple(out.shape) == (3, 2048, 3)
+        assert torch.equal(out[:, :n], U.fps(xyz, n)[0]) and not out[:, n:].any()
 
 
 def test_chamfer_sharded_entry_world1_equals_plain(U, dev):
