@@ -450,6 +450,9 @@ def main():
     ap.add_argument("--workload", default="upp_cls_geometry+chamfer", choices=sorted(DEFAULT_B))
     ap.add_argument("--batch", type=int, default=0, help="clouds per GPU (default: the config's B)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the config's batch is the GLOBAL batch, split evenly over the ranks "
+                         "(SURVEY.md 8d C4); default is weak scaling (the config's batch per GPU)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -458,6 +461,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     B = args.batch or DEFAULT_B[args.workload]
+    if args.strong:
+        if B % world:
+            raise SystemExit(f"--strong: global batch {B} is not divisible by {world} ranks")
+        B //= world
+    scaling = "strong" if args.strong else "weak"
     config = {"workload": args.workload, "description": DESCR[args.workload], "clouds_per_gpu": B,
               "l2": "flushed between timed steps (256 MiB memset outside the event pair); inputs are << L2"}
 
@@ -467,7 +475,7 @@ def main():
         cb, sec, bs = time_cpu(args.workload, B, 0, args.steps, args.warmup, budget_s=120.0)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(config, clouds_per_step=bs), "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
@@ -694,7 +702,7 @@ def main():
                                      "busy_sms": min(B, N_SM)}
 
     line = {"metric": METRIC, "value": clouds / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": clouds / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps,
