@@ -890,16 +890,17 @@ static int launch_fps_cluster(const float* xyz, int B, int N, int M, int Nc, int
 // profiles/r01e_sweep_fps_cluster.jsonl; us per round, one CTA per cloud -> cluster):
 //   B32 N6144 0.453 -> 0.282 (4)   B32 N4096 0.359 -> 0.254 (4)   B16 N8192 0.543 -> 0.299 (8)   B8 N8192 0.542 -> 0.283 (8)
 //   B64 N8192 0.543 -> 0.364 (4, two CTAs per SM)   B32 N2048 0.193 -> 0.231 (slower: the ~300-cycle exchange dominates)
-// so: clouds of >= 4096 points; 8 CTAs when they all get an SM of their own and the cloud is > 6144 points, else 4
-// CTAs while every cluster is still resident at two CTAs per SM.  Two-CTA clusters (slices of up to 4096 points,
-// 32 points per thread) lose to one CTA per cloud and are never chosen.
+//   mid-size clouds (r01e_sweep_fps_cluster_mid.jsonl, B32): N3584 0.345 -> 0.260 (4), N3072 0.270 -> 0.250, N2560 0.255 -> 0.247
+// so: clouds of more than 3072 points (where one CTA per cloud moves to its 8-warp kernels); 8 CTAs when they all
+// get an SM of their own and the cloud has >= 5120 points, else 4 CTAs while every cluster is still resident at two
+// CTAs per SM.  Two-CTA clusters (slices of up to 4096 points, 32 points per thread) lose and are never chosen.
 // UPP_FPS_CLUSTER: 0 = never, 2/4/8 = force that size (tuning / tests).  Returns 0 for "one CTA per cloud".
 static int fps_pick_cluster(int B, int N) {
   const int forced = env_int("UPP_FPS_CLUSTER", -1);
   if (forced == 0 || N > kFpsMaxRegPoints) return 0;
   int cs = 0;
   if (forced == 2 || forced == 4 || forced == 8) cs = forced;
-  else if (N >= 4096) cs = (B * 8 <= kNumSMs && N > 6144) ? 8 : (B * 4 <= 2 * kNumSMs ? 4 : 0);
+  else if (N > 3072) cs = (B * 8 <= kNumSMs && N >= 5120) ? 8 : (B * 4 <= 2 * kNumSMs ? 4 : 0);
   while (cs > 1 && N / cs < 256) cs >>= 1;  // a slice is at least 256 points
   return cs >= 2 ? cs : 0;
 }

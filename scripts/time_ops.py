@@ -97,8 +97,12 @@ def main():
                 os.environ.pop(k, None)
         return
     if args.sweep_fps_cluster:  # one cloud per cluster of CTAs against one CTA per cloud (UPP_FPS_CLUSTER=0)
-        for (B, N, M) in [(32, 6144, 1024), (32, 4096, 1024), (16, 8192, 1024), (8, 8192, 1024), (1, 6144, 1024),
-                          (32, 2048, 1024), (64, 8192, 1024), (16, 4096, 512)]:
+        shapes = [(32, 6144, 1024), (32, 4096, 1024), (16, 8192, 1024), (8, 8192, 1024), (1, 6144, 1024),
+                  (32, 2048, 1024), (64, 8192, 1024), (16, 4096, 512)]
+        if args.only == "mid":  # where between 2048 and 4096 points the cluster starts to pay
+            shapes = [(B, N, 512) for N in (2560, 3072, 3584, 5120) for B in (8, 32, 64)] + [(64, 4096, 512), (72, 6144, 512)]
+            args.only = ""
+        for (B, N, M) in shapes:
             x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
             want = None
             for cs in ("0", "2", "4", "8", None):

@@ -120,9 +120,9 @@ def test_fps_duplicates_all_skipped_and_m_gt_n(U, O, dev):
     assert np.array_equal(U.ops.fps(small.to(dev), 25).cpu().numpy(), O.fps(small.numpy(), 25))
 
 
-@pytest.mark.parametrize("B,N,M", [(16, 8192, 300), (32, 6144, 200), (37, 4096, 64), (18, 4099, 64), (148, 4096, 16)])
+@pytest.mark.parametrize("B,N,M", [(16, 8192, 300), (32, 6144, 200), (37, 4096, 64), (18, 5121, 64), (74, 3073, 16), (75, 3100, 16)])
 def test_fps_cluster_heuristic_batches(U, O, dev, B, N, M):
-    """Batches the heuristic itself sends to the cluster kernel (B * CS <= 148 SMs, N >= 4096) and its edges, with the
+    """Batches the heuristic itself sends to the cluster kernel (N > 3072; 8 CTAs while B * 8 <= 148, else 4 while B * 4 <= 296) and its edges, with the
     fused centre gather, against the oracle."""
     xyz = unit_sphere(torch.randn(B, N, 3, generator=torch.Generator().manual_seed(B + N)) * 0.3)
     idx, centers = U.ops.fps(xyz.to(dev), M, True)
