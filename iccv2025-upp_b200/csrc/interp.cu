@@ -325,8 +325,9 @@ __global__ void __launch_bounds__(kSelThreads)
 }
 
 // K = 0: any k <= 32 (neighbour loop not unrolled, no register prefetch of the next record batch).
-template <int K>
-__global__ void __launch_bounds__(kBlendWarps * kWarp)
+// NWB warps per CTA (8 or 16: the staged feature slice caps the CTAs per SM at three, so warps per CTA set the occupancy).
+template <int K, int NWB>
+__global__ void __launch_bounds__(NWB * kWarp)
     interp_blend_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ base, float alpha,
                         const int32_t* __restrict__ idx, const float* __restrict__ weight, int N, int S, int C,
                         int krt, int span, float* __restrict__ out) {
@@ -348,14 +349,14 @@ __global__ void __launch_bounds__(kBlendWarps * kWarp)
     tma_load_2d(s_blend, &fmap, chunk * kBlendCh, b * S, &s_bar);
   }
   // records of one batch: entry e of the batch <-> flat (target, j) position, contiguous in idx / weight
-  constexpr int PE = K > 0 ? (kBlendSub * K + kBlendWarps * kWarp - 1) / (kBlendWarps * kWarp) : 1;
+  constexpr int PE = K > 0 ? (kBlendSub * K + NWB * kWarp - 1) / (NWB * kWarp) : 1;
   uint2 pre[PE];
   auto fetch = [&](int s0) {
     const int cnt = (min(n1, s0 + kBlendSub) - s0) * k;
     const size_t p0 = (static_cast<size_t>(b) * N + s0) * k;
 #pragma unroll
     for (int u = 0; u < PE; ++u) {
-      const int e = t + u * (kBlendWarps * kWarp);
+      const int e = t + u * (NWB * kWarp);
       pre[u] = e < cnt ? make_uint2(static_cast<unsigned>(__ldg(idx + p0 + e)) * (kBlendCh * 4u),
                                     __float_as_uint(__ldg(weight + p0 + e)))
                        : make_uint2(0u, 0u);
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(kBlendWarps * kWarp)
   auto commit = [&]() {
 #pragma unroll
     for (int u = 0; u < PE; ++u) {
-      const int e = t + u * (kBlendWarps * kWarp);
+      const int e = t + u * (NWB * kWarp);
       if (e < kBlendSub * k) s_rec[e] = pre[u];
     }
   };
@@ -384,16 +385,16 @@ __global__ void __launch_bounds__(kBlendWarps * kWarp)
       if (s0 + kBlendSub < n1) fetch(s0 + kBlendSub);  // next batch: loads in flight under this batch's blend
     } else {
       __syncthreads();
-      for (int e = t; e < cnt * k; e += kBlendWarps * kWarp) {
+      for (int e = t; e < cnt * k; e += NWB * kWarp) {
         const size_t p = (static_cast<size_t>(b) * N + s0) * k + e;
         s_rec[e] = make_uint2(static_cast<unsigned>(__ldg(idx + p)) * (kBlendCh * 4u), __float_as_uint(__ldg(weight + p)));
       }
       __syncthreads();
     }
     // two targets per warp and trip: 2k independent LDS.128 in flight
-    for (int tl = warp; tl < cnt; tl += 2 * kBlendWarps) {
-      const bool two = tl + kBlendWarps < cnt;
-      const int tb = two ? tl + kBlendWarps : tl;
+    for (int tl = warp; tl < cnt; tl += 2 * NWB) {
+      const bool two = tl + NWB < cnt;
+      const int tb = two ? tl + NWB : tl;
       const uint2* ra = s_rec + tl * k;
       const uint2* rb = s_rec + tb * k;
       f32x2 a0 = pack2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
@@ -854,17 +855,14 @@ static bool aligned16(const void* a, const void* b = nullptr, const void* c = nu
   return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) % 16) == 0;
 }
 
-// fewest target spans per (cloud, chunk) whose CTA count fills whole residency waves (within 3 % of the best fill)
-static int blend_pick_spans(long items0, int N, long wave) {
-  int best = 1;
-  double best_eff = 0.0;
-  const int smax = N / 128 < 1 ? 1 : (N / 128 > 64 ? 64 : N / 128);
-  for (int sp = 1; sp <= smax; ++sp) {
-    const long items = items0 * sp;
-    const double eff = static_cast<double>(items) / (static_cast<double>(wave) * ((items + wave - 1) / wave));
-    if (eff > best_eff + 0.03) { best_eff = eff; best = sp; }
-  }
-  return best;
+// Target spans per (cloud, chunk).  Every CTA pays its feature-tile load (64 KB, ~3 us of exposed latency: CTAs of a
+// wave start together, so nothing overlaps it) before it streams, so FEWER, LONGER CTAs win as long as every SM has
+// work: B200 sweep at the seg shape (288 (cloud, chunk) items, forward us): 1 span 63.0, 2: 67.1, 3: 68.6, 6: 67.6,
+// 12: 69.1, 24: 75.3.  Hence: the fewest spans that give about 1.5 CTAs per SM.
+static int blend_pick_spans(long items0, int N) {
+  const long want = (3 * 148 / 2 + items0 - 1) / items0;
+  const long smax = N / 128 < 1 ? 1 : N / 128;
+  return static_cast<int>(want < 1 ? 1 : (want > smax ? smax : want));
 }
 
 int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, const float* base, float alpha,
@@ -935,24 +933,31 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
 
   const int chunks = C / kBlendCh;
   const size_t bsmem = static_cast<size_t>(S) * kBlendCh * sizeof(float) + static_cast<size_t>(kBlendSub) * k * 8;
-  const long per_sm = bsmem <= 74 * 1024 ? 3 : 2;
-  const int spans = blend_pick_spans(static_cast<long>(chunks) * B, N, per_sm * 148);
-  int span = ((N + spans - 1) / spans + 15) & ~15;  // whole trips of 8 warps x 2 targets
+  const char* sv2 = getenv("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
+  const int spans = sv2 ? max(1, atoi(sv2)) : blend_pick_spans(static_cast<long>(chunks) * B, N);
+  const char* wv = getenv("UPP_BLEND_WARPS");  // tuning aid: 8 or 16 warps per CTA
+  const int nwb = (wv && atoi(wv) == 8) ? 8 : 16;
+  int span = ((N + spans - 1) / spans + 2 * nwb - 1) / (2 * nwb) * (2 * nwb);  // whole trips of nwb warps x 2 targets
   dim3 bgrid(chunks, (N + span - 1) / span, B);
-#define UPP_BLEND(K_)                                                                                                    \
+#define UPP_BLEND(K_, W_)                                                                                               \
   do {                                                                                                                   \
     if (bsmem > 40 * 1024) {                                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(interp_blend_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+      cudaError_t e = cudaFuncSetAttribute(interp_blend_kernel<K_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                            static_cast<int>(bsmem));                                                     \
       if (e != cudaSuccess) return static_cast<int>(e);                                                                  \
     }                                                                                                                    \
-    interp_blend_kernel<K_><<<bgrid, kBlendWarps * kWarp, bsmem, st>>>(fmap, base, alpha, idx, weight, N, S, C, k, span, \
-                                                                      out);                                             \
+    interp_blend_kernel<K_, W_><<<bgrid, W_ * kWarp, bsmem, st>>>(fmap, base, alpha, idx, weight, N, S, C, k, span, out); \
   } while (0)
-  if (k == 3) UPP_BLEND(3);
-  else if (k == 4) UPP_BLEND(4);
-  else if (k == 8) UPP_BLEND(8);
-  else UPP_BLEND(0);
+#define UPP_BLEND_K(W_)              \
+  do {                               \
+    if (k == 3) UPP_BLEND(3, W_);    \
+    else if (k == 4) UPP_BLEND(4, W_); \
+    else if (k == 8) UPP_BLEND(8, W_); \
+    else UPP_BLEND(0, W_);           \
+  } while (0)
+  if (nwb == 8) UPP_BLEND_K(8);
+  else UPP_BLEND_K(16);
+#undef UPP_BLEND_K
 #undef UPP_BLEND
   count_launch();
   return launch_status();
