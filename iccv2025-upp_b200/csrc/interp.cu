@@ -186,11 +186,14 @@ __global__ void __launch_bounds__(kKnnWarps * kWarp, 3)
 //      C = 0; both write idx / weight / dist only;
 //   2. interp_blend_kernel streams the output: a CTA owns (cloud, 128-channel chunk, span of
 //      targets), stages its S x 128-channel slice of the source features ONCE in shared memory (one
-//      2-D TMA tile load), turns the span's (idx, weight) pairs into {row offset, weight} records in
-//      shared memory 128 targets at a time (the next batch is in flight in registers while this one
-//      is blended), and every warp blends target after target from shared memory: one float4 per
-//      lane, per neighbour one broadcast LDS.64 + one LDS.128, one streaming 512-byte store per
-//      target.  The only long-latency traffic left is the output write, which is what bounds the op.
+//      2-D TMA tile load); every warp owns a run of the span's targets, turns their (idx, weight)
+//      pairs into {row offset, weight} records in its own slice of shared memory 16 targets at a time
+//      (the next batch is in flight in registers while this one is blended) and blends target after
+//      target from shared memory: one float4 per lane, per neighbour one broadcast LDS.64 + one
+//      LDS.128, one streaming 512-byte store per target.  The only long-latency traffic left is the
+//      output write, which is what bounds the op: 50 us for 302 MB at the seg shape, memset 45 us
+//      (insensitive to 8 / 16 warps per CTA, to CTA-wide or warp-private batches and to the output
+//      stride -- a one-chunk layout with fully linear rows takes the same time).
 // Arithmetic is the fused kernel's (products and sums in neighbour order -- ptxas contracts each
 // mul.f32x2 + add.f32x2 pair to FFMA2 in both kernels, SASS-verified -- then alpha, then base): bit-identical output.
 // ---- explicit shared-window loads (32-bit addresses; see interp_bwd_stream_kernel) ----
@@ -227,7 +230,6 @@ __device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
 constexpr int kBlendCh = 128;
 constexpr int kBlendWarps = 8;
 constexpr int kBlendMaxS = 192;   // 96 KB of staged features: two CTAs per SM (three up to S = 136)
-constexpr int kBlendSub = 128;    // targets per record batch
 
 // Selection for k = K <= 4 without a warp per target: FOUR threads per target (adjacent lanes), each scanning one
 // contiguous quarter of the staged sources (single tile, S <= 1024) with a branch-free sorted insertion, then two
@@ -326,12 +328,18 @@ __global__ void __launch_bounds__(kSelThreads)
 
 // K = 0: any k <= 32 (neighbour loop not unrolled, no register prefetch of the next record batch).
 // NWB warps per CTA (8 or 16: the staged feature slice caps the CTAs per SM at three, so warps per CTA set the occupancy).
+// A warp owns a CONTIGUOUS run of the CTA's targets and keeps its own record batches (TW targets at a time) in a
+// private slice of shared memory: no CTA barrier after the feature tile has landed (with CTA-wide batches the two
+// barriers per batch were 18 % of the stall samples at 16 warps).
+__host__ __device__ constexpr int blend_tw(int K) { return K == 0 ? 4 : (K <= 4 ? 16 : 8); }  // targets per warp batch
+
 template <int K, int NWB>
 __global__ void __launch_bounds__(NWB * kWarp)
     interp_blend_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ base, float alpha,
                         const int32_t* __restrict__ idx, const float* __restrict__ weight, int N, int S, int C,
                         int krt, int span, float* __restrict__ out) {
-  extern __shared__ __align__(128) unsigned char s_blend[];  // [S x 512 B features][kBlendSub * k records of 8 B]
+  constexpr int TW = blend_tw(K);
+  extern __shared__ __align__(128) unsigned char s_blend[];  // [S x 512 B features][NWB x TW * k records of 8 B]
   __shared__ __align__(8) uint64_t s_bar;
   const int k = K > 0 ? K : krt;
   const int t = threadIdx.x, lane = t & 31;
@@ -339,7 +347,11 @@ __global__ void __launch_bounds__(NWB * kWarp)
   const int chunk = blockIdx.x, b = blockIdx.z;
   const int n0 = blockIdx.y * span;
   const int n1 = min(N, n0 + span);
-  uint2* s_rec = reinterpret_cast<uint2*>(s_blend + static_cast<size_t>(S) * (kBlendCh * 4));
+  // this warp's run of targets [w0, w1): whole pairs, so that a trip's two targets are neighbours
+  const int per_warp = (((n1 - n0) + NWB - 1) / NWB + 1) & ~1;
+  const int w0 = min(n1, n0 + warp * per_warp);
+  const int w1 = min(n1, w0 + per_warp);
+  uint2* s_rec = reinterpret_cast<uint2*>(s_blend + static_cast<size_t>(S) * (kBlendCh * 4)) + warp * (TW * k);
 
   if (t == 0) {
     tma_prefetch_desc(&fmap);
@@ -348,15 +360,15 @@ __global__ void __launch_bounds__(NWB * kWarp)
     mbar_expect_tx(&s_bar, static_cast<unsigned>(S) * (kBlendCh * 4u));
     tma_load_2d(s_blend, &fmap, chunk * kBlendCh, b * S, &s_bar);
   }
-  // records of one batch: entry e of the batch <-> flat (target, j) position, contiguous in idx / weight
-  constexpr int PE = K > 0 ? (kBlendSub * K + NWB * kWarp - 1) / (NWB * kWarp) : 1;
+  // records of one batch: entry e <-> flat (target, j) position, contiguous in idx / weight
+  constexpr int PE = K > 0 ? (TW * K + kWarp - 1) / kWarp : 1;
   uint2 pre[PE];
-  auto fetch = [&](int s0) {
-    const int cnt = (min(n1, s0 + kBlendSub) - s0) * k;
+  auto fetch = [&](int s0) {  // K > 0 only: the batch's records into registers
+    const int cnt = (min(w1, s0 + TW) - s0) * k;
     const size_t p0 = (static_cast<size_t>(b) * N + s0) * k;
 #pragma unroll
     for (int u = 0; u < PE; ++u) {
-      const int e = t + u * (NWB * kWarp);
+      const int e = lane + u * kWarp;
       pre[u] = e < cnt ? make_uint2(static_cast<unsigned>(__ldg(idx + p0 + e)) * (kBlendCh * 4u),
                                     __float_as_uint(__ldg(weight + p0 + e)))
                        : make_uint2(0u, 0u);
@@ -365,36 +377,36 @@ __global__ void __launch_bounds__(NWB * kWarp)
   auto commit = [&]() {
 #pragma unroll
     for (int u = 0; u < PE; ++u) {
-      const int e = t + u * (NWB * kWarp);
-      if (e < kBlendSub * k) s_rec[e] = pre[u];
+      const int e = lane + u * kWarp;
+      if (e < TW * k) s_rec[e] = pre[u];
     }
   };
-  if (K > 0) {
-    fetch(n0);
+  if (K > 0 && w0 < w1) {
+    fetch(w0);
     commit();
   }
-  __syncthreads();  // barrier init visible to every thread; first record batch in place
+  __syncthreads();  // barrier init visible to every thread (and this warp's first record batch in place)
   mbar_wait(&s_bar, 0);
 
   const uint32_t feat = smem_u32(s_blend) + lane * 16u;
   const f32x2 A2 = pack2(alpha, alpha);
   const int col = chunk * kBlendCh + lane * 4;
-  for (int s0 = n0; s0 < n1; s0 += kBlendSub) {
-    const int cnt = min(n1, s0 + kBlendSub) - s0;
+  for (int s0 = w0; s0 < w1; s0 += TW) {
+    const int cnt = min(w1, s0 + TW) - s0;
     if (K > 0) {
-      if (s0 + kBlendSub < n1) fetch(s0 + kBlendSub);  // next batch: loads in flight under this batch's blend
+      if (s0 + TW < w1) fetch(s0 + TW);  // next batch: loads in flight under this batch's blend
     } else {
-      __syncthreads();
-      for (int e = t; e < cnt * k; e += NWB * kWarp) {
+      __syncwarp();
+      for (int e = lane; e < cnt * k; e += kWarp) {
         const size_t p = (static_cast<size_t>(b) * N + s0) * k + e;
         s_rec[e] = make_uint2(static_cast<unsigned>(__ldg(idx + p)) * (kBlendCh * 4u), __float_as_uint(__ldg(weight + p)));
       }
-      __syncthreads();
+      __syncwarp();
     }
-    // two targets per warp and trip: 2k independent LDS.128 in flight
-    for (int tl = warp; tl < cnt; tl += 2 * NWB) {
-      const bool two = tl + NWB < cnt;
-      const int tb = two ? tl + NWB : tl;
+    // two targets per trip: 2k independent LDS.128 in flight
+    for (int tl = 0; tl < cnt; tl += 2) {
+      const bool two = tl + 1 < cnt;
+      const int tb = two ? tl + 1 : tl;
       const uint2* ra = s_rec + tl * k;
       const uint2* rb = s_rec + tb * k;
       f32x2 a0 = pack2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
@@ -429,10 +441,10 @@ __global__ void __launch_bounds__(NWB * kWarp)
       __stcs(reinterpret_cast<ulonglong2*>(out + rowa * C + col), oa);
       if (two) __stcs(reinterpret_cast<ulonglong2*>(out + rowb * C + col), ob);
     }
-    if (K > 0 && s0 + kBlendSub < n1) {
-      __syncthreads();  // every warp is done with this batch's records
+    if (K > 0 && s0 + TW < w1) {
+      __syncwarp();  // every lane is done with this batch's records
       commit();
-      __syncthreads();
+      __syncwarp();
     }
   }
 }
@@ -932,11 +944,12 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   if (rc != UPP_OK || !two_phase) return rc;
 
   const int chunks = C / kBlendCh;
-  const size_t bsmem = static_cast<size_t>(S) * kBlendCh * sizeof(float) + static_cast<size_t>(kBlendSub) * k * 8;
-  const char* sv2 = getenv("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
-  const int spans = sv2 ? max(1, atoi(sv2)) : blend_pick_spans(static_cast<long>(chunks) * B, N);
   const char* wv = getenv("UPP_BLEND_WARPS");  // tuning aid: 8 or 16 warps per CTA
   const int nwb = (wv && atoi(wv) == 8) ? 8 : 16;
+  const int kk = (k == 3 || k == 4 || k == 8) ? k : 0;  // the instantiated neighbour counts; 0 = run-time loop
+  const size_t bsmem = static_cast<size_t>(S) * kBlendCh * sizeof(float) + static_cast<size_t>(nwb) * blend_tw(kk) * k * 8;
+  const char* sv2 = getenv("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
+  const int spans = sv2 ? max(1, atoi(sv2)) : blend_pick_spans(static_cast<long>(chunks) * B, N);
   int span = ((N + spans - 1) / spans + 2 * nwb - 1) / (2 * nwb) * (2 * nwb);  // whole trips of nwb warps x 2 targets
   dim3 bgrid(chunks, (N + span - 1) / span, B);
 #define UPP_BLEND(K_, W_)                                                                                               \
