@@ -908,14 +908,18 @@ static int fps_pick_cluster(int B, int N) {
 static int dispatch_fps_cluster(int cs, const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                                 cudaStream_t st) {
   const int nc = (((N + cs - 1) / cs) + 1) & ~1;  // slice length: whole point pairs
-  // 4 warps per CTA; point pairs per thread sized to the slice (instantiated: 1, 2, 3, 4, 6, 8, 12, 16)
-  const int want = (nc + 255) / 256;
+  // warps per CTA: 4, or 8 for clusters of up to 4 CTAs (CS * NW <= 32 entries; UPP_FPS_CLUSTER_NW forces 4 / 8);
+  // point pairs per thread sized to the slice (instantiated: 1, 2, 3, 4, 6, 8, 12, 16)
+  const int nw_env = env_int("UPP_FPS_CLUSTER_NW", 0);
+  const int nw = (cs <= 4 && (nw_env == 8 || (nw_env == 0 && cs == 2))) ? 8 : 4;  // measured: 8 warps only pay for 2-CTA clusters
+  const int want = (nc + nw * 64 - 1) / (nw * 64);
   const int p2 = want <= 4 ? want : (want <= 6 ? 6 : (want <= 8 ? 8 : (want <= 12 ? 12 : 16)));
-  if (p2 > 16 || static_cast<long>(p2) * 256 < nc) return UPP_ERR_UNSUPPORTED;
-#define UPP_CL(CS_, P2_) \
-  if (cs == CS_ && p2 == P2_) return launch_fps_cluster<CS_, 4, P2_>(xyz, B, N, M, nc, idx, centers, st);
-#define UPP_CL_ROW(CS_) UPP_CL(CS_, 1) UPP_CL(CS_, 2) UPP_CL(CS_, 3) UPP_CL(CS_, 4) UPP_CL(CS_, 6) UPP_CL(CS_, 8) UPP_CL(CS_, 12) UPP_CL(CS_, 16)
-  UPP_CL_ROW(2) UPP_CL_ROW(4) UPP_CL_ROW(8)
+  if (p2 > 16 || static_cast<long>(p2) * nw * 64 < nc) return UPP_ERR_UNSUPPORTED;
+#define UPP_CL(CS_, NW_, P2_) \
+  if (cs == CS_ && nw == NW_ && p2 == P2_) return launch_fps_cluster<CS_, NW_, P2_>(xyz, B, N, M, nc, idx, centers, st);
+#define UPP_CL_ROW(CS_, NW_) UPP_CL(CS_, NW_, 1) UPP_CL(CS_, NW_, 2) UPP_CL(CS_, NW_, 3) UPP_CL(CS_, NW_, 4) \
+  UPP_CL(CS_, NW_, 6) UPP_CL(CS_, NW_, 8) UPP_CL(CS_, NW_, 12) UPP_CL(CS_, NW_, 16)
+  UPP_CL_ROW(2, 4) UPP_CL_ROW(4, 4) UPP_CL_ROW(8, 4) UPP_CL_ROW(2, 8) UPP_CL_ROW(4, 8)
 #undef UPP_CL_ROW
 #undef UPP_CL
   return UPP_ERR_UNSUPPORTED;

@@ -20,6 +20,8 @@ for _ in range(4):
         ops.fps((torch.rand(32, 1228, 3, generator=g) * 2 - 1).to(dev), 1024)
     elif what == "fps8k":
         ops.fps((torch.rand(128, 8192, 3, generator=g) * 2 - 1).to(dev), 1024)
+    elif what == "fps_cluster":  # seprate_point_cloud's large side: B x 6144 -> 1024 on clusters of 4 CTAs
+        ops.fps((torch.rand(32, 6144, 3, generator=g) * 2 - 1).to(dev), 1024)
     elif what == "knn":
         r = (torch.rand(32, 1024, 3, generator=g) * 2 - 1).to(dev)
         ops.knn(r, r[:, :64].contiguous(), 32)

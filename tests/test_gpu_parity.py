@@ -59,6 +59,9 @@ FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
     "cluster2": {"UPP_FPS_CLUSTER": "2"},
     "cluster4": {"UPP_FPS_CLUSTER": "4"},
     "cluster8": {"UPP_FPS_CLUSTER": "8"},
+    "cluster2_nw8": {"UPP_FPS_CLUSTER": "2", "UPP_FPS_CLUSTER_NW": "8"},  # 4 / 8 warps per CTA (8: clusters of <= 4 CTAs)
+    "cluster4_nw8": {"UPP_FPS_CLUSTER": "4", "UPP_FPS_CLUSTER_NW": "8"},
+    "cluster4_nw4": {"UPP_FPS_CLUSTER": "4", "UPP_FPS_CLUSTER_NW": "4"},
     "v1": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "0"},                       # round-1a strided kernels
     "v1_w4": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "1"},
 }
