@@ -105,6 +105,10 @@ __device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int
     // ---- 2. seed the list with the sorted lane minima (first block only) ----
     // (Seeding with the 32 smallest of the 128 per-lane GROUP minima -- four row sorts + three top-32 merges, ~4x
     //  fewer survivors below -- was measured on B200 and lost: kNN 64q x 1024 went from 15.4 to 19.5 us.)
+    // (Tightening the seed bound by counting -- a six-probe bisection over the sorted seeds for the smallest seed
+    //  distance with >= k elements strictly below it, REDUX.ADD per probe -- cuts the insertions per 1024-reference
+    //  query from ~100 to ~13 but costs as many instructions as it saves: 15.4 us either way, 29.2 -> 31.7 us at
+    //  B = 128.  The per-query instruction budget (2400) is spread over control flow, not concentrated in insertions.)
     if (!st.seeded) {
       st.seeded = true;
       st.ld = lmin;
