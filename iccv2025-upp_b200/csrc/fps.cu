@@ -366,6 +366,10 @@ __device__ __forceinline__ void fps_span(const f32x2 (&X)[P2], const f32x2 (&Y)[
 //     thread resolves the block winner itself: S2 == 0 scans the NW posted pairs with vector
 //     LDS + a select tree (NW <= 8), S2 == 1 does REDUX.MAX + ballot over them (NW >= 16).
 //   * a single warp (NW == 1) needs no shared-memory round trip at all.
+// (Posting {key, x, y, z} per warp -- every lane fetching its own candidate's coordinates while the REDUX / vote are in
+//  flight, so that the select tree after the barrier yields the next centre with no second shared-memory round
+//  trip -- was built and measured at N = 1228: 0.207 us per round against 0.153; the 3 extra divergent LDS per lane
+//  and round and the wider select tree cost more than the dependent load they remove.)
 // SEARCH: 0 = in-thread slot search in the shadow of the REDUX (select chain / min tree; small clouds,
 // latency bound), 2 = the posting lane descends a kept max tree after the vote (large clouds, ALU bound).
 template <int NW, int P2, int S2, int SEARCH = 0>
