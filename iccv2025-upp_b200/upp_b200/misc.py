@@ -46,8 +46,11 @@ def seprate_point_cloud(xyz, num_points, crop, fixed_points=None, padding_zeros=
             else:
                 fixed_point = fixed_points
             center = fixed_point.reshape(1, 1, 3)
-        centers.append(center.to(xyz.device, xyz.dtype))
-    centers = torch.cat(centers, 0)                                                     # (B,1,3)
+        centers.append(center)
+    if all(c.device.type == "cpu" for c in centers):  # the usual case: ONE host-to-device copy instead of B
+        centers = torch.cat(centers, 0).to(xyz.device, xyz.dtype)                       # (B,1,3)
+    else:
+        centers = torch.cat([c.to(xyz.device, xyz.dtype) for c in centers], 0)
     distance_matrix = torch.norm(centers.unsqueeze(2) - xyz.unsqueeze(1), p=2, dim=-1)  # (B,1,n)
     idx = torch.argsort(distance_matrix, dim=-1, descending=False)[:, 0]                # (B,n)
     take = lambda ix: torch.gather(xyz, 1, ix.unsqueeze(-1).expand(-1, -1, 3))  # noqa: E731

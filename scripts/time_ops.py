@@ -13,15 +13,17 @@ import upp_b200  # noqa: E402
 from upp_b200 import ops  # noqa: E402
 
 
-def timeit(fn, iters=20, warm=5, flush=None, reps=4):
-    """Kernel-only time: the op is captured into a CUDA graph and replayed (no Python / launch gaps)."""
+def timeit(fn, iters=20, warm=5, flush=None, reps=4, graph=True):
+    """Kernel-only time: the op is captured into a CUDA graph and replayed (no Python / launch gaps); graph=False times
+    eager calls (functions with host-side random draws / pageable copies cannot be captured)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        fn()
-    fn = g.replay
+    if graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        fn = g.replay
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -54,10 +56,10 @@ def main():
     g = torch.Generator().manual_seed(0)
     rows = []
 
-    def rec(name, fn, work=None):
+    def rec(name, fn, work=None, graph=True):
         if args.only and args.only not in name:
             return
-        med, best = timeit(fn, flush=flush)
+        med, best = timeit(fn, flush=flush, graph=graph, reps=4 if graph else 1)
         r = {"op": name, "us_median": round(med, 2), "us_min": round(best, 2)}
         if work:
             r.update(work(med))
@@ -172,6 +174,26 @@ def main():
         x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
         rec(f"fps B{B} N{N} M{M}", lambda: ops.fps(x, M),
             lambda us: {"us_per_iter": round(us / max(M - 1, 1), 4), "gflops": round(8.0 * N * (M - 1) * B / us / 1e3, 1)})
+    # seprate_point_cloud as the runners call it (tools/runner_module.py:131: 8192 points, crop in [1/4, 3/4] of them,
+    # both sides resampled to 1024): the reference's 2*B batch-1 FPS launches are two batched ones here, the larger
+    # (up to 6144 points, B <= 37) on clusters of CTAs.  UPP_FPS_CLUSTER=0 gives the one-CTA-per-cloud number.
+    if not args.only or "seprate" in args.only:
+        import random
+        x = (torch.rand(32, 8192, 3, generator=g) * 2 - 1).to(dev)
+        for crop in (2048, 4096, 6144):
+            for cl in (None, "0"):
+                if cl is None:
+                    os.environ.pop("UPP_FPS_CLUSTER", None)
+                else:
+                    os.environ["UPP_FPS_CLUSTER"] = cl
+
+                def run():
+                    random.seed(1)
+                    torch.manual_seed(1)
+                    return upp_b200.misc.seprate_point_cloud(x, 8192, crop, sample_points=1024)
+                rec(f"seprate_point_cloud B32 N8192 crop{crop} -> 1024 + 1024 (eager){' [UPP_FPS_CLUSTER=0]' if cl else ''}", run,
+                    graph=False)
+        os.environ.pop("UPP_FPS_CLUSTER", None)
     for (B, N, Q, k) in [(32, 1024, 64, 32), (32, 1096, 32, 16), (32, 32, 32, 16), (32, 64, 32, 8), (128, 1024, 64, 32),
                          (32, 2048, 128, 32), (32, 1536, 128, 32)]:
         r = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
