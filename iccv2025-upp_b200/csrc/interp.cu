@@ -7,14 +7,18 @@
 // which build the full (B,N,S) square_distance matrix, SORT every row, slice k columns, materialise
 // index_points(points2, idx) as a (B,N,k,C) tensor, multiply by the weights and sum.
 //
-// Here, forward is ONE launch: the S source points of a cloud are staged once per CTA by TMA bulk copy,
-// one warp per target point selects its k nearest sources with the register-resident warp top-k of
-// topk.cuh on the reference's own distance form (square_distance: -2 a.b + |a|^2 + |b|^2), turns them
-// into weights (1/(d+eps), normalised) and immediately gathers the k feature rows (float4, coalesced
-// over channels) into the output row -- no distance matrix, no sort, no (B,N,k,C) tensor.
+// Here, small / narrow problems take ONE forward launch: the S source points of a cloud are staged once per
+// CTA by TMA bulk copy, one warp per target point selects its k nearest sources with the register-resident
+// warp top-k of topk.cuh on the reference's own distance form (square_distance: -2 a.b + |a|^2 + |b|^2),
+// turns them into weights (1/(d+eps), normalised) and immediately gathers the k feature rows (float4,
+// coalesced over channels) into the output row -- no distance matrix, no sort, no (B,N,k,C) tensor.
 // Backward is deterministic and atomic-free: a target-side kernel (one warp per target) produces
 // d loss / d dist and grad_xyz1; a source-side kernel (one CTA per source point) scans the cloud's
 // (N,k) index list in order and accumulates grad_points2 / grad_xyz2 rows in registers.
+// Wide features (the seg propagation: 2048 <- 128 sources, 1152 channels) are HBM-bound and get their own
+// kernels further down: selection + shared-memory blend over a 2-D TMA tile (forward), per-tile CSR + a
+// TMA pipeline that streams grad_out exactly once (feature gradient).  Same results, see the dispatch in
+// interp_fwd_launch / interp_bwd_launch.
 #include "topk.cuh"
 
 namespace upp {
@@ -228,7 +232,6 @@ __device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
 //  kernel -- griddepcontrol.wait after the prologue / feature tile load -- was built and measured: 68.1 vs 68.6 us
 //  forward, 65.0 vs 64.5 us backward, C5 step 0.1956 vs 0.1951 ms.  No gain; ordinary launches kept.)
 constexpr int kBlendCh = 128;
-constexpr int kBlendWarps = 8;
 constexpr int kBlendMaxS = 192;   // 96 KB of staged features: two CTAs per SM (three up to S = 136)
 
 // Selection for k = K <= 4 without a warp per target: FOUR threads per target (adjacent lanes), each scanning one
@@ -410,18 +413,21 @@ __global__ void __launch_bounds__(NWB * kWarp)
       const uint2* ra = s_rec + tl * k;
       const uint2* rb = s_rec + tb * k;
       f32x2 a0 = pack2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+      auto neighbour = [&](int j) {
+        const uint2 ea = ra[j], eb = rb[j];
+        const ulonglong2 fa = lds_v2u64(feat + ea.x), fb = lds_v2u64(feat + eb.x);
+        const f32x2 WA = pack2(__uint_as_float(ea.y), __uint_as_float(ea.y));
+        const f32x2 WB = pack2(__uint_as_float(eb.y), __uint_as_float(eb.y));
+        a0 = add2(a0, mul2(fa.x, WA));
+        a1 = add2(a1, mul2(fa.y, WA));
+        b0 = add2(b0, mul2(fb.x, WB));
+        b1 = add2(b1, mul2(fb.y, WB));
+      };
+      if constexpr (K > 0) {
 #pragma unroll
-      for (int j = 0; j < (K > 0 ? K : 1); ++j) {
-        for (int jj = j; jj < k; jj += (K > 0 ? k : 1)) {  // K > 0: exactly one trip (unrolled); K == 0: the run-time loop
-          const uint2 ea = ra[jj], eb = rb[jj];
-          const ulonglong2 fa = lds_v2u64(feat + ea.x), fb = lds_v2u64(feat + eb.x);
-          const f32x2 WA = pack2(__uint_as_float(ea.y), __uint_as_float(ea.y));
-          const f32x2 WB = pack2(__uint_as_float(eb.y), __uint_as_float(eb.y));
-          a0 = add2(a0, mul2(fa.x, WA));
-          a1 = add2(a1, mul2(fa.y, WA));
-          b0 = add2(b0, mul2(fb.x, WB));
-          b1 = add2(b1, mul2(fb.y, WB));
-        }
+        for (int j = 0; j < K; ++j) neighbour(j);
+      } else {
+        for (int j = 0; j < k; ++j) neighbour(j);
       }
       ulonglong2 oa, ob;
       oa.x = mul2(A2, a0);
@@ -950,7 +956,7 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   const size_t bsmem = static_cast<size_t>(S) * kBlendCh * sizeof(float) + static_cast<size_t>(nwb) * blend_tw(kk) * k * 8;
   const char* sv2 = getenv("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
   const int spans = sv2 ? max(1, atoi(sv2)) : blend_pick_spans(static_cast<long>(chunks) * B, N);
-  int span = ((N + spans - 1) / spans + 2 * nwb - 1) / (2 * nwb) * (2 * nwb);  // whole trips of nwb warps x 2 targets
+  const int span = ((N + spans - 1) / spans + 1) & ~1;  // whole pairs of targets (a warp blends two per trip)
   dim3 bgrid(chunks, (N + span - 1) / span, B);
 #define UPP_BLEND(K_, W_)                                                                                               \
   do {                                                                                                                   \
