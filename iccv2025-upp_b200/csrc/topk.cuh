@@ -93,13 +93,23 @@ __device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int
     float d[SLOTS];
     float lmin = kInf;
     int lmin_s = 0;
+    const bool full = blk + SLOTS * kWarp <= tile;  // warp-uniform: every slot of the block is in range
+    if (full) {  // no guards, one base address + immediates (the guards and 3*c products are ~15 % of a query's instructions)
+      const float* pr = s_ref + 3 * (blk + lane);
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int c = blk + s * kWarp + lane;
-      d[s] = kInf;
-      if (blk + s * kWarp < tile) {  // warp-uniform guard, then the per-lane tail
-        if (c < tile) d[s] = dist(s_ref[3 * c], s_ref[3 * c + 1], s_ref[3 * c + 2]);
+      for (int s = 0; s < SLOTS; ++s) {
+        d[s] = dist(pr[3 * kWarp * s], pr[3 * kWarp * s + 1], pr[3 * kWarp * s + 2]);
         if (d[s] < lmin) { lmin = d[s]; lmin_s = s; }  // strict '<': lowest index among equal minima
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        const int c = blk + s * kWarp + lane;
+        d[s] = kInf;
+        if (blk + s * kWarp < tile) {  // warp-uniform guard, then the per-lane tail
+          if (c < tile) d[s] = dist(s_ref[3 * c], s_ref[3 * c + 1], s_ref[3 * c + 2]);
+          if (d[s] < lmin) { lmin = d[s]; lmin_s = s; }
+        }
       }
     }
     // ---- 2. seed the list with the sorted lane minima (first block only) ----
@@ -123,7 +133,7 @@ __device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int
     // ---- 3. stream the register slots through the threshold filter ----
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-      if (blk + s * kWarp < tile) {  // warp-uniform
+      if (full || blk + s * kWarp < tile) {  // warp-uniform
         const int myi = base + blk + s * kWarp + lane;
         unsigned m = __ballot_sync(0xffffffffu, key_less(d[s], myi, st.thr_d, st.thr_i));
         if (m != 0) {
