@@ -23,6 +23,7 @@ constexpr int kKnnSlots = 32;    // distances per lane per block (block = 1024 r
 // ---- distance forms ---------------------------------------------------------------------
 // KNN_CUDA 0.2 knn.cu (cuComputeDistanceGlobal): ssd += (r - q)^2 over x, y, z.
 struct DistDirect {
+  static constexpr bool kNonNegative = true;  // sums of squares: (distance, index) compares as one unsigned 64-bit key
   float qx, qy, qz;
   __device__ __forceinline__ void set(float x, float y, float z) { qx = x; qy = y; qz = z; }
   __device__ __forceinline__ float operator()(float rx, float ry, float rz) const {
@@ -33,6 +34,7 @@ struct DistDirect {
 // in that association (the form propagate / PointNetFeaturePropagation sort on).  It can be slightly
 // negative for coincident points, exactly like the reference's.
 struct DistExpanded {
+  static constexpr bool kNonNegative = false;  // can be slightly negative: float compare
   float qx, qy, qz, s1;
   __device__ __forceinline__ void set(float x, float y, float z) {
     qx = x; qy = y; qz = z;
@@ -48,8 +50,21 @@ struct DistExpanded {
 __device__ __forceinline__ bool key_less(float da, int ia, float db, int ib) {
   return da < db || (da == db && ia < ib);
 }
+// The same order for NON-NEGATIVE distances (no NaN) and non-negative indices, as one 64-bit unsigned compare of
+// (distance bits : index) -- two ISETP instead of FSETP + FSETP + ISETP + PLOP3, on the serial insertion chain.
+template <bool BITS>
+__device__ __forceinline__ bool key_less_t(float da, int ia, float db, int ib) {
+  if constexpr (BITS) {
+    const unsigned long long ka = (static_cast<unsigned long long>(__float_as_uint(da)) << 32) | static_cast<unsigned>(ia);
+    const unsigned long long kb = (static_cast<unsigned long long>(__float_as_uint(db)) << 32) | static_cast<unsigned>(ib);
+    return ka < kb;
+  } else {
+    return key_less(da, ia, db, ib);
+  }
+}
 
 // Bitonic sort of one (d, i) pair per lane, ascending by (d, i) over lanes 0..31, via shuffles.
+template <bool BITS = false>
 __device__ __forceinline__ void warp_bitonic_sort(float& d, int& i, int lane) {
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
@@ -60,7 +75,7 @@ __device__ __forceinline__ void warp_bitonic_sort(float& d, int& i, int lane) {
       const bool ascending = ((lane & size) == 0);  // direction of the merge this lane is in
       const bool lower = ((lane & stride) == 0);    // lower lane of the compared pair
       const bool keep_min = (lower == ascending);
-      const bool take = keep_min ? key_less(od, oi, d, i) : key_less(d, i, od, oi);
+      const bool take = keep_min ? key_less_t<BITS>(od, oi, d, i) : key_less_t<BITS>(d, i, od, oi);
       if (take) { d = od; i = oi; }
     }
   }
@@ -123,7 +138,7 @@ __device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int
       st.seeded = true;
       st.ld = lmin;
       st.li = lmin < kInf ? base + blk + lmin_s * kWarp + lane : 0x7fffffff;
-      warp_bitonic_sort(st.ld, st.li, lane);
+      warp_bitonic_sort<Dist::kNonNegative>(st.ld, st.li, lane);
 #pragma unroll
       for (int s = 0; s < SLOTS; ++s)
         if (s == lmin_s) d[s] = kInf;  // consumed
@@ -135,7 +150,7 @@ __device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int
     for (int s = 0; s < SLOTS; ++s) {
       if (full || blk + s * kWarp < tile) {  // warp-uniform
         const int myi = base + blk + s * kWarp + lane;
-        unsigned m = __ballot_sync(0xffffffffu, key_less(d[s], myi, st.thr_d, st.thr_i));
+        unsigned m = __ballot_sync(0xffffffffu, key_less_t<Dist::kNonNegative>(d[s], myi, st.thr_d, st.thr_i));
         if (m != 0) {
           while (m) {
             const int src = __ffs(m) - 1;
@@ -145,8 +160,8 @@ __device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int
             const float ud = __shfl_up_sync(0xffffffffu, st.ld, 1);
             const int ui = __shfl_up_sync(0xffffffffu, st.li, 1);
             // entries greater than the candidate shift right by one; the first of them is replaced
-            const bool mine_gt = key_less(cd, ci, st.ld, st.li);
-            const bool left_gt = (lane > 0) && key_less(cd, ci, ud, ui);
+            const bool mine_gt = key_less_t<Dist::kNonNegative>(cd, ci, st.ld, st.li);
+            const bool left_gt = (lane > 0) && key_less_t<Dist::kNonNegative>(cd, ci, ud, ui);
             st.li = mine_gt ? (left_gt ? ui : ci) : st.li;
             st.ld = mine_gt ? (left_gt ? ud : cd) : st.ld;
           }
