@@ -687,11 +687,14 @@ constexpr unsigned kBsOffBytes = 272;       // 129 uint16 offsets, padded to a m
 constexpr unsigned kBsRowBytes = kBlendCh * 4;
 constexpr unsigned kBsStagePad = 16;         // the entry prefetch reads one slot past the last entry
 
-__host__ __device__ inline unsigned bs_block_bytes(int k) { return kBsOffBytes + static_cast<unsigned>(kBsTile) * k * 8u; }
+// CSR block of one (cloud, tile): [uint16 off[129] (pad)][E entries of 8 B][E bytes: neighbour slot j of each entry],
+// E = kBsTile * k.  The streamed kernel copies the first two parts only; the j bytes serve the coordinate gradient.
+__host__ __device__ inline unsigned bs_block_copy_bytes(int k) { return kBsOffBytes + static_cast<unsigned>(kBsTile) * k * 8u; }
+__host__ __device__ inline unsigned bs_block_bytes(int k) { return bs_block_copy_bytes(k) + static_cast<unsigned>(kBsTile) * k; }
 
 // stage = [tile][CSR block][pad for the entry prefetch], rounded to the 128-byte alignment TMA tile loads need
 __host__ __device__ inline unsigned bs_stage_bytes(int k) {
-  return (kBsTile * kBsRowBytes + bs_block_bytes(k) + kBsStagePad + 127u) & ~127u;
+  return (kBsTile * kBsRowBytes + bs_block_copy_bytes(k) + kBsStagePad + 127u) & ~127u;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -742,6 +745,7 @@ __global__ void __launch_bounds__(256)
   unsigned char* blk = csr + static_cast<size_t>(wg) * bs_block_bytes(k);
   uint16_t* off = reinterpret_cast<uint16_t*>(blk);
   uint2* ent = reinterpret_cast<uint2*>(blk + kBsOffBytes);
+  unsigned char* jb = blk + bs_block_copy_bytes(k);
   int run = incl - tot;
   __syncwarp();
 #pragma unroll
@@ -765,7 +769,10 @@ __global__ void __launch_bounds__(256)
       __syncwarp();
       if (valid && rank == 0) cnt[s] += __popc(m);
       __syncwarp();
-      if (valid) ent[pos] = make_uint2(static_cast<unsigned>(e / k) * kBsRowBytes, __float_as_uint(sw[r]));
+      if (valid) {
+        ent[pos] = make_uint2(static_cast<unsigned>(e / k) * kBsRowBytes, __float_as_uint(sw[r]));
+        jb[pos] = static_cast<unsigned char>(e % k);
+      }
     }
   }
 }
@@ -778,7 +785,8 @@ __global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int chunk = blockIdx.x, b = blockIdx.y;
-  const unsigned blk_bytes = bs_block_bytes(k);
+  const unsigned blk_bytes = bs_block_copy_bytes(k);  // what a stage holds of a block
+  const unsigned blk_stride = bs_block_bytes(k);      // distance between blocks in the workspace
   const unsigned stage_bytes = bs_stage_bytes(k);
 
   if (threadIdx.x == 0) {
@@ -794,7 +802,7 @@ __global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
   if (warp == kBsWarps) {  // ---- producer: one 2-D TMA tile (64 rows x 512 B) + the tile's CSR block per stage ----
     if (lane == 0) {
       tma_prefetch_desc(&gmap);
-      const unsigned char* csrc = csr + static_cast<size_t>(b) * tiles * blk_bytes;
+      const unsigned char* csrc = csr + static_cast<size_t>(b) * tiles * blk_stride;
       for (int t = 0; t < tiles; ++t) {
         const int st = t % kBsStages;
         unsigned char* dst = s_stage + static_cast<size_t>(st) * stage_bytes;
@@ -802,7 +810,7 @@ __global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
         // rows past this cloud's N (next cloud's, or zero fill past the tensor) are loaded but never referenced
         mbar_expect_tx(&s_full[st], kBsTile * kBsRowBytes + blk_bytes);
         tma_load_2d(dst, &gmap, chunk * kBlendCh, b * N + t * kBsTile, &s_full[st]);
-        bulk_g2s(dst + kBsTile * kBsRowBytes, csrc + static_cast<size_t>(t) * blk_bytes, blk_bytes, &s_full[st]);
+        bulk_g2s(dst + kBsTile * kBsRowBytes, csrc + static_cast<size_t>(t) * blk_stride, blk_bytes, &s_full[st]);
       }
     }
     return;
@@ -859,6 +867,48 @@ __global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
       o.y = mul2(A2, acc[i][1]);
       *reinterpret_cast<ulonglong2*>(gfeat2 + (static_cast<size_t>(b) * S + s) * C + chunk * kBlendCh + lane * 4) = o;
     }
+  }
+}
+
+// Coordinate gradient of the sources from the CSR (replaces the source-side kernel's list scan when the streamed
+// path runs): one warp per (cloud, source), lane l takes tiles l, l + 32, ...; per match
+//   grad_xyz2[b,s] += -2 * gd[p] * (x1[n] - x2[s])        (d/dx2 of -2 x1.x2 + |x1|^2 + |x2|^2 is -2 (x1 - x2))
+// accumulated per lane in tile order, then combined by a fixed shuffle tree: deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+    interp_bwd_xyz2_kernel(const unsigned char* __restrict__ csr, const float* __restrict__ gd,
+                           const float* __restrict__ xyz1, const float* __restrict__ xyz2, int B, int N, int S, int k,
+                           int tiles, float* __restrict__ gxyz2) {
+  const int lane = threadIdx.x & 31;
+  const long wg = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (wg >= static_cast<long>(B) * S) return;
+  const int b = static_cast<int>(wg / S), s = static_cast<int>(wg % S);
+  const float* p2 = xyz2 + (static_cast<size_t>(b) * S + s) * 3;
+  const float sx = __ldg(p2), sy = __ldg(p2 + 1), sz = __ldg(p2 + 2);
+  const unsigned stride = bs_block_bytes(k);
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  for (int t = lane; t < tiles; t += 32) {
+    const unsigned char* blk = csr + (static_cast<size_t>(b) * tiles + t) * stride;
+    const uint16_t* off = reinterpret_cast<const uint16_t*>(blk);
+    const uint2* ent = reinterpret_cast<const uint2*>(blk + kBsOffBytes);
+    const unsigned char* jb = blk + bs_block_copy_bytes(k);
+    const int beg = off[s], end = off[s + 1];
+    for (int m = beg; m < end; ++m) {
+      const int n = t * kBsTile + static_cast<int>(ent[m].x / kBsRowBytes);
+      const size_t row = static_cast<size_t>(b) * N + n;
+      const float g = __fmul_rn(-2.0f, __ldg(gd + row * k + jb[m]));
+      ax = __fmaf_rn(g, __ldg(xyz1 + row * 3) - sx, ax);
+      ay = __fmaf_rn(g, __ldg(xyz1 + row * 3 + 1) - sy, ay);
+      az = __fmaf_rn(g, __ldg(xyz1 + row * 3 + 2) - sz, az);
+    }
+  }
+  ax = warp_sum(ax);
+  ay = warp_sum(ay);
+  az = warp_sum(az);
+  if (lane == 0) {
+    float* o = gxyz2 + (static_cast<size_t>(b) * S + s) * 3;
+    o[0] = ax;
+    o[1] = ay;
+    o[2] = az;
   }
 }
 
@@ -1009,8 +1059,8 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
     int rc = launch_status();
     if (rc != UPP_OK) return rc;
   }
-  // wide features: the feature gradient streams grad_out once (interp_bwd_stream_kernel); the source-side kernel
-  // then only carries the coordinate terms (C = 0: list scan, no feature rows)
+  // wide features: the feature gradient streams grad_out once (interp_bwd_stream_kernel) and the sources' coordinate
+  // gradient is read off the same CSR (interp_bwd_xyz2_kernel); the source-side kernel is not launched at all
   const int env = interp_path_env();
   const size_t need = interp_bwd_workspace_bytes(B, N, S, C, k);
   const bool stream_ok = need > 0 && ws != nullptr && ws_bytes >= need && aligned16(gout, gfeat2, ws);
@@ -1020,21 +1070,19 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
   if (streamed && make_tmap_2d_f32(&gmap, gout, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * N,
                                    static_cast<uint64_t>(C) * sizeof(float), kBlendCh, kBsTile) != UPP_OK)
     streamed = false;  // no tensor-map encoder in this driver: the source-side kernel serves every shape
-  const int csrc = streamed ? 0 : C;
-  if (!streamed || want_xyz) {
+  if (!streamed) {
     dim3 grid(S, B);
     const float* gdp = want_xyz ? gd_ws : nullptr;
     float* g2p = want_xyz ? gxyz2 : nullptr;
 #define UPP_SRC(G_) \
-  interp_bwd_source_kernel<G_><<<grid, kSrcThreads, 0, st>>>(gout, idx, weight, gdp, xyz1, xyz2, alpha, N, S, csrc, k, gfeat2, g2p)
-    if (csrc > 1024) UPP_SRC(1);       // 256 threads x 8 channels per pass
-    else if (csrc > 512) UPP_SRC(2);
-    else if (csrc > 256) UPP_SRC(4);
+  interp_bwd_source_kernel<G_><<<grid, kSrcThreads, 0, st>>>(gout, idx, weight, gdp, xyz1, xyz2, alpha, N, S, C, k, gfeat2, g2p)
+    if (C > 1024) UPP_SRC(1);       // 256 threads x 8 channels per pass
+    else if (C > 512) UPP_SRC(2);
+    else if (C > 256) UPP_SRC(4);
     else UPP_SRC(8);                // 32 threads x 8 channels = 256 channels per group
 #undef UPP_SRC
     count_launch();
-    int rc = launch_status();
-    if (rc != UPP_OK || !streamed) return rc;
+    return launch_status();
   }
   const int tiles = (N + kBsTile - 1) / kBsTile;
   const long warps = static_cast<long>(B) * tiles;
@@ -1043,6 +1091,14 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
   count_launch();
   int rc = launch_status();
   if (rc != UPP_OK) return rc;
+  if (want_xyz && gxyz2 != nullptr) {
+    const long w2 = static_cast<long>(B) * S;
+    interp_bwd_xyz2_kernel<<<static_cast<unsigned>((w2 + 7) / 8), 256, 0, st>>>(static_cast<const unsigned char*>(ws), gd_ws,
+                                                                              xyz1, xyz2, B, N, S, k, tiles, gxyz2);
+    count_launch();
+    rc = launch_status();
+    if (rc != UPP_OK) return rc;
+  }
   const size_t ssmem = static_cast<size_t>(kBsStages) * bs_stage_bytes(k);
   cudaError_t e = cudaFuncSetAttribute(interp_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(ssmem));
