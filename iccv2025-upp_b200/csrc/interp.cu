@@ -342,6 +342,8 @@ __global__ void __launch_bounds__(NWB * kWarp)
                         const int32_t* __restrict__ idx, const float* __restrict__ weight, int N, int S, int C,
                         int krt, int span, float* __restrict__ out) {
   constexpr int TW = blend_tw(K);
+  // bytes of one staged feature row: 512 for 128-channel chunks, 4 C when the whole (narrow, C < 128) row is one chunk
+  const unsigned rowb = static_cast<unsigned>(min(C, kBlendCh)) * 4u;
   extern __shared__ __align__(128) unsigned char s_blend[];  // [S x 512 B features][NWB x TW * k records of 8 B]
   __shared__ __align__(8) uint64_t s_bar;
   const int k = K > 0 ? K : krt;
@@ -354,13 +356,13 @@ __global__ void __launch_bounds__(NWB * kWarp)
   const int per_warp = (((n1 - n0) + NWB - 1) / NWB + 1) & ~1;
   const int w0 = min(n1, n0 + warp * per_warp);
   const int w1 = min(n1, w0 + per_warp);
-  uint2* s_rec = reinterpret_cast<uint2*>(s_blend + static_cast<size_t>(S) * (kBlendCh * 4)) + warp * (TW * k);
+  uint2* s_rec = reinterpret_cast<uint2*>(s_blend + ((static_cast<size_t>(S) * rowb + 15) & ~static_cast<size_t>(15))) + warp * (TW * k);
 
   if (t == 0) {
     tma_prefetch_desc(&fmap);
     mbar_init(&s_bar, 1);
     mbar_fence_init();
-    mbar_expect_tx(&s_bar, static_cast<unsigned>(S) * (kBlendCh * 4u));
+    mbar_expect_tx(&s_bar, static_cast<unsigned>(S) * rowb);
     tma_load_2d(s_blend, &fmap, chunk * kBlendCh, b * S, &s_bar);
   }
   // records of one batch: entry e <-> flat (target, j) position, contiguous in idx / weight
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(NWB * kWarp)
 #pragma unroll
     for (int u = 0; u < PE; ++u) {
       const int e = lane + u * kWarp;
-      pre[u] = e < cnt ? make_uint2(static_cast<unsigned>(__ldg(idx + p0 + e)) * (kBlendCh * 4u),
+      pre[u] = e < cnt ? make_uint2(static_cast<unsigned>(__ldg(idx + p0 + e)) * rowb,
                                     __float_as_uint(__ldg(weight + p0 + e)))
                        : make_uint2(0u, 0u);
     }
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(NWB * kWarp)
   const uint32_t feat = smem_u32(s_blend) + lane * 16u;
   const f32x2 A2 = pack2(alpha, alpha);
   const int col = chunk * kBlendCh + lane * 4;
+  const bool lane_on = lane * 16u < rowb;  // narrow rows: the upper lanes compute on whatever follows and store nothing
   for (int s0 = w0; s0 < w1; s0 += TW) {
     const int cnt = min(w1, s0 + TW) - s0;
     if (K > 0) {
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(NWB * kWarp)
       __syncwarp();
       for (int e = lane; e < cnt * k; e += kWarp) {
         const size_t p = (static_cast<size_t>(b) * N + s0) * k + e;
-        s_rec[e] = make_uint2(static_cast<unsigned>(__ldg(idx + p)) * (kBlendCh * 4u), __float_as_uint(__ldg(weight + p)));
+        s_rec[e] = make_uint2(static_cast<unsigned>(__ldg(idx + p)) * rowb, __float_as_uint(__ldg(weight + p)));
       }
       __syncwarp();
     }
@@ -435,17 +438,19 @@ __global__ void __launch_bounds__(NWB * kWarp)
       ob.x = mul2(A2, b0);
       ob.y = mul2(A2, b1);
       const size_t rowa = static_cast<size_t>(b) * N + s0 + tl;
-      const size_t rowb = static_cast<size_t>(b) * N + s0 + tb;
-      if (base) {
+      const size_t rowb2 = static_cast<size_t>(b) * N + s0 + tb;
+      if (base && lane_on) {
         const ulonglong2 pa = __ldg(reinterpret_cast<const ulonglong2*>(base + rowa * C + col));
-        const ulonglong2 pb = __ldg(reinterpret_cast<const ulonglong2*>(base + rowb * C + col));
+        const ulonglong2 pb = __ldg(reinterpret_cast<const ulonglong2*>(base + rowb2 * C + col));
         oa.x = add2(pa.x, oa.x);
         oa.y = add2(pa.y, oa.y);
         ob.x = add2(pb.x, ob.x);
         ob.y = add2(pb.y, ob.y);
       }
-      __stcs(reinterpret_cast<ulonglong2*>(out + rowa * C + col), oa);
-      if (two) __stcs(reinterpret_cast<ulonglong2*>(out + rowb * C + col), ob);
+      if (lane_on) {
+        __stcs(reinterpret_cast<ulonglong2*>(out + rowa * C + col), oa);
+        if (two) __stcs(reinterpret_cast<ulonglong2*>(out + rowb2 * C + col), ob);
+      }
     }
     if (K > 0 && s0 + TW < w1) {
       __syncwarp();  // every lane is done with this batch's records
@@ -939,19 +944,26 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   const bool vec4 = (C % 4 == 0) && aligned16(feat2, out, base);
   // wide features: selection alone, then the shared-memory blend (interp_blend_kernel)
   const int env = interp_path_env();
-  const bool blend_ok = vec4 && C > 0 && C % kBlendCh == 0 && S <= kBlendMaxS && B <= 65535;
+  // 128-channel chunks, or one narrower chunk holding the whole row (C < 128)
+  const bool blend_ok = vec4 && C > 0 && (C % kBlendCh == 0 || C < kBlendCh) && S <= kBlendMaxS && B <= 65535;
+  // thread-per-target selection: instantiated neighbour counts, cost ~ S * k compare/selects per target
+  const bool sel_k = k == 1 || k == 2 || k == 3 || k == 4 || k == 6 || k == 8 || k == 16;
+  const bool sel_ok = sel_k && S <= 1024 && static_cast<long>(S) * k <= 1024;
   const bool blend_big = static_cast<size_t>(B) * N * C >= (static_cast<size_t>(8) << 20) && N >= 256;
-  bool two_phase = blend_ok && (env == 1 || (env < 0 && blend_big));
+  // narrow / mid-size problems whose one-launch cost is the per-target warp selection (k = 16 of 32 sources: a 15-stage
+  // sort and a 16-step weight sum per target) also split, as long as the selection can go thread-per-target
+  const bool blend_mid = sel_ok && static_cast<long>(B) * N >= 8192 && N >= 256;
+  bool two_phase = blend_ok && (env == 1 || (env < 0 && (blend_big || blend_mid)));
   CUtensorMap fmap;  // feat2 as (B*S rows) x C, box = S rows x 128 channels
   if (two_phase && make_tmap_2d_f32(&fmap, feat2, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * S,
-                                    static_cast<uint64_t>(C) * sizeof(float), kBlendCh, static_cast<uint32_t>(S)) != UPP_OK)
+                                    static_cast<uint64_t>(C) * sizeof(float), static_cast<uint32_t>(min(C, kBlendCh)),
+                                    static_cast<uint32_t>(S)) != UPP_OK)
     two_phase = false;  // no tensor-map encoder in this driver: the one-launch kernel serves every shape
   const int csel = two_phase ? 0 : C;
   // UPP_INTERP_SELECT (test aid): 0 = never the thread-per-target selection, 1 = whenever k <= 4 and S <= 1024
   const char* sv = getenv("UPP_INTERP_SELECT");
   const int senv = sv ? atoi(sv) : -1;
-  const bool thread_select = two_phase && k <= 4 && S <= 1024 && senv != 0 &&
-                             (senv == 1 || static_cast<long>(B) * N >= 4096);
+  const bool thread_select = two_phase && sel_ok && senv != 0 && (senv == 1 || static_cast<long>(B) * N >= 4096);
   if (thread_select) {
     const char* tv = getenv("UPP_INTERP_TPT");  // tuning aid: threads per target (1, 2, 4)
     const int tpt = tv ? atoi(tv) : 1;
@@ -968,7 +980,10 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
     else if (k == 3) UPP_SELECT(3, T_); \
     else UPP_SELECT(4, T_);         \
   } while (0)
-    if (tpt == 4) UPP_SELECT_K(4);
+    if (k == 6) UPP_SELECT(6, 1);
+    else if (k == 8) UPP_SELECT(8, 1);
+    else if (k == 16) UPP_SELECT(16, 1);
+    else if (tpt == 4) UPP_SELECT_K(4);
     else if (tpt == 2) UPP_SELECT_K(2);
     else UPP_SELECT_K(1);
 #undef UPP_SELECT_K
@@ -999,11 +1014,13 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   int rc = launch_status();
   if (rc != UPP_OK || !two_phase) return rc;
 
-  const int chunks = C / kBlendCh;
+  const int chunks = C >= kBlendCh ? C / kBlendCh : 1;
+  const int chw = min(C, kBlendCh);  // channels of a staged row
   const char* wv = getenv("UPP_BLEND_WARPS");  // tuning aid: 8 or 16 warps per CTA
   const int nwb = (wv && atoi(wv) == 8) ? 8 : 16;
-  const int kk = (k == 3 || k == 4 || k == 8) ? k : 0;  // the instantiated neighbour counts; 0 = run-time loop
-  const size_t bsmem = static_cast<size_t>(S) * kBlendCh * sizeof(float) + static_cast<size_t>(nwb) * blend_tw(kk) * k * 8;
+  const int kk = (k == 3 || k == 4 || k == 8 || k == 16) ? k : 0;  // the instantiated neighbour counts; 0 = run-time loop
+  const size_t bsmem = ((static_cast<size_t>(S) * chw * sizeof(float) + 15) & ~static_cast<size_t>(15)) +
+                       static_cast<size_t>(nwb) * blend_tw(kk) * k * 8;
   const char* sv2 = getenv("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
   const int spans = sv2 ? max(1, atoi(sv2)) : blend_pick_spans(static_cast<long>(chunks) * B, N);
   const int span = ((N + spans - 1) / spans + 1) & ~1;  // whole pairs of targets (a warp blends two per trip)
@@ -1022,6 +1039,7 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
     if (k == 3) UPP_BLEND(3, W_);    \
     else if (k == 4) UPP_BLEND(4, W_); \
     else if (k == 8) UPP_BLEND(8, W_); \
+    else if (k == 16) UPP_BLEND(16, W_); \
     else UPP_BLEND(0, W_);           \
   } while (0)
   if (nwb == 8) UPP_BLEND_K(8);

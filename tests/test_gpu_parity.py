@@ -586,6 +586,8 @@ WIDE_SHAPES = [  # shapes the wide-feature kernels accept: C a multiple of 128, 
     (2, 333, 150, 256, 5),    # ragged target count, S > 128 (blend only; the streamed backward declines)
     (1, 130, 128, 128, 8),    # one channel chunk, S and k at the streamed backward's limits, N % 64 != 0
     (2, 17, 5, 128, 1),
+    (2, 1096, 32, 96, 16),    # rectify-prompter propagation: narrow rows (one 96-channel chunk), thread-per-target k = 16
+    (2, 300, 40, 64, 6), (3, 70, 20, 4, 2), (2, 260, 128, 100, 8),
 ]
 
 
@@ -637,7 +639,7 @@ def test_interp_backward_streamed_matches_source_side_kernel(U, O, dev, monkeypa
         res[path, "feat"] = U.ops.interp_backward(go.to(dev), idx, w, S, alpha=alpha)
         n1 = U.launch_count()
         res[path, "xyz"] = U.ops.interp_backward(go.to(dev), idx, w, S, alpha=alpha, xyz_terms=terms)
-        streamed = path == "1" and S <= 128 and k <= 8
+        streamed = path == "1" and S <= 128 and k <= 8 and C % 128 == 0
         assert n1 - n0 == (2 if streamed else 1) and U.launch_count() - n1 == (4 if streamed else 2)  # target, csr, xyz2, stream
     ref, new = res["0", "feat"][0], res["1", "feat"][0]
     if C > 1024:
