@@ -687,7 +687,8 @@ constexpr int kBsTile = 64;                 // targets per streamed tile
 constexpr int kBsSrc = 128;                 // sources covered: 8 warps x 16 register accumulators
 constexpr int kBsWarps = 8;                 // consumer warps (+ 1 producer warp)
 constexpr int kBsStages = 3;
-constexpr int kBsMaxK = 8;                  // entries per tile kBsTile * k <= 512
+constexpr int kBsMaxK = 8;                  // streamed kernel: entries per tile kBsTile * k <= 512
+constexpr int kBsMaxKNarrow = 16;           // CSR gather kernel (C <= 128): entries per tile <= 1024
 constexpr unsigned kBsOffBytes = 272;       // 129 uint16 offsets, padded to a multiple of 16 B
 constexpr unsigned kBsRowBytes = kBlendCh * 4;
 constexpr unsigned kBsStagePad = 16;         // the entry prefetch reads one slot past the last entry
@@ -708,6 +709,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // One warp per (cloud, tile): block = [uint16 off[129] (pad)][entries sorted by (source, list position)],
 // entry = {byte offset of the target's row inside the staged tile, weight bits}.
+template <int kRounds>  // 32-entry rounds held in registers: 16 for k <= 8, 32 for k <= 16
 __global__ void __launch_bounds__(256)
     interp_csr_kernel(const int32_t* __restrict__ idx, const float* __restrict__ weight, int B, int N, int k,
                       int tiles, unsigned char* __restrict__ csr) {
@@ -724,7 +726,6 @@ __global__ void __launch_bounds__(256)
   const int E = nt * k;
   const size_t p0 = (static_cast<size_t>(b) * N + static_cast<size_t>(tile) * kBsTile) * k;
   // the tile's whole list in registers first (one exposed memory latency instead of one per round)
-  constexpr int kRounds = kBsTile * kBsMaxK / 32;
   int si[kRounds];
   float sw[kRounds];
 #pragma unroll
@@ -872,6 +873,68 @@ __global__ void __launch_bounds__((kBsWarps + 1) * kWarp)
       o.y = mul2(A2, acc[i][1]);
       *reinterpret_cast<ulonglong2*>(gfeat2 + (static_cast<size_t>(b) * S + s) * C + chunk * kBlendCh + lane * 4) = o;
     }
+  }
+}
+
+// Feature gradient for NARROW features (C <= 128, k <= 16; the rectify-prompter propagation 1096 <- 32 sources, 96
+// channels, k = 16) from the same CSR: a CTA per (cloud, source), warp w walks tiles w, w + NWG, ... and adds
+// weight * grad_out row (one float4 per lane, up to four rows in flight) for the source's entries of each tile in
+// list order; the NWG partial rows are combined through shared memory in warp order.  No list scan (the source-side
+// kernel compacts the cloud's N * k entries once per source: 116 us at that shape), deterministic, no atomics.
+constexpr int kGatherWarps = 8;
+
+__global__ void __launch_bounds__(kGatherWarps * kWarp)
+    interp_bwd_gather_csr_kernel(const float* __restrict__ gout, const unsigned char* __restrict__ csr, float alpha, int N,
+                                 int S, int C, int k, int tiles, float* __restrict__ gfeat2) {
+  __shared__ float4 s_part[kGatherWarps][kWarp];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.x, b = blockIdx.y;
+  const bool lane_on = lane * 4 < C;
+  const unsigned stride = bs_block_bytes(k);
+  const float* gb = gout + static_cast<size_t>(b) * N * C + lane * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = warp; t < tiles; t += kGatherWarps) {
+    const unsigned char* blk = csr + (static_cast<size_t>(b) * tiles + t) * stride;
+    const uint16_t* off = reinterpret_cast<const uint16_t*>(blk);
+    const uint2* ent = reinterpret_cast<const uint2*>(blk + kBsOffBytes);
+    const int beg = off[s], end = off[s + 1];
+    for (int m0 = beg; m0 < end; m0 += 4) {
+      float w[4];
+      float4 g[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int m = m0 + v;
+        const uint2 e = m < end ? ent[m] : make_uint2(0u, 0u);  // weight 0 past the end: adds +0 to the row of target 0
+        w[v] = __uint_as_float(e.y);
+        const int n = t * kBsTile + static_cast<int>(e.x / kBsRowBytes);
+        g[v] = (lane_on && m < end) ? __ldg(reinterpret_cast<const float4*>(gb + static_cast<size_t>(n) * C))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (m0 + v < end) {  // warp-uniform
+          acc.x = __fmaf_rn(w[v], g[v].x, acc.x);
+          acc.y = __fmaf_rn(w[v], g[v].y, acc.y);
+          acc.z = __fmaf_rn(w[v], g[v].z, acc.z);
+          acc.w = __fmaf_rn(w[v], g[v].w, acc.w);
+        }
+      }
+    }
+  }
+  s_part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && lane_on) {
+    float4 tot = s_part[0][lane];
+    for (int wi = 1; wi < kGatherWarps; ++wi) {
+      const float4 p = s_part[wi][lane];
+      tot.x += p.x; tot.y += p.y; tot.z += p.z; tot.w += p.w;
+    }
+    float4 o;
+    o.x = __fmul_rn(alpha, tot.x);
+    o.y = __fmul_rn(alpha, tot.y);
+    o.z = __fmul_rn(alpha, tot.z);
+    o.w = __fmul_rn(alpha, tot.w);
+    *reinterpret_cast<float4*>(gfeat2 + (static_cast<size_t>(b) * S + s) * C + lane * 4) = o;
   }
 }
 
@@ -1052,7 +1115,10 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
 
 // Workspace of the streamed backward (one CSR block per cloud and 64-target tile); 0 when the shape has no such path.
 size_t interp_bwd_workspace_bytes(int B, int N, int S, int C, int k) {
-  if (B <= 0 || N <= 0 || C <= 0 || C % kBlendCh != 0 || S > kBsSrc || k > kBsMaxK || B > 65535) return 0;
+  if (B <= 0 || N <= 0 || C <= 0 || S > kBsSrc || B > 65535) return 0;
+  const bool wide = C % kBlendCh == 0 && k <= kBsMaxK;                     // streamed kernel
+  const bool narrow = C <= kBlendCh && C % 4 == 0 && k <= kBsMaxKNarrow;   // CSR gather kernel
+  if (!wide && !narrow) return 0;
   const size_t tiles = (static_cast<size_t>(N) + kBsTile - 1) / kBsTile;
   return static_cast<size_t>(B) * tiles * bs_block_bytes(k);
 }
@@ -1081,14 +1147,19 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
   // gradient is read off the same CSR (interp_bwd_xyz2_kernel); the source-side kernel is not launched at all
   const int env = interp_path_env();
   const size_t need = interp_bwd_workspace_bytes(B, N, S, C, k);
-  const bool stream_ok = need > 0 && ws != nullptr && ws_bytes >= need && aligned16(gout, gfeat2, ws);
+  const bool csr_ok = need > 0 && ws != nullptr && ws_bytes >= need && aligned16(gout, gfeat2, ws);
+  const bool wide = C % kBlendCh == 0 && k <= kBsMaxK;
   const bool stream_big = static_cast<long>(C / kBlendCh) * B >= 120 && N >= 512;
-  bool streamed = stream_ok && (env == 1 || (env < 0 && stream_big));
+  bool streamed = csr_ok && wide && (env == 1 || (env < 0 && stream_big));
+  // narrow features (one chunk of <= 128 channels): gather from the CSR, no streaming pipeline
+  const bool gather_big = static_cast<long>(N) * k >= 4096;
+  const bool gathered = csr_ok && !streamed && C <= kBlendCh && C % 4 == 0 && k <= kBsMaxKNarrow &&
+                        (env == 1 || (env < 0 && gather_big));
   CUtensorMap gmap;  // grad_out as (B*N rows) x C, box = 64 rows x 128 channels
   if (streamed && make_tmap_2d_f32(&gmap, gout, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * N,
                                    static_cast<uint64_t>(C) * sizeof(float), kBlendCh, kBsTile) != UPP_OK)
     streamed = false;  // no tensor-map encoder in this driver: the source-side kernel serves every shape
-  if (!streamed) {
+  if (!streamed && !gathered) {
     dim3 grid(S, B);
     const float* gdp = want_xyz ? gd_ws : nullptr;
     float* g2p = want_xyz ? gxyz2 : nullptr;
@@ -1104,8 +1175,12 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
   }
   const int tiles = (N + kBsTile - 1) / kBsTile;
   const long warps = static_cast<long>(B) * tiles;
-  interp_csr_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>(idx, weight, B, N, k, tiles,
-                                                                            static_cast<unsigned char*>(ws));
+  if (k <= kBsMaxK)
+    interp_csr_kernel<kBsTile * kBsMaxK / 32><<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>(
+        idx, weight, B, N, k, tiles, static_cast<unsigned char*>(ws));
+  else
+    interp_csr_kernel<kBsTile * kBsMaxKNarrow / 32><<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>(
+        idx, weight, B, N, k, tiles, static_cast<unsigned char*>(ws));
   count_launch();
   int rc = launch_status();
   if (rc != UPP_OK) return rc;
@@ -1116,6 +1191,12 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
     count_launch();
     rc = launch_status();
     if (rc != UPP_OK) return rc;
+  }
+  if (gathered) {
+    interp_bwd_gather_csr_kernel<<<dim3(S, B), kGatherWarps * kWarp, 0, st>>>(gout, static_cast<const unsigned char*>(ws),
+                                                                              alpha, N, S, C, k, tiles, gfeat2);
+    count_launch();
+    return launch_status();
   }
   const size_t ssmem = static_cast<size_t>(kBsStages) * bs_stage_bytes(k);
   cudaError_t e = cudaFuncSetAttribute(interp_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

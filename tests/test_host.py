@@ -58,7 +58,8 @@ def test_cabi_argument_validation_without_gpu(lib):
     # streamed interpolation backward: one CSR block (272 + 64*k*9 bytes) per cloud and 64-target tile; 0 = no such path
     assert lib.upp_interp_bwd_workspace_bytes(32, 2048, 128, 1152, 3) == 32 * 32 * (272 + 64 * 3 * 9)
     assert lib.upp_interp_bwd_workspace_bytes(2, 130, 128, 128, 8) == 2 * 3 * (272 + 64 * 8 * 9)
-    for shape in ((2, 100, 129, 128, 3), (2, 100, 64, 96, 3), (2, 100, 64, 128, 9), (0, 100, 64, 128, 3)):
+    assert lib.upp_interp_bwd_workspace_bytes(2, 100, 64, 96, 16) == 2 * 2 * (272 + 64 * 16 * 9)   # narrow rows: k up to 16
+    for shape in ((2, 100, 129, 128, 3), (2, 100, 64, 98, 3), (2, 100, 64, 256, 9), (2, 100, 64, 96, 17), (0, 100, 64, 128, 3)):
         assert lib.upp_interp_bwd_workspace_bytes(*shape) == 0
     assert lib.upp_interp_bwd_f32(None, None, None, None, None, None, None, 1.0, 1e-4, 2, 8, 4, 16, 3,
                                   None, None, None, None, None, 0, None) == -1   # null pointers
