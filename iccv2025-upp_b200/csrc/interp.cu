@@ -938,6 +938,121 @@ __global__ void __launch_bounds__(kGatherWarps * kWarp)
   }
 }
 
+// Feature gradient for SMALL source blocks (S * C <= 3072 floats, C <= 128: the rectify-prompter propagation, 32
+// sources x 96 channels): grad_out is read ONCE and no sort is needed.  A CTA takes a span of one cloud's targets;
+// every warp keeps a private copy of all S accumulator rows in shared memory (12 KB each) and walks its targets in
+// order: one coalesced row load (a float4 per lane), then k shared-memory read-modify-writes acc[idx_j] += w_j * row
+// (the k sources of a target are distinct, and a warp owns its copy: no conflicts, no atomics).  The 8 copies are
+// combined in warp order into a per-CTA partial; interp_bwd_acc_combine_kernel adds the partials of a cloud in span
+// order and applies alpha.  Fixed assignment + fixed order: deterministic.
+constexpr int kAccWarps = 8;
+constexpr int kAccMaxFloats = 3072;  // S * C per accumulator copy: 8 copies = 96 KB, two CTAs per SM
+
+// spans per cloud: about two CTAs per SM, at least 64 targets each
+__host__ inline int acc_spans(int B, int N) {
+  int sp = 2 * 148 / B;  // every CTA resident at once (a second, nearly empty wave would double the time)
+  const int smax = (N + 63) / 64;
+  sp = sp > smax ? smax : sp;
+  return sp < 1 ? 1 : sp;
+}
+
+__global__ void __launch_bounds__(kAccWarps * kWarp)
+    interp_bwd_acc_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx, const float* __restrict__ weight,
+                          int N, int S, int C, int k, int span, float* __restrict__ partial) {
+  extern __shared__ __align__(16) float s_acc[];  // kAccWarps x S * C
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * span, n1 = min(N, n0 + span);
+  const int SC = S * C;
+  for (int f = t * 4; f < kAccWarps * SC; f += kAccWarps * kWarp * 4)
+    *reinterpret_cast<float4*>(s_acc + f) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const bool lane_on = lane * 4 < C;
+  float* acc = s_acc + warp * SC + lane * 4;
+  const float* gb = gout + static_cast<size_t>(b) * N * C + lane * 4;
+  // the next target's selection and row are in flight while this one is accumulated
+  int ni = 0;
+  float nw = 0.f;
+  float4 ng = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](int n) {
+    if (n < n1) {
+      const size_t row = static_cast<size_t>(b) * N + n;
+      if (lane < k) {
+        ni = __ldg(idx + row * k + lane);
+        nw = __ldg(weight + row * k + lane);
+      }
+      if (lane_on) ng = __ldg(reinterpret_cast<const float4*>(gb + static_cast<size_t>(n) * C));
+    }
+  };
+  fetch(n0 + warp);
+  for (int n = n0 + warp; n < n1; n += kAccWarps) {
+    const int ci = ni;
+    const float cw = nw;
+    const float4 g = ng;
+    fetch(n + kAccWarps);
+    // four neighbours at a time: their rows are DISTINCT (a target's k sources are), so the four read-modify-writes
+    // are independent -- loads first, then the stores (one at a time they serialise on possible aliasing)
+    for (int j0 = 0; j0 < k; j0 += 4) {
+      int sj[4];
+      float wj[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        sj[v] = __shfl_sync(0xffffffffu, ci, (j0 + v) & 31);
+        wj[v] = __shfl_sync(0xffffffffu, cw, (j0 + v) & 31);
+      }
+      if (lane_on) {
+        float4 r[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (j0 + v < k) r[v] = *reinterpret_cast<const float4*>(acc + sj[v] * C);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (j0 + v < k) {
+            r[v].x = __fmaf_rn(wj[v], g.x, r[v].x);
+            r[v].y = __fmaf_rn(wj[v], g.y, r[v].y);
+            r[v].z = __fmaf_rn(wj[v], g.z, r[v].z);
+            r[v].w = __fmaf_rn(wj[v], g.w, r[v].w);
+          }
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (j0 + v < k) *reinterpret_cast<float4*>(acc + sj[v] * C) = r[v];
+      }
+    }
+  }
+  __syncthreads();
+  float* out = partial + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * SC;
+  for (int f = t * 4; f < SC; f += kAccWarps * kWarp * 4) {
+    float4 tot = *reinterpret_cast<const float4*>(s_acc + f);
+#pragma unroll
+    for (int w = 1; w < kAccWarps; ++w) {
+      const float4 p = *reinterpret_cast<const float4*>(s_acc + w * SC + f);
+      tot.x += p.x; tot.y += p.y; tot.z += p.z; tot.w += p.w;
+    }
+    *reinterpret_cast<float4*>(out + f) = tot;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    interp_bwd_acc_combine_kernel(const float* __restrict__ partial, float alpha, int SC, int spans,
+                                  float* __restrict__ gfeat2) {
+  const int b = blockIdx.y;
+  const int f = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (f >= SC) return;
+  const float* p = partial + static_cast<size_t>(b) * spans * SC + f;
+  float4 tot = *reinterpret_cast<const float4*>(p);
+  for (int sp = 1; sp < spans; ++sp) {
+    const float4 q = *reinterpret_cast<const float4*>(p + static_cast<size_t>(sp) * SC);
+    tot.x += q.x; tot.y += q.y; tot.z += q.z; tot.w += q.w;
+  }
+  float4 o;
+  o.x = __fmul_rn(alpha, tot.x);
+  o.y = __fmul_rn(alpha, tot.y);
+  o.z = __fmul_rn(alpha, tot.z);
+  o.w = __fmul_rn(alpha, tot.w);
+  *reinterpret_cast<float4*>(gfeat2 + static_cast<size_t>(b) * SC + f) = o;
+}
+
 // Coordinate gradient of the sources from the CSR (replaces the source-side kernel's list scan when the streamed
 // path runs): one warp per (cloud, source), lane l takes tiles l, l + 32, ...; per match
 //   grad_xyz2[b,s] += -2 * gd[p] * (x1[n] - x2[s])        (d/dx2 of -2 x1.x2 + |x1|^2 + |x2|^2 is -2 (x1 - x2))
@@ -1114,13 +1229,24 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
 }
 
 // Workspace of the streamed backward (one CSR block per cloud and 64-target tile); 0 when the shape has no such path.
-size_t interp_bwd_workspace_bytes(int B, int N, int S, int C, int k) {
+// [CSR blocks][per-span partial sums of the small-source-block kernel]; either part may be absent
+static size_t interp_bwd_csr_bytes(int B, int N, int S, int C, int k) {
   if (B <= 0 || N <= 0 || C <= 0 || S > kBsSrc || B > 65535) return 0;
   const bool wide = C % kBlendCh == 0 && k <= kBsMaxK;                     // streamed kernel
-  const bool narrow = C <= kBlendCh && C % 4 == 0 && k <= kBsMaxKNarrow;   // CSR gather kernel
+  const bool narrow = C <= kBlendCh && C % 4 == 0 && k <= kBsMaxKNarrow;   // CSR gather kernel / coordinate terms
   if (!wide && !narrow) return 0;
   const size_t tiles = (static_cast<size_t>(N) + kBsTile - 1) / kBsTile;
-  return static_cast<size_t>(B) * tiles * bs_block_bytes(k);
+  return (static_cast<size_t>(B) * tiles * bs_block_bytes(k) + 255) & ~static_cast<size_t>(255);
+}
+static bool interp_bwd_acc_shape(int B, int N, int S, int C, int k) {
+  return B > 0 && B <= 65535 && N > 0 && S > 0 && C > 0 && C <= kBlendCh && C % 4 == 0 && k <= 32 &&
+         static_cast<long>(S) * C <= kAccMaxFloats;
+}
+size_t interp_bwd_workspace_bytes(int B, int N, int S, int C, int k) {
+  size_t bytes = interp_bwd_csr_bytes(B, N, S, C, k);
+  if (interp_bwd_acc_shape(B, N, S, C, k))
+    bytes += static_cast<size_t>(B) * acc_spans(B, N) * S * C * sizeof(float);
+  return bytes;
 }
 
 int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight, const float* distk,
@@ -1147,19 +1273,46 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
   // gradient is read off the same CSR (interp_bwd_xyz2_kernel); the source-side kernel is not launched at all
   const int env = interp_path_env();
   const size_t need = interp_bwd_workspace_bytes(B, N, S, C, k);
-  const bool csr_ok = need > 0 && ws != nullptr && ws_bytes >= need && aligned16(gout, gfeat2, ws);
+  const size_t csr_bytes = interp_bwd_csr_bytes(B, N, S, C, k);
+  const bool ws_ok = need > 0 && ws != nullptr && ws_bytes >= need && aligned16(gout, gfeat2, ws);
+  const bool csr_ok = ws_ok && csr_bytes > 0;
   const bool wide = C % kBlendCh == 0 && k <= kBsMaxK;
   const bool stream_big = static_cast<long>(C / kBlendCh) * B >= 120 && N >= 512;
   bool streamed = csr_ok && wide && (env == 1 || (env < 0 && stream_big));
   // narrow features (one chunk of <= 128 channels): gather from the CSR, no streaming pipeline
   const bool gather_big = static_cast<long>(N) * k >= 4096;
-  const bool gathered = csr_ok && !streamed && C <= kBlendCh && C % 4 == 0 && k <= kBsMaxKNarrow &&
+  // small source blocks: per-warp accumulator copies in shared memory, grad_out read once (coordinate terms still
+  // come off the CSR, so with them the CSR must exist too)
+  const bool accumulated = ws_ok && !streamed && interp_bwd_acc_shape(B, N, S, C, k) && (!want_xyz || csr_ok) &&
+                           (env == 1 || (env < 0 && gather_big));
+  const bool gathered = csr_ok && !streamed && !accumulated && C <= kBlendCh && C % 4 == 0 && k <= kBsMaxKNarrow &&
                         (env == 1 || (env < 0 && gather_big));
   CUtensorMap gmap;  // grad_out as (B*N rows) x C, box = 64 rows x 128 channels
   if (streamed && make_tmap_2d_f32(&gmap, gout, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * N,
                                    static_cast<uint64_t>(C) * sizeof(float), kBlendCh, kBsTile) != UPP_OK)
     streamed = false;  // no tensor-map encoder in this driver: the source-side kernel serves every shape
-  if (!streamed && !gathered) {
+  if (accumulated) {
+    const int spans = acc_spans(B, N);
+    const int span = (N + spans - 1) / spans;
+    const size_t asmem = static_cast<size_t>(kAccWarps) * S * C * sizeof(float);
+    float* partial = reinterpret_cast<float*>(static_cast<unsigned char*>(ws) + csr_bytes);
+    if (asmem > 40 * 1024) {
+      cudaError_t ae = cudaFuncSetAttribute(interp_bwd_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(asmem));
+      if (ae != cudaSuccess) return static_cast<int>(ae);
+    }
+    interp_bwd_acc_kernel<<<dim3((N + span - 1) / span, B), kAccWarps * kWarp, asmem, st>>>(gout, idx, weight, N, S, C, k,
+                                                                                           span, partial);
+    count_launch();
+    int arc = launch_status();
+    if (arc != UPP_OK) return arc;
+    interp_bwd_acc_combine_kernel<<<dim3((S * C / 4 + 255) / 256, B), 256, 0, st>>>(partial, alpha, S * C,
+                                                                                     (N + span - 1) / span, gfeat2);
+    count_launch();
+    arc = launch_status();
+    if (arc != UPP_OK || !want_xyz) return arc;
+  }
+  if (!streamed && !gathered && !accumulated) {
     dim3 grid(S, B);
     const float* gdp = want_xyz ? gd_ws : nullptr;
     float* g2p = want_xyz ? gxyz2 : nullptr;
@@ -1192,6 +1345,7 @@ int interp_bwd_launch(const float* gout, const int32_t* idx, const float* weight
     rc = launch_status();
     if (rc != UPP_OK) return rc;
   }
+  if (accumulated) return UPP_OK;  // (coordinate terms only: the features were done above)
   if (gathered) {
     interp_bwd_gather_csr_kernel<<<dim3(S, B), kGatherWarps * kWarp, 0, st>>>(gout, static_cast<const unsigned char*>(ws),
                                                                               alpha, N, S, C, k, tiles, gfeat2);

@@ -55,10 +55,15 @@ def test_cabi_argument_validation_without_gpu(lib):
     assert lib.upp_gather_f32(None, None, 2, 3, 8, 4, None, None) == -1
     assert lib.upp_fps_workspace_bytes(32, 1024, 64) == 0          # register-resident: no scratch
     assert lib.upp_fps_workspace_bytes(4, 10000, 64) == 4 * 10000 * 4
-    # streamed interpolation backward: one CSR block (272 + 64*k*9 bytes) per cloud and 64-target tile; 0 = no such path
-    assert lib.upp_interp_bwd_workspace_bytes(32, 2048, 128, 1152, 3) == 32 * 32 * (272 + 64 * 3 * 9)
-    assert lib.upp_interp_bwd_workspace_bytes(2, 130, 128, 128, 8) == 2 * 3 * (272 + 64 * 8 * 9)
-    assert lib.upp_interp_bwd_workspace_bytes(2, 100, 64, 96, 16) == 2 * 2 * (272 + 64 * 16 * 9)   # narrow rows: k up to 16
+    # interpolation backward scratch: [CSR: one block (272 + 64*k*9 bytes) per cloud and 64-target tile, rounded to 256 B]
+    # [+ per-span partial sums (B * spans * S * C floats) when the source block is small (S*C <= 3072, C <= 128)]; 0 = neither
+    r256 = lambda v: (v + 255) // 256 * 256  # noqa: E731
+    assert lib.upp_interp_bwd_workspace_bytes(32, 2048, 128, 1152, 3) == r256(32 * 32 * (272 + 64 * 3 * 9))
+    assert lib.upp_interp_bwd_workspace_bytes(2, 130, 128, 128, 8) == r256(2 * 3 * (272 + 64 * 8 * 9))
+    assert lib.upp_interp_bwd_workspace_bytes(2, 100, 64, 96, 16) == r256(2 * 2 * (272 + 64 * 16 * 9))   # narrow rows: k up to 16
+    spans = max(1, min(2 * 148 // 32, (1096 + 63) // 64))                                               # <= 2 CTAs per SM, all resident
+    assert lib.upp_interp_bwd_workspace_bytes(32, 1096, 32, 96, 16) == r256(32 * 18 * (272 + 64 * 16 * 9)) + 32 * spans * 32 * 96 * 4
+    assert lib.upp_interp_bwd_workspace_bytes(2, 100, 16, 96, 20) == 2 * 2 * 16 * 96 * 4                 # k > 16: partial sums only
     for shape in ((2, 100, 129, 128, 3), (2, 100, 64, 98, 3), (2, 100, 64, 256, 9), (2, 100, 64, 96, 17), (0, 100, 64, 128, 3)):
         assert lib.upp_interp_bwd_workspace_bytes(*shape) == 0
     assert lib.upp_interp_bwd_f32(None, None, None, None, None, None, None, 1.0, 1e-4, 2, 8, 4, 16, 3,
