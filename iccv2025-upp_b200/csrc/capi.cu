@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" surface of libupp_geom.so (include/upp_geom.h): argument checks and
 // dispatch only.  No allocation, no host synchronisation, no state besides the launch counter.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -46,6 +47,16 @@ int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t inner, uint64
   return r == CUDA_SUCCESS ? UPP_OK : UPP_ERR_INVALID_ARG;
 }
 
+const char* tuning_env(const char* name) {
+  const char* on = getenv("UPP_TUNING");
+  if (on == nullptr || on[0] != '1' || on[1] != '\0') return nullptr;
+  return getenv(name);
+}
+int tuning_env_int(const char* name, int dflt) {
+  const char* s = tuning_env(name);
+  return s ? atoi(s) : dflt;
+}
+
 void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
 
 int fps_launch(const float*, int, int, int, int32_t*, float*, void*, size_t, cudaStream_t);
@@ -56,7 +67,10 @@ int chamfer_fwd_launch(const float*, const float*, int, int, int, float*, float*
 size_t chamfer_fwd_workspace_bytes(int, int, int);
 int peer_finish_launch(const upp_peer_exchange*, float*, cudaStream_t);
 int chamfer_bwd_launch(const float*, const float*, const int32_t*, const int32_t*, const float*,
-                       const float*, int, int, int, float*, float*, cudaStream_t);
+                       const float*, int, int, int, float*, float*, float*, void*, size_t, const upp_peer_exchange*,
+                       cudaStream_t);
+size_t chamfer_bwd_stats_workspace_bytes(int, int, int);
+int peer_allreduce_launch(const upp_peer_exchange*, const float*, float*, cudaStream_t);
 int gather_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int gather_grad_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int group_gather_launch(const float*, const float*, const int64_t*, int, int, int, int, float*,
@@ -64,6 +78,7 @@ int group_gather_launch(const float*, const float*, const int64_t*, int, int, in
 int rows_scatter_add_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int group_bwd_launch(const float*, const float*, const int64_t*, const int32_t*, int, int, int, int,
                      float*, cudaStream_t);
+int group_fused_launch(const float*, int, int, int, int, float*, float*, int64_t*, int32_t*, cudaStream_t);
 
 int knn_points_launch(const float*, const float*, int, int, int, int, float*, int64_t*, float*, cudaStream_t);
 int interp_fwd_launch(const float*, const float*, const float*, const float*, float, float, int, int, int, int,
@@ -173,11 +188,16 @@ int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int N, int 
 int upp_chamfer_fwd_sharded_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                                 float* dist2, int32_t* idx1, int32_t* idx2, float* global_sums, void* workspace,
                                 size_t workspace_bytes, const upp_peer_exchange* peers, upp_stream_t stream) {
-  UPP_REQUIRE(B >= 1 && N >= 1 && M >= 1);  // every rank must contribute to the exchange: no empty shards
-  UPP_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2 && global_sums && peers);
+  UPP_REQUIRE(B >= 0 && N >= 1 && M >= 1);
+  UPP_REQUIRE(global_sums && peers);
   UPP_REQUIRE(peers->world >= 1 && peers->world <= UPP_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world);
   UPP_REQUIRE(peers->world == 1 || peers->seq != nullptr);
   for (int r = 0; r < peers->world && peers->world > 1; ++r) UPP_REQUIRE(peers->slots[r] != nullptr);
+  if (B == 0) {  // an empty shard still takes part in the exchange (zeros), so the ranks' call sequences stay aligned
+    if (peers->world == 1) return static_cast<int>(cudaMemsetAsync(global_sums, 0, 16, S(stream)));
+    return peer_allreduce_launch(peers, nullptr, global_sums, S(stream));
+  }
+  UPP_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2);
   return chamfer_fwd_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, global_sums, workspace, workspace_bytes,
                             peers, S(stream));
 }
@@ -205,7 +225,43 @@ int upp_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* idx
   }
   UPP_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && grad_dist1 && grad_dist2);
   return chamfer_bwd_launch(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, B, N, M, grad_xyz1,
-                            grad_xyz2, S(stream));
+                            grad_xyz2, nullptr, nullptr, 0, nullptr, S(stream));
+}
+
+size_t upp_chamfer_bwd_stats_workspace_bytes(int B, int N, int M) { return chamfer_bwd_stats_workspace_bytes(B, N, M); }
+
+int upp_chamfer_bwd_stats_f32(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
+                              const float* grad_dist1, const float* grad_dist2, int B, int N, int M,
+                              float* grad_xyz1, float* grad_xyz2, float* sqnorm_out, void* workspace,
+                              size_t workspace_bytes, const upp_peer_exchange* peers, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && sqnorm_out != nullptr);
+  if (peers != nullptr) {
+    UPP_REQUIRE(peers->world >= 1 && peers->world <= UPP_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world);
+    UPP_REQUIRE(peers->world == 1 || peers->seq != nullptr);
+    for (int r = 0; r < peers->world && peers->world > 1; ++r) UPP_REQUIRE(peers->slots[r] != nullptr);
+  }
+  const size_t n1 = static_cast<size_t>(B) * N, n2 = static_cast<size_t>(B) * M;
+  UPP_REQUIRE(n1 == 0 || grad_xyz1);
+  UPP_REQUIRE(n2 == 0 || grad_xyz2);
+  if (N == 0 || M == 0 || B == 0) {  // no pairs: zero gradients, zero statistics -- but still one exchange when sharded
+    cudaError_t e = cudaSuccess;
+    if (n1) e = cudaMemsetAsync(grad_xyz1, 0, n1 * 12, S(stream));
+    if (n2 && e == cudaSuccess) e = cudaMemsetAsync(grad_xyz2, 0, n2 * 12, S(stream));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (peers != nullptr && peers->world > 1) return peer_allreduce_launch(peers, nullptr, sqnorm_out, S(stream));  // 4 floats
+    return static_cast<int>(cudaMemsetAsync(sqnorm_out, 0, 8, S(stream)));
+  }
+  UPP_REQUIRE(xyz1 && xyz2 && idx1 && idx2 && grad_dist1 && grad_dist2);
+  return chamfer_bwd_launch(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, B, N, M, grad_xyz1, grad_xyz2, sqnorm_out,
+                            workspace, workspace_bytes, peers, S(stream));
+}
+
+int upp_peer_allreduce_f32(const upp_peer_exchange* peers, const float* local4, float* global4, upp_stream_t stream) {
+  UPP_REQUIRE(peers && global4);
+  UPP_REQUIRE(peers->world >= 2 && peers->world <= UPP_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world);
+  UPP_REQUIRE(peers->seq != nullptr);
+  for (int r = 0; r < peers->world; ++r) UPP_REQUIRE(peers->slots[r] != nullptr);
+  return peer_allreduce_launch(peers, local4, global4, S(stream));
 }
 
 int upp_group_f32(const float* xyz, int B, int N, int G, int k, float* neighborhood, float* center,
@@ -215,7 +271,11 @@ int upp_group_f32(const float* xyz, int B, int N, int G, int k, float* neighborh
   UPP_REQUIRE(k >= 1 && k <= N);
   if (B == 0 || G == 0) return UPP_OK;
   UPP_REQUIRE(xyz && neighborhood && center && idx && center_idx);
-  int rc = fps_launch(xyz, B, N, G, center_idx, center, workspace, workspace_bytes, S(stream));
+  // one launch: the kNN of centre j runs behind the FPS chain that is still producing centres j+1... (group.cu)
+  int rc = group_fused_launch(xyz, B, N, G, k, neighborhood, center, idx, center_idx, S(stream));
+  if (rc == UPP_OK) return UPP_OK;
+  if (rc > 0) (void)cudaGetLastError();  // a cluster that cannot be placed: compose the two launches below
+  rc = fps_launch(xyz, B, N, G, center_idx, center, workspace, workspace_bytes, S(stream));
   if (rc != UPP_OK) return rc;
   // kNN with the fused epilogue: neighbourhood = xyz[idx] - center, no separate gather launch
   return knn_launch(xyz, center, B, N, G, k, nullptr, idx, neighborhood, S(stream));

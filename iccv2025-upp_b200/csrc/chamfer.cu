@@ -17,7 +17,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
-#include "common.cuh"
+#include "scatter.cuh"
 
 namespace upp {
 
@@ -468,13 +468,6 @@ __global__ void __launch_bounds__(256)
 // computes bit-identical global sums, deterministically, with no NCCL launch and no host involvement.
 // Two parities make slot reuse safe: rank r can only write call s+2 after it has finished call s+1, which needed
 // every peer's call-s+1 contribution, which a peer sends only after it has read call s.
-struct PeerXchg {
-  float* slots[UPP_MAX_PEERS];  // slots[r] = rank r's exchange buffer (device pointer valid in THIS process)
-  int rank, world;
-  unsigned* seq;                // this rank's call counter (device memory, zero before the first call)
-  int defer;                    // 1: only SEND here; peer_finish_kernel (a later launch) waits and adds
-};
-
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -482,6 +475,38 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+struct PeerXchg {
+  float* slots[UPP_MAX_PEERS];  // slots[r] = rank r's exchange buffer (device pointer valid in THIS process)
+  int rank, world;
+  unsigned* seq;                // this rank's call counter (device memory, zero before the first call)
+  int defer;                    // 1: only SEND here; peer_finish_kernel (a later launch) waits and adds
+  unsigned* status;             // nullable: receives the sequence number of a wait that timed out (host-visible memory)
+  long long timeout;            // SM clocks a wait may last (0: kPeerTimeoutDefault)
+};
+
+// A peer that is late is NORMAL under data-parallel training (rank-0 checkpointing or evaluation, a data-loader stall):
+// the wait is long (2^38 clocks, ~2.3 minutes at 1.965 GHz -- the order of NCCL's own watchdog, not of a kernel), and a
+// wait that does run out is REPORTED: the sums are poisoned with NaN and, when the caller gave a status word, the
+// sequence number of the failed call is stored there with system scope so that the host can raise (parallel.PeerExchange
+// .check()); nothing is skipped silently.
+constexpr long long kPeerTimeoutDefault = 1LL << 38;
+
+__device__ __forceinline__ bool peer_wait_tag(const float* src, unsigned seq, const PeerXchg& px) {
+  const long long limit = px.timeout > 0 ? px.timeout : kPeerTimeoutDefault;
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (ld_acquire_sys_u32(reinterpret_cast<const unsigned*>(src + 4)) != seq) {
+    if ((++spins & 1023u) == 0u && clock64() - t0 > limit) {
+      if (px.status != nullptr) {
+        *reinterpret_cast<volatile unsigned*>(px.status) = seq;
+        __threadfence_system();
+      }
+      return false;
+    }
+  }
+  return true;
 }
 
 // Called by ONE CTA (256 threads) after `local` (4 floats, thread 0's registers) is final.  Returns the global
@@ -509,12 +534,7 @@ __device__ __forceinline__ void peer_allreduce4(const PeerXchg& px, float (&v)[4
   if (t < px.world) {
     // receive: rank t's contribution from my own buffer
     const float* src = px.slots[px.rank] + ((seq & 1u) * px.world + t) * 8;
-    // bounded wait (~3 s of SM clocks): a peer that never arrives poisons the sums with NaN instead of hanging
-    const long long t0 = clock64();
-    bool ok = true;
-    while (ld_acquire_sys_u32(reinterpret_cast<const unsigned*>(src + 4)) != seq) {
-      if (clock64() - t0 > (6LL << 30)) { ok = false; break; }
-    }
+    const bool ok = peer_wait_tag(src, seq, px);  // long, reported wait (see kPeerTimeoutDefault)
     const volatile float* vs = src;  // after the acquire: the payload written before the tag
     const float nan = __int_as_float(0x7fc00000);
     s_x[1 + t][0] = ok ? vs[0] : nan; s_x[1 + t][1] = ok ? vs[1] : nan;
@@ -539,11 +559,7 @@ __global__ void __launch_bounds__(32) peer_finish_kernel(const PeerXchg px, floa
   const unsigned seq = *px.seq;
   for (int r = t; r < px.world; r += 32) {
     const float* src = px.slots[px.rank] + ((seq & 1u) * px.world + r) * 8;
-    const long long t0 = clock64();
-    bool ok = true;
-    while (ld_acquire_sys_u32(reinterpret_cast<const unsigned*>(src + 4)) != seq) {
-      if (clock64() - t0 > (6LL << 30)) { ok = false; break; }
-    }
+    const bool ok = peer_wait_tag(src, seq, px);
     const volatile float* vs = src;
     const float nan = __int_as_float(0x7fc00000);
 #pragma unroll
@@ -554,6 +570,24 @@ __global__ void __launch_bounds__(32) peer_finish_kernel(const PeerXchg px, floa
     float tot = 0.f;
     for (int r = 0; r < px.world; ++r) tot += s_v[r][t];
     global_sums[t] = tot;
+  }
+}
+
+// The exchange on its own: all-reduce (SUM, rank order) of 4 floats that are already in device memory -- an EMPTY shard's
+// contribution to a sharded Chamfer call (local == nullptr: zeros; every rank must take part in every exchange), or the
+// gradient statistics of chamfer_bwd_stats.  One CTA.
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(const PeerXchg px, const float* __restrict__ local,
+                                                             float* __restrict__ global_sums) {
+  __shared__ float s_x[1 + UPP_MAX_PEERS][4];
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (threadIdx.x == 0 && local != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = local[q];
+  }
+  peer_allreduce4(px, v, s_x);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) global_sums[q] = v[q];
   }
 }
 
@@ -743,53 +777,120 @@ __global__ void __cluster_dims__(kSumCluster, 1, 1) __launch_bounds__(kSumThread
   cluster.sync();  // keep every CTA's shared memory alive until CTA 0 has read it
 }
 
-// Backward pass 1: own term, plain stores.  grad_a[j] = 2 g[j] (a_j - b_idx[j]) for both clouds.
+// Backward: ONE launch, deterministic (ordered gather, scatter.cuh) -- no atomics, no memset.  blockIdx.z picks the
+// side; a lane owns destinations j of that side's cloud `self`:
+//   grad_self[j] = 2 g_self[j] (self_j - other[idx_self[j]])                      own term (chamfer.cu:186-191)
+//                - sum_{k : idx_other[k] == j} 2 g_other[k] (other_k - self_j)    partner terms (chamfer.cu:192-198),
+// the partner terms added in ascending k.  inf * 0 = NaN lands exactly where the reference's atomics put it (a row is
+// poisoned by its own term or by a partner that points at it, never by anything else).
+struct ChamferBwdOp {
+  const float* self;        // (B,Ns,3) this side's cloud
+  const float* other;       // (B,No,3)
+  const int32_t* idx_self;  // (B,Ns) nearest `other` point of every `self` point
+  const int32_t* idx_other; // (B,No) nearest `self` point of every `other` point: the scatter list
+  const float* g_self;      // (B,Ns)
+  const float* g_other;     // (B,No)
+  float* grad;              // (B,Ns,3)
+  int b, Ns, No;
+  __device__ __forceinline__ int entries() const { return No; }
+  __device__ __forceinline__ int dst(int e) const { return __ldg(idx_other + static_cast<size_t>(b) * No + e); }
+  __device__ __forceinline__ void fetch(int e, float (&v)[3]) const {
+    const size_t k = static_cast<size_t>(b) * No + e;
+    const float* o = other + k * 3;
+    const float* a = self + (static_cast<size_t>(b) * Ns + __ldg(idx_other + k)) * 3;
+    const float g = __fmul_rn(__ldg(g_other + k), 2.0f);
+    v[0] = -__fmul_rn(g, __ldg(o) - __ldg(a));
+    v[1] = -__fmul_rn(g, __ldg(o + 1) - __ldg(a + 1));
+    v[2] = -__fmul_rn(g, __ldg(o + 2) - __ldg(a + 2));
+  }
+  __device__ __forceinline__ void init(int j, float (&acc)[3]) const {
+    const size_t p = static_cast<size_t>(b) * Ns + j;
+    const float* a = self + p * 3;
+    const float* o = other + (static_cast<size_t>(b) * No + __ldg(idx_self + p)) * 3;
+    const float g = __fmul_rn(__ldg(g_self + p), 2.0f);
+    acc[0] = __fmul_rn(g, __ldg(a) - __ldg(o));
+    acc[1] = __fmul_rn(g, __ldg(a + 1) - __ldg(o + 1));
+    acc[2] = __fmul_rn(g, __ldg(a + 2) - __ldg(o + 2));
+  }
+  __device__ __forceinline__ void store(int j, const float (&acc)[3]) const {
+    float* out = grad + (static_cast<size_t>(b) * Ns + j) * 3;
+    out[0] = acc[0]; out[1] = acc[1]; out[2] = acc[2];
+  }
+};
+
 __global__ void __launch_bounds__(256)
-    chamfer_bwd_own_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
-                           const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2,
-                           const float* __restrict__ g1, const float* __restrict__ g2, int B, int N,
-                           int M, float* __restrict__ gx1, float* __restrict__ gx2) {
-  const size_t n1 = static_cast<size_t>(B) * N, n2 = static_cast<size_t>(B) * M;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n1 + n2;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const bool first = i < n1;
-    const size_t p = first ? i : i - n1;
-    const int na = first ? N : M, nb = first ? M : N;
-    const size_t b = p / na;
-    const float* a = (first ? xyz1 : xyz2) + p * 3;
-    const int j2 = (first ? idx1 : idx2)[p];
-    const float* o = (first ? xyz2 : xyz1) + (b * nb + j2) * 3;
-    const float g = __fmul_rn((first ? g1 : g2)[p], 2.0f);
-    float* out = (first ? gx1 : gx2) + p * 3;
-    out[0] = __fmul_rn(g, a[0] - o[0]);
-    out[1] = __fmul_rn(g, a[1] - o[1]);
-    out[2] = __fmul_rn(g, a[2] - o[2]);
+    chamfer_bwd_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                       const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2,
+                       const float* __restrict__ g1, const float* __restrict__ g2, int N, int M, int blocks1,
+                       float* __restrict__ gx1, float* __restrict__ gx2, float* __restrict__ sq_partials,
+                       unsigned* __restrict__ ticket, float* __restrict__ sq_out, const PeerXchg px) {
+  extern __shared__ int s_dst[];
+  const int b = blockIdx.y;
+  // blockIdx.x < blocks1: destinations are cloud 1's points; else cloud 2's (one grid, both sides)
+  const bool first = static_cast<int>(blockIdx.x) < blocks1;
+  float sq;
+  if (first) {
+    ChamferBwdOp op{xyz1, xyz2, idx1, idx2, g1, g2, gx1, b, N, M};
+    sq = ordered_scatter_cta<2>(op, N, s_dst);
+  } else {
+    ChamferBwdOp op{xyz2, xyz1, idx2, idx1, g2, g1, gx2, b, M, N};
+    sq = ordered_scatter_cta<2>(op, M, s_dst, blocks1);
+  }
+  if (sq_partials == nullptr) return;
+  // ---- gradient statistics: sum ||grad||^2 per side.  Fixed-shape block reduction -> one partial per CTA; the CTA that
+  //      draws the last ticket adds the partials in CTA order (deterministic whichever CTA that is), then -- batch sharded
+  //      over GPUs -- all-reduces the two sums over NVLink peer memory like the forward's loss sums. ----
+  __shared__ float s_w[8];
+  __shared__ bool s_last;
+  __shared__ float s_x[1 + UPP_MAX_PEERS][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  sq = warp_sum(sq);
+  if (lane == 0) s_w[warp] = sq;
+  __syncthreads();
+  const unsigned ncta = gridDim.x * gridDim.y;
+  const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < nwarps; ++w) tot += s_w[w];
+    sq_partials[cta] = tot;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) + 1u == ncta);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float loc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (threadIdx.x == 0) {  // a few thousand partials at most: one thread, index order
+    const volatile float* pp = sq_partials;
+    for (unsigned i = 0; i < ncta; ++i) loc[(i % gridDim.x) < static_cast<unsigned>(blocks1) ? 0 : 1] += pp[i];
+    *ticket = 0u;  // leave the ticket as it was found
+  }
+  if (px.world > 1) peer_allreduce4(px, loc, s_x);
+  if (threadIdx.x == 0) {
+    sq_out[0] = loc[0];
+    sq_out[1] = loc[1];
   }
 }
 
-// Backward pass 2: partner term, scattered with RED.ADD.F32.  grad_b[idx[j]] += -(2 g[j] (a_j - b_idx[j])).
-__global__ void __launch_bounds__(256)
-    chamfer_bwd_scatter_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
-                               const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2,
-                               const float* __restrict__ g1, const float* __restrict__ g2, int B,
-                               int N, int M, float* __restrict__ gx1, float* __restrict__ gx2) {
-  const size_t n1 = static_cast<size_t>(B) * N, n2 = static_cast<size_t>(B) * M;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n1 + n2;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const bool first = i < n1;
-    const size_t p = first ? i : i - n1;
-    const int na = first ? N : M, nb = first ? M : N;
-    const size_t b = p / na;
-    const float* a = (first ? xyz1 : xyz2) + p * 3;
-    const int j2 = (first ? idx1 : idx2)[p];
-    const size_t op = (b * nb + j2) * 3;
-    const float* o = (first ? xyz2 : xyz1) + op;
-    const float g = __fmul_rn((first ? g1 : g2)[p], 2.0f);
-    float* out = (first ? gx2 : gx1) + op;
-    atomicAdd(out + 0, -__fmul_rn(g, a[0] - o[0]));
-    atomicAdd(out + 1, -__fmul_rn(g, a[1] - o[1]));
-    atomicAdd(out + 2, -__fmul_rn(g, a[2] - o[2]));
+static PeerXchg make_px(const upp_peer_exchange* peers) {
+  PeerXchg px;
+  px.world = 1;
+  px.rank = 0;
+  px.seq = nullptr;
+  px.defer = 0;
+  px.status = nullptr;
+  px.timeout = 0;
+  for (int r = 0; r < UPP_MAX_PEERS; ++r) px.slots[r] = nullptr;
+  if (peers != nullptr && peers->world > 1) {
+    px.world = peers->world;
+    px.rank = peers->rank;
+    px.seq = peers->seq;
+    px.defer = peers->defer ? 1 : 0;
+    px.status = peers->status;
+    px.timeout = peers->timeout_cycles;
+    for (int r = 0; r < peers->world; ++r) px.slots[r] = peers->slots[r];
   }
+  return px;
 }
 
 template <int R, int THREADS>
@@ -883,27 +984,15 @@ static int launch_chamfer_both(const float* a, const float* bpts, int B, int NA,
 }
 
 static int env_chunks() {
-  const char* v = getenv("UPP_CH_CHUNKS");  // tuning aid: force the number of column chunks
+  const char* v = tuning_env("UPP_CH_CHUNKS");  // tuning aid: force the number of column chunks
   return v ? atoi(v) : 0;
 }
 
 int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                        float* dist2, int32_t* idx1, int32_t* idx2, float* sums, void* workspace,
                        size_t workspace_bytes, const upp_peer_exchange* peers, cudaStream_t st) {
-  PeerXchg px;
-  px.world = 1;
-  px.rank = 0;
-  px.seq = nullptr;
-  for (int r = 0; r < UPP_MAX_PEERS; ++r) px.slots[r] = nullptr;
-  px.defer = 0;
-  if (peers != nullptr && peers->world > 1) {
-    px.world = peers->world;
-    px.rank = peers->rank;
-    px.seq = peers->seq;
-    px.defer = peers->defer ? 1 : 0;
-    for (int r = 0; r < peers->world; ++r) px.slots[r] = peers->slots[r];
-  }
-  const char* v = getenv("UPP_CH_VARIANT");  // tuning aid
+  const PeerXchg px = make_px(peers);
+  const char* v = tuning_env("UPP_CH_VARIANT");  // tuning aid
   const int variant = v ? atoi(v) : -1;
   const bool have_ws = workspace != nullptr && workspace_bytes >= chamfer_fwd_workspace_bytes(B, N, M);
   // single pass: rows = the larger cloud (fills the 32*R-row tiles), columns = the smaller one (any size);
@@ -966,28 +1055,47 @@ int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M
 }
 
 int peer_finish_launch(const upp_peer_exchange* peers, float* global_sums, cudaStream_t st) {
-  PeerXchg px;
-  px.world = peers->world;
-  px.rank = peers->rank;
-  px.seq = peers->seq;
+  PeerXchg px = make_px(peers);
   px.defer = 0;
-  for (int r = 0; r < UPP_MAX_PEERS; ++r) px.slots[r] = r < peers->world ? peers->slots[r] : nullptr;
   peer_finish_kernel<<<1, 32, 0, st>>>(px, global_sums);
   count_launch();
   return launch_status();
 }
 
+size_t chamfer_bwd_stats_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  // ticket (16 B) + one float per CTA; CTAs per cloud <= ceil(N / 64) + ceil(M / 64) (one-warp CTAs at worst)
+  return 16 + static_cast<size_t>(B) * ((N + 63) / 64 + (M + 63) / 64 + 2) * sizeof(float);
+}
+
+// sq_out == nullptr: plain backward.  Otherwise sq_out[0..1] = sum ||grad_xyz1||^2, sum ||grad_xyz2||^2 (over all ranks
+// when peers is given), workspace as sized by chamfer_bwd_stats_workspace_bytes.
 int chamfer_bwd_launch(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2,
                        const float* g1, const float* g2, int B, int N, int M, float* gx1, float* gx2,
+                       float* sq_out, void* workspace, size_t workspace_bytes, const upp_peer_exchange* peers,
                        cudaStream_t st) {
-  const size_t total = static_cast<size_t>(B) * (static_cast<size_t>(N) + M);
-  const size_t want = (total + 255) / 256;
-  const int blocks = static_cast<int>(want > 148 * 16 ? 148 * 16 : want);
-  chamfer_bwd_own_kernel<<<blocks, 256, 0, st>>>(xyz1, xyz2, idx1, idx2, g1, g2, B, N, M, gx1, gx2);
+  // one grid for both sides: the same CTA shape serves both (the smaller side just needs fewer CTAs)
+  const ScatterGrid a = scatter_grid(N, M, 2), c = scatter_grid(M, N, 2);
+  const int warps = a.warps > c.warps ? a.warps : c.warps;
+  const int blocks1 = (N + warps * 64 - 1) / (warps * 64), blocks2 = (M + warps * 64 - 1) / (warps * 64);
+  const size_t smem = a.smem > c.smem ? a.smem : c.smem;
+  unsigned* ticket = nullptr;
+  float* partials = nullptr;
+  if (sq_out != nullptr) {
+    if (workspace == nullptr || workspace_bytes < chamfer_bwd_stats_workspace_bytes(B, N, M)) return UPP_ERR_WORKSPACE;
+    ticket = static_cast<unsigned*>(workspace);
+    partials = reinterpret_cast<float*>(ticket + 4);
+    cudaError_t e = cudaMemsetAsync(ticket, 0, 16, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  chamfer_bwd_kernel<<<dim3(blocks1 + blocks2, B), warps * 32, smem, st>>>(xyz1, xyz2, idx1, idx2, g1, g2, N, M, blocks1,
+                                                                          gx1, gx2, partials, ticket, sq_out, make_px(peers));
   count_launch();
-  int rc = launch_status();
-  if (rc != UPP_OK) return rc;
-  chamfer_bwd_scatter_kernel<<<blocks, 256, 0, st>>>(xyz1, xyz2, idx1, idx2, g1, g2, B, N, M, gx1, gx2);
+  return launch_status();
+}
+
+int peer_allreduce_launch(const upp_peer_exchange* peers, const float* local, float* global_sums, cudaStream_t st) {
+  peer_allreduce_kernel<<<1, 256, 0, st>>>(make_px(peers), local, global_sums);
   count_launch();
   return launch_status();
 }

@@ -17,6 +17,13 @@ constexpr int kWarp = 32;
 // ---- launch accounting (bench.py's gpu_launches, tests) -------------------------------
 void count_launch(int n = 1);
 
+// ---- tuning / A-B switches --------------------------------------------------------------
+// The UPP_FPS_* / UPP_CH_* / UPP_INTERP_* / UPP_BLEND_* / UPP_GROUP_* environment switches select kernel variants
+// for timing sweeps and for the parity tests that force every variant.  They are honoured ONLY when
+// UPP_TUNING=1 is set as well: a stray variable in a user's environment never changes the product path.
+const char* tuning_env(const char* name);
+int tuning_env_int(const char* name, int dflt);
+
 // ---- distance forms: spelled with explicit roundings, never left to contraction -------
 // chamfer.cu:40-43 / upstream sampling_gpu.cu: nvcc contracts dx*dx + dy*dy + dz*dz to this.
 __device__ __forceinline__ float dist_yxz(float dx, float dy, float dz) {
@@ -169,6 +176,40 @@ __device__ __forceinline__ void stage_points(float* dst, const float* __restrict
     parity ^= 1u;
   }
   __syncthreads();
+}
+
+// ---- thread-block clusters / distributed shared memory --------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, unsigned rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, int lo, int hi, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+               "r"(lo), "r"(hi), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// plain 32-bit store into the shared memory of CTA `rank`-mapped address (mapa result)
+__device__ __forceinline__ void st_cluster_u32(uint32_t remote_addr, int v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile_shared_s32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
 }
 
 // ---- host-side launch check -----------------------------------------------------------

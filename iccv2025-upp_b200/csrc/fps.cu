@@ -17,18 +17,11 @@
 // x^2+y^2+z^2 <= 1e-3 (double compare) never selected, d = fma(dz,dz,fma(dx,dx,dy*dy)).
 #include <limits.h>
 
-#include "common.cuh"
+#include "fps_round.cuh"
 
 namespace upp {
 
-constexpr float kSkipped = -1.0f;      // |p|^2 <= 1e-3 : bits 0xBF800000, s32 -1082130432
-constexpr float kOutOfRange = -0.5f;   // slot >= N     : bits 0xBF000000, s32 -1090519040 (lower)
 constexpr int kFpsMaxRegPoints = 8192; // largest N the register-resident kernel covers
-
-__device__ __forceinline__ float fps_initial_md(float x, float y, float z) {
-  const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
-  return (static_cast<double>(mag) <= 1e-3) ? kSkipped : 1e10f;
-}
 
 // THREADS is any multiple of 32; one warp means no barrier and no second stage at all.
 // TT == 0 is the tuning variant: thread count taken from blockDim.x at run time.
@@ -285,72 +278,6 @@ struct KeyTree {
   __device__ __forceinline__ int find(int best) const { return descend<4, 0>(best); }
 };
 
-// One span [R0, R1) of a thread's point pairs: distances to the new centre, running-min update,
-// span maximum (order-preserving float bits) and the lowest slot holding it.  TREE: independent
-// compare/selects + a VIMNMX3 tree (short dependent chain) instead of one select chain.
-template <int P2, int R0, int R1, bool TREE>
-__device__ __forceinline__ void fps_span(const f32x2 (&X)[P2], const f32x2 (&Y)[P2], const f32x2 (&Z)[P2],
-                                         float (&md)[2 * P2], f32x2 CX, f32x2 CY, f32x2 CZ, int& best,
-                                         int& ls) {
-  constexpr int NP = R1 - R0, NS = 2 * NP;
-  // all packed distance chains are independent: spelled stage by stage so that they are scheduled
-  // interleaved (one warp per scheduler has nobody else to hide a dependent chain)
-  f32x2 D[NP];
-#pragma unroll
-  for (int r = 0; r < NP; ++r) D[r] = sub2(Y[R0 + r], CY);
-#pragma unroll
-  for (int r = 0; r < NP; ++r) D[r] = mul2(D[r], D[r]);
-#pragma unroll
-  for (int r = 0; r < NP; ++r) { const f32x2 dx = sub2(X[R0 + r], CX); D[r] = fma2(dx, dx, D[r]); }
-#pragma unroll
-  for (int r = 0; r < NP; ++r) { const f32x2 dz = sub2(Z[R0 + r], CZ); D[r] = fma2(dz, dz, D[r]); }
-  int key[NS];
-#pragma unroll
-  for (int r = 0; r < NP; ++r) {
-    float d0, d1;
-    unpack2(D[r], d0, d1);
-    md[2 * (R0 + r)] = fminf(md[2 * (R0 + r)], d0);
-    md[2 * (R0 + r) + 1] = fminf(md[2 * (R0 + r) + 1], d1);
-    key[2 * r] = __float_as_int(md[2 * (R0 + r)]);
-    key[2 * r + 1] = __float_as_int(md[2 * (R0 + r) + 1]);
-  }
-  int red[NS];
-#pragma unroll
-  for (int s = 0; s < NS; ++s) red[s] = key[s];
-#pragma unroll
-  for (int n = NS; n > 1; n = (n + 2) / 3) {  // balanced VIMNMX3 tree
-#pragma unroll
-    for (int q = 0; q < (n + 2) / 3; ++q) {
-      int v = red[3 * q];
-      if (3 * q + 1 < n) v = max(v, red[3 * q + 1]);
-      if (3 * q + 2 < n) v = max(v, red[3 * q + 2]);
-      red[q] = v;
-    }
-  }
-  best = red[0];
-  if constexpr (TREE) {
-    int cnd[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) cnd[s] = key[s] == best ? 2 * R0 + s : 2 * P2;
-#pragma unroll
-    for (int n = NS; n > 1; n = (n + 2) / 3) {
-#pragma unroll
-      for (int q = 0; q < (n + 2) / 3; ++q) {
-        int v = cnd[3 * q];
-        if (3 * q + 1 < n) v = min(v, cnd[3 * q + 1]);
-        if (3 * q + 2 < n) v = min(v, cnd[3 * q + 2]);
-        cnd[q] = v;
-      }
-    }
-    ls = cnd[0];
-  } else {
-    ls = 2 * R0 + NS - 1;
-#pragma unroll
-    for (int s = NS - 2; s >= 0; --s)
-      if (key[s] == best) ls = 2 * R0 + s;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // v2 (fps_blk_kernel): the same register-resident scheme re-cut around what the B200 measurements
 // say binds one round (scripts/microbench2.cu): issue slots and the dependent REDUX/BAR/LDS chain.
@@ -525,25 +452,6 @@ __global__ void __launch_bounds__(NW * 32)
 // No intra-CTA barrier and no cluster barrier inside the loop: two entry buffers / two mbarriers alternate by
 // round parity (a CTA can only send round j+2 after it has received every CTA's round j+1, i.e. after every
 // CTA has consumed round j).  Same selection rule as every other FPS kernel here, bit-identical indices.
-__device__ __forceinline__ unsigned cluster_ctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, unsigned rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, int lo, int hi, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
-               "r"(lo), "r"(hi), "r"(remote_bar)
-               : "memory");
-}
-
 template <int CS, int NW, int P2>
 __global__ void __launch_bounds__(NW * 32, 1)
     fps_cluster_kernel(const float* __restrict__ xyz, int N, int M, int Nc, int32_t* __restrict__ idx_out,
@@ -698,10 +606,7 @@ struct FpsConfig {
   int threads, p;
 };
 
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s ? atoi(s) : dflt;
-}
+static int env_int(const char* name, int dflt) { return tuning_env_int(name, dflt); }  // UPP_TUNING=1 only
 
 // FPS is a serial latency chain: one warp per scheduler, ~40 % issue utilisation, every instruction on
 // the critical path.  Any co-resident CTA of a throughput kernel (measured: the packed Chamfer kernel

@@ -3,8 +3,9 @@
 // gather_points / gather_points_grad replace pointnet2_ops gather_operation (reference call site
 // utils/misc.py:19).  group_gather fuses Group.forward's index gather + centre subtraction
 // (models/Point_MAE_unify.py:72-88); group_bwd is its scatter-add gradient.
-// All HBM-bound copies: one thread per output element, coalesced on the output side.
-#include "common.cuh"
+// Forward gathers: one thread per output element, coalesced on the output side.  Backward scatter-adds: ordered
+// gathers (scatter.cuh) -- deterministic, no float atomics, no memset.
+#include "scatter.cuh"
 
 namespace upp {
 
@@ -20,16 +21,35 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void __launch_bounds__(256)
-    gather_points_grad_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx, int C,
-                              int N, int M, size_t total, float* __restrict__ gfeat) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int j = static_cast<int>(i % M);
-    const size_t bc = i / M;
-    const size_t b = bc / C;
-    atomicAdd(gfeat + bc * N + __ldg(idx + b * M + j), __ldg(gout + i));
+// Gradient of the channel-first gather (upstream gather_points_grad_kernel: float atomicAdd): ordered gather, see
+// scatter.cuh.  Destinations are the N points of a cloud, entries the M sampled indices; blockIdx.z walks the channels
+// three at a time.
+struct GatherGradOp {
+  const float* gout;    // (B,C,M)
+  const int32_t* idx;   // (B,M)
+  float* gfeat;         // (B,C,N)
+  int b, c0, C, N, M;
+  __device__ __forceinline__ int entries() const { return M; }
+  __device__ __forceinline__ int dst(int e) const { return __ldg(idx + static_cast<size_t>(b) * M + e); }
+  __device__ __forceinline__ void fetch(int e, float (&v)[3]) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c0 + c < C) v[c] = __ldg(gout + (static_cast<size_t>(b) * C + c0 + c) * M + e);
   }
+  __device__ __forceinline__ void init(int, float (&)[3]) const {}
+  __device__ __forceinline__ void store(int j, const float (&a)[3]) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c0 + c < C) gfeat[(static_cast<size_t>(b) * C + c0 + c) * N + j] = a[c];
+  }
+};
+
+__global__ void __launch_bounds__(256)
+    gather_points_grad_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx, int C, int N, int M,
+                              float* __restrict__ gfeat) {
+  extern __shared__ int s_dst[];
+  GatherGradOp op{gout, idx, gfeat, static_cast<int>(blockIdx.y), static_cast<int>(blockIdx.z) * 3, C, N, M};
+  ordered_scatter_cta<2>(op, N, s_dst);
 }
 
 // neighborhood[b,g,j,:] = xyz[b, idx[b,g,j], :] - center[b,g,:]   (one thread per neighbour)
@@ -50,46 +70,86 @@ __global__ void __launch_bounds__(256)
 }
 
 // grad_xyz[b, idx[b,g,j]] += gnb[b,g,j]; grad_xyz[b, cidx[b,g]] += gcenter[b,g] - sum_j gnb[b,g,j]
-// One warp per group: the k neighbour gradients are summed by shuffle for the centre term.
+// Ordered gather (scatter.cuh): per cloud the entry list is the G*k neighbour slots in (g, j) order followed by the G
+// centre slots in g order; a centre entry's value is formed by the lane that holds it (k sequential adds in j order).
+struct GroupBwdOp {
+  const float* gnb;       // (B,G,k,3)
+  const float* gcenter;   // (B,G,3) or null
+  const int64_t* idx;     // (B,G,k)
+  const int32_t* cidx;    // (B,G)
+  float* gxyz;            // (B,N,3)
+  int b, N, G, k;
+  __device__ __forceinline__ int entries() const { return G * k + G; }
+  __device__ __forceinline__ int dst(int e) const {
+    const int nk = G * k;
+    return e < nk ? static_cast<int>(idx[static_cast<size_t>(b) * nk + e]) : __ldg(cidx + static_cast<size_t>(b) * G + (e - nk));
+  }
+  __device__ __forceinline__ void fetch(int e, float (&v)[3]) const {
+    const int nk = G * k;
+    if (e < nk) {
+      const float* p = gnb + (static_cast<size_t>(b) * nk + e) * 3;
+      v[0] = __ldg(p); v[1] = __ldg(p + 1); v[2] = __ldg(p + 2);
+    } else {
+      const int g = e - nk;
+      const float* p = gnb + (static_cast<size_t>(b) * G + g) * k * 3;
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      for (int j = 0; j < k; ++j) {
+        sx = __fadd_rn(sx, __ldg(p + 3 * j)); sy = __fadd_rn(sy, __ldg(p + 3 * j + 1)); sz = __fadd_rn(sz, __ldg(p + 3 * j + 2));
+      }
+      v[0] = -sx; v[1] = -sy; v[2] = -sz;
+      if (gcenter) {
+        const float* c = gcenter + (static_cast<size_t>(b) * G + g) * 3;
+        v[0] = __fadd_rn(v[0], __ldg(c)); v[1] = __fadd_rn(v[1], __ldg(c + 1)); v[2] = __fadd_rn(v[2], __ldg(c + 2));
+      }
+    }
+  }
+  __device__ __forceinline__ void init(int, float (&)[3]) const {}
+  __device__ __forceinline__ void store(int j, const float (&a)[3]) const {
+    float* o = gxyz + (static_cast<size_t>(b) * N + j) * 3;
+    o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
+  }
+};
+
 __global__ void __launch_bounds__(256)
     group_bwd_kernel(const float* __restrict__ gnb, const float* __restrict__ gcenter,
                      const int64_t* __restrict__ idx, const int32_t* __restrict__ cidx, int N, int G,
-                     int k, size_t groups, float* __restrict__ gxyz) {
-  const int lane = threadIdx.x & 31;
-  for (size_t bg = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-       bg < groups; bg += static_cast<size_t>(gridDim.x) * (blockDim.x >> 5)) {
-    const size_t b = bg / G;
-    float* gb = gxyz + b * N * 3;
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (int j = lane; j < k; j += 32) {
-      const size_t i = bg * k + j;
-      const float vx = gnb[3 * i], vy = gnb[3 * i + 1], vz = gnb[3 * i + 2];
-      float* dst = gb + static_cast<size_t>(idx[i]) * 3;
-      atomicAdd(dst, vx); atomicAdd(dst + 1, vy); atomicAdd(dst + 2, vz);
-      sx += vx; sy += vy; sz += vz;
-    }
-    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-    if (lane == 0) {
-      float cx = -sx, cy = -sy, cz = -sz;
-      if (gcenter) { cx += gcenter[3 * bg]; cy += gcenter[3 * bg + 1]; cz += gcenter[3 * bg + 2]; }
-      float* dst = gb + static_cast<size_t>(cidx[bg]) * 3;
-      atomicAdd(dst, cx); atomicAdd(dst + 1, cy); atomicAdd(dst + 2, cz);
-    }
-  }
+                     int k, float* __restrict__ gxyz) {
+  extern __shared__ int s_dst[];
+  GroupBwdOp op{gnb, gcenter, idx, cidx, gxyz, static_cast<int>(blockIdx.y), N, G, k};
+  ordered_scatter_cta<2>(op, N, s_dst);
 }
 
 // grad[b, idx[b,j], :] += rows[b,j,:]  (row-major / channel-last; the gradient of the coordinate gather fused
-// into upp_fps_f32's centers_out, i.e. of utils/misc.py:19 without its two transposes)
+// into upp_fps_f32's centers_out, i.e. of utils/misc.py:19 without its two transposes).  Ordered gather, channels
+// three at a time (blockIdx.z).
+struct RowsScatterOp {
+  const float* rows;     // (B,M,C)
+  const int32_t* idx;    // (B,M)
+  float* grad;           // (B,N,C)
+  int b, c0, C, N, M;
+  __device__ __forceinline__ int entries() const { return M; }
+  __device__ __forceinline__ int dst(int e) const { return __ldg(idx + static_cast<size_t>(b) * M + e); }
+  __device__ __forceinline__ void fetch(int e, float (&v)[3]) const {
+    const float* p = rows + (static_cast<size_t>(b) * M + e) * C + c0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c0 + c < C) v[c] = __ldg(p + c);
+  }
+  __device__ __forceinline__ void init(int, float (&)[3]) const {}
+  __device__ __forceinline__ void store(int j, const float (&a)[3]) const {
+    float* o = grad + (static_cast<size_t>(b) * N + j) * C + c0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c0 + c < C) o[c] = a[c];
+  }
+};
+
 __global__ void __launch_bounds__(256)
     rows_scatter_add_kernel(const float* __restrict__ rows, const int32_t* __restrict__ idx, int N, int M, int C,
-                            size_t total, float* __restrict__ grad) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const size_t bj = i / C;  // b*M + j
-    const size_t b = bj / M;
-    atomicAdd(grad + (b * N + __ldg(idx + bj)) * C + c, __ldg(rows + i));
-  }
+                            float* __restrict__ grad) {
+  extern __shared__ int s_dst[];
+  RowsScatterOp op{rows, idx, grad, static_cast<int>(blockIdx.y), static_cast<int>(blockIdx.z) * 3, C, N, M};
+  ordered_scatter_cta<2>(op, N, s_dst);
 }
 
 static int grid_for(size_t total, int per_block) {
@@ -109,22 +169,19 @@ int gather_launch(const float* feat, const int32_t* idx, int B, int C, int N, in
 
 int gather_grad_launch(const float* gout, const int32_t* idx, int B, int C, int N, int M,
                        float* gfeat, cudaStream_t st) {
-  const size_t total = static_cast<size_t>(B) * C * M;
-  cudaError_t e = cudaMemsetAsync(gfeat, 0, static_cast<size_t>(B) * C * N * sizeof(float), st);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  if (total == 0) return UPP_OK;
-  gather_points_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(gout, idx, C, N, M, total, gfeat);
+  if (static_cast<size_t>(B) * C * N == 0) return UPP_OK;
+  // every destination is written exactly once (zero where nothing lands): no memset, no atomics
+  const ScatterGrid g = scatter_grid(N, M, 2);
+  gather_points_grad_kernel<<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(gout, idx, C, N, M, gfeat);
   count_launch();
   return launch_status();
 }
 
 int rows_scatter_add_launch(const float* rows, const int32_t* idx, int B, int N, int M, int C, float* grad,
                             cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(grad, 0, static_cast<size_t>(B) * N * C * sizeof(float), st);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  const size_t total = static_cast<size_t>(B) * M * C;
-  if (total == 0) return UPP_OK;
-  rows_scatter_add_kernel<<<grid_for(total, 256), 256, 0, st>>>(rows, idx, N, M, C, total, grad);
+  if (static_cast<size_t>(B) * N * C == 0) return UPP_OK;
+  const ScatterGrid g = scatter_grid(N, M, 2);
+  rows_scatter_add_kernel<<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(rows, idx, N, M, C, grad);
   count_launch();
   return launch_status();
 }
@@ -140,11 +197,9 @@ int group_gather_launch(const float* xyz, const float* center, const int64_t* id
 
 int group_bwd_launch(const float* gnb, const float* gcenter, const int64_t* idx, const int32_t* cidx,
                      int B, int N, int G, int k, float* gxyz, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(gxyz, 0, static_cast<size_t>(B) * N * 3 * sizeof(float), st);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  const size_t groups = static_cast<size_t>(B) * G;
-  if (groups == 0) return UPP_OK;
-  group_bwd_kernel<<<grid_for(groups, 8), 256, 0, st>>>(gnb, gcenter, idx, cidx, N, G, k, groups, gxyz);
+  if (static_cast<size_t>(B) * N == 0) return UPP_OK;
+  const ScatterGrid g = scatter_grid(N, G * k + G, 2);
+  group_bwd_kernel<<<dim3(g.blocks, B), g.warps * 32, g.smem, st>>>(gnb, gcenter, idx, cidx, N, G, k, gxyz);
   count_launch();
   return launch_status();
 }

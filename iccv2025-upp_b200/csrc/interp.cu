@@ -1098,7 +1098,7 @@ __global__ void __launch_bounds__(256)
 // UPP_INTERP_PATH (tuning / test aid): 0 = never take the wide-feature paths, 1 = take them whenever the
 // shape allows, unset = when the shape allows AND the problem is large enough to pay for the extra launch.
 static int interp_path_env() {
-  const char* v = getenv("UPP_INTERP_PATH");
+  const char* v = tuning_env("UPP_INTERP_PATH");
   return v ? atoi(v) : -1;
 }
 
@@ -1139,11 +1139,11 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
     two_phase = false;  // no tensor-map encoder in this driver: the one-launch kernel serves every shape
   const int csel = two_phase ? 0 : C;
   // UPP_INTERP_SELECT (test aid): 0 = never the thread-per-target selection, 1 = whenever k <= 4 and S <= 1024
-  const char* sv = getenv("UPP_INTERP_SELECT");
+  const char* sv = tuning_env("UPP_INTERP_SELECT");
   const int senv = sv ? atoi(sv) : -1;
   const bool thread_select = two_phase && sel_ok && senv != 0 && (senv == 1 || static_cast<long>(B) * N >= 4096);
   if (thread_select) {
-    const char* tv = getenv("UPP_INTERP_TPT");  // tuning aid: threads per target (1, 2, 4)
+    const char* tv = tuning_env("UPP_INTERP_TPT");  // tuning aid: threads per target (1, 2, 4)
     const int tpt = tv ? atoi(tv) : 1;
 #define UPP_SELECT(K_, T_)                                                                                          \
   do {                                                                                                             \
@@ -1194,12 +1194,12 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
 
   const int chunks = C >= kBlendCh ? C / kBlendCh : 1;
   const int chw = min(C, kBlendCh);  // channels of a staged row
-  const char* wv = getenv("UPP_BLEND_WARPS");  // tuning aid: 8 or 16 warps per CTA
+  const char* wv = tuning_env("UPP_BLEND_WARPS");  // tuning aid: 8 or 16 warps per CTA
   const int nwb = (wv && atoi(wv) == 8) ? 8 : 16;
   const int kk = (k == 3 || k == 4 || k == 8 || k == 16) ? k : 0;  // the instantiated neighbour counts; 0 = run-time loop
   const size_t bsmem = ((static_cast<size_t>(S) * chw * sizeof(float) + 15) & ~static_cast<size_t>(15)) +
                        static_cast<size_t>(nwb) * blend_tw(kk) * k * 8;
-  const char* sv2 = getenv("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
+  const char* sv2 = tuning_env("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
   const int spans = sv2 ? max(1, atoi(sv2)) : blend_pick_spans(static_cast<long>(chunks) * B, N);
   const int span = ((N + spans - 1) / spans + 1) & ~1;  // whole pairs of targets (a warp blends two per trip)
   dim3 bgrid(chunks, (N + span - 1) / span, B);

@@ -29,7 +29,10 @@ _SIGNATURES = {
     "upp_chamfer_fwd_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "upp_chamfer_fwd_sharded_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp],
     "upp_peer_allreduce_finish_f32": [_vp, _vp, _vp],
+    "upp_peer_allreduce_f32": [_vp, _vp, _vp, _vp],
     "upp_chamfer_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "upp_chamfer_bwd_stats_workspace_bytes": [_i, _i, _i],
+    "upp_chamfer_bwd_stats_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp, _vp],
     "upp_group_f32": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "upp_group_bwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "upp_knn_points_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -42,6 +45,7 @@ _RESTYPES = {
     "upp_launch_count": ctypes.c_ulonglong,
     "upp_fps_workspace_bytes": _sz,
     "upp_chamfer_fwd_workspace_bytes": _sz,
+    "upp_chamfer_bwd_stats_workspace_bytes": _sz,
     "upp_interp_bwd_workspace_bytes": _sz,
 }
 
@@ -53,7 +57,8 @@ UPP_MAX_PEERS = 16
 class PeerExchangeStruct(ctypes.Structure):
     """upp_peer_exchange of include/upp_geom.h."""
     _fields_ = [("slots", ctypes.c_void_p * UPP_MAX_PEERS), ("rank", ctypes.c_int), ("world", ctypes.c_int),
-                ("seq", ctypes.c_void_p), ("defer", ctypes.c_int)]
+                ("seq", ctypes.c_void_p), ("defer", ctypes.c_int), ("status", ctypes.c_void_p),
+                ("timeout_cycles", ctypes.c_longlong)]
 
 _lib = None
 

@@ -170,10 +170,13 @@ def chamfer_forward(xyz1, xyz2, want_sums=False):
     return [d1, d2, i1, i2] + ([sums] if want_sums else [])
 
 
-def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
+def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, want_sqnorm=False, peers=None):
     """chamfer.backward (extensions/chamfer_dist/chamfer.cu:203-229) -> [grad_xyz1, grad_xyz2].
     grad_dist* may arrive non-contiguous (expanded scalars from mean/sqrt backward); they are
-    densified here -- the reference silently assumes dense (chamfer.cu:217)."""
+    densified here -- the reference silently assumes dense (chamfer.cu:217).  Deterministic (no atomics).
+    want_sqnorm: also return a 4-float tensor whose first two entries are sum ||grad_xyz1||^2, sum ||grad_xyz2||^2
+    (upp_chamfer_bwd_stats_f32) -- over the GLOBAL sharded batch when `peers` (a parallel.PeerExchange) is given: the
+    gradient statistics a clip_grad_norm_ over the coordinate gradients needs, exchanged inside the kernel."""
     _xyz("xyz1", xyz1)
     _xyz("xyz2", xyz2)
     _need("idx1", idx1, torch.int32, 2)
@@ -188,9 +191,24 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2):
     g2 = grad_dist2.to(torch.float32).contiguous()
     gx1 = torch.empty_like(xyz1)
     gx2 = torch.empty_like(xyz2)
+    lib = _lib.load()
+    if want_sqnorm:
+        import ctypes
+        sq = torch.zeros(4, dtype=torch.float32, device=xyz1.device)
+        wbytes = int(lib.upp_chamfer_bwd_stats_workspace_bytes(B, N, M))
+        ws = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=xyz1.device)
+        pp = None
+        if peers is not None:
+            peers.struct.defer = 0
+            pp = ctypes.addressof(peers.struct)
+        with _on(xyz1):
+            rc = lib.upp_chamfer_bwd_stats_f32(_ptr(xyz1), _ptr(xyz2), _ptr(idx1), _ptr(idx2), _ptr(g1), _ptr(g2), B, N, M,
+                                               _ptr(gx1), _ptr(gx2), _ptr(sq), _ptr(ws), wbytes, pp, _stream(xyz1))
+        _lib.check(rc, "upp_chamfer_bwd_stats_f32")
+        return [gx1, gx2, sq]
     with _on(xyz1):
-        rc = _lib.load().upp_chamfer_bwd_f32(_ptr(xyz1), _ptr(xyz2), _ptr(idx1), _ptr(idx2), _ptr(g1),
-                                             _ptr(g2), B, N, M, _ptr(gx1), _ptr(gx2), _stream(xyz1))
+        rc = lib.upp_chamfer_bwd_f32(_ptr(xyz1), _ptr(xyz2), _ptr(idx1), _ptr(idx2), _ptr(g1),
+                                     _ptr(g2), B, N, M, _ptr(gx1), _ptr(gx2), _stream(xyz1))
     _lib.check(rc, "upp_chamfer_bwd_f32")
     return [gx1, gx2]
 
@@ -332,6 +350,20 @@ def peer_allreduce_finish(peers, device):
     return sums
 
 
+def peer_allreduce(peers, local4=None, defer=False):
+    """upp_peer_allreduce_f32: SUM all-reduce of 4 floats over the mapped peer buffers (local4 None: zeros -- what a rank
+    with an EMPTY shard contributes).  -> global sums (4 floats), or the local ones when defer=True."""
+    import ctypes
+    peers.struct.defer = 1 if defer else 0
+    out = torch.empty(4, dtype=torch.float32, device=peers.device)
+    if local4 is not None:
+        _need("local4", local4, torch.float32, 1)
+    with _on(out):
+        rc = _lib.load().upp_peer_allreduce_f32(ctypes.addressof(peers.struct), _ptr(local4), _ptr(out), _stream(out))
+    _lib.check(rc, "upp_peer_allreduce_f32")
+    return out
+
+
 def chamfer_forward_sharded(xyz1, xyz2, peers, defer=False):
     """upp_chamfer_fwd_sharded_f32: chamfer.forward of this rank's clouds, fused with the all-reduce of its sums
     over NVLink peer memory.  `peers` is a parallel.PeerExchange.  -> [dist1, dist2, idx1, idx2, global_sums].
@@ -351,7 +383,7 @@ def chamfer_forward_sharded(xyz1, xyz2, peers, defer=False):
     sums = torch.empty(4, dtype=torch.float32, device=dev)
     lib = _lib.load()
     wbytes = int(lib.upp_chamfer_fwd_workspace_bytes(B, N, M))
-    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
     import ctypes
     with _on(xyz1):
         rc = lib.upp_chamfer_fwd_sharded_f32(_ptr(xyz1), _ptr(xyz2), B, N, M, _ptr(d1), _ptr(d2), _ptr(i1), _ptr(i2),

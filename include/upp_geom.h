@@ -136,7 +136,8 @@ UPP_API int upp_chamfer_fwd_f32(const float* xyz1, const float* xyz2, int B, int
  *             bytes, zero-filled once before the first call;
  *   seq       this rank's call counter in device memory, zero before the first call.
  * Requires the workspace (single-pass path) and max(N, M) >= 128; otherwise UPP_ERR_UNSUPPORTED (use
- * upp_chamfer_fwd_f32 + an NCCL all-reduce of its partial sums).
+ * upp_chamfer_fwd_f32 + an NCCL all-reduce of its partial sums).  B == 0 (this rank's shard is empty) is valid: the rank
+ * contributes zeros to the exchange and receives the global sums like everybody else.
  */
 #define UPP_MAX_PEERS 16
 typedef struct upp_peer_exchange {
@@ -146,12 +147,24 @@ typedef struct upp_peer_exchange {
   unsigned int* seq;
   int defer; /* 0: the call returns the global sums; 1: the call only SENDS (global_sums receives this rank's local
                 sums) and upp_peer_allreduce_finish_f32, launched later on the same stream, waits and adds */
+  unsigned int* status; /* nullable: host-visible (pinned, mapped) word, zero before the first call.  A wait for a peer
+                that runs out stores the failed call's sequence number here (system scope) besides poisoning the sums with
+                NaN, so the host can raise instead of training on NaN silently. */
+  long long timeout_cycles; /* SM clocks a wait for a peer may last; 0 = default 2^38 (about 2.3 minutes at 1.965 GHz:
+                rank skew of seconds -- checkpointing, evaluation, a data-loader stall -- is normal and is waited out) */
 } upp_peer_exchange;
 #define upp_peer_exchange_bytes(world) ((size_t)2 * (size_t)(world) * 8 * sizeof(float))
 UPP_API int upp_chamfer_fwd_sharded_f32(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
                                 float* dist2, int32_t* idx1, int32_t* idx2, float* global_sums,
                                 void* workspace, size_t workspace_bytes, const upp_peer_exchange* peers,
                                 upp_stream_t stream);
+
+/* The exchange on its own: SUM all-reduce of 4 floats over the mapped peer buffers, rank order, bit-identical on every
+ * rank; one tiny launch, honours peers->defer like the sharded forward.  local4 == NULL contributes zeros: this is what a
+ * rank whose shard is EMPTY issues in place of upp_chamfer_fwd_sharded_f32 (which does it itself for B == 0), so that the
+ * ranks' call sequences stay aligned.  Mirrors utils/dist_utils.py:41-48 for a 16-byte payload. */
+UPP_API int upp_peer_allreduce_f32(const upp_peer_exchange* peers, const float* local4, float* global4,
+                                   upp_stream_t stream);
 
 /* Second half of a deferred exchange (peers->defer was 1 in the last upp_chamfer_fwd_sharded_f32 call on this
  * stream): waits for every rank's contribution of that call and writes the rank-ordered sum to global_sums (4 floats).
@@ -170,11 +183,27 @@ UPP_API int upp_peer_allreduce_finish_f32(const upp_peer_exchange* peers, float*
  * and symmetrically for grad_xyz2; inf*0 = NaN appears exactly where the reference produces it.
  * grad_dist1 (B,N), grad_dist2 (B,M) must be dense (the binding makes them so; the reference
  * silently assumes it, chamfer.cu:217).
+ * One launch, no memset, no float atomics: each output row is produced by one thread that adds its partner terms in
+ * ascending point order, so the gradients are bit-identical run to run (the reference's atomicAdd order is not).
  */
 UPP_API int upp_chamfer_bwd_f32(const float* xyz1, const float* xyz2, const int32_t* idx1,
                         const int32_t* idx2, const float* grad_dist1, const float* grad_dist2,
                         int B, int N, int M, float* grad_xyz1, float* grad_xyz2,
                         upp_stream_t stream);
+
+/* Chamfer backward + gradient statistics (BASELINE.json north_star: "all-reduce the scalar Chamfer loss and its gradient
+ * statistics"; the quantity tools/runner_module.py:204 clip_grad_norm_ needs of the coordinate gradients).
+ * Same gradients as upp_chamfer_bwd_f32 (same kernel), plus sqnorm_out[0..1] = { sum ||grad_xyz1||^2, sum ||grad_xyz2||^2 }
+ * over the call, summed in a fixed order (deterministic).  With peers != NULL (batch sharded over the GPUs of one node)
+ * the two sums are all-reduced over NVLink peer memory inside the same kernel, exactly like the forward's loss sums:
+ * every rank receives the sums over the GLOBAL batch, bit-identical; all ranks must call in the same order.
+ * workspace: upp_chamfer_bwd_stats_workspace_bytes(B,N,M) bytes of scratch (contents irrelevant on entry). */
+UPP_API size_t upp_chamfer_bwd_stats_workspace_bytes(int B, int N, int M);
+UPP_API int upp_chamfer_bwd_stats_f32(const float* xyz1, const float* xyz2, const int32_t* idx1,
+                              const int32_t* idx2, const float* grad_dist1, const float* grad_dist2,
+                              int B, int N, int M, float* grad_xyz1, float* grad_xyz2, float* sqnorm_out,
+                              void* workspace, size_t workspace_bytes, const upp_peer_exchange* peers,
+                              upp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused Group divider (opt-in fast path; the unchanged call site composes the ops above).

@@ -44,7 +44,6 @@ def main():
         rel = abs(loss.item() - full.item()) / abs(full.item())
         assert rel <= 1e-5, (kind, loss.item(), full.item())
         # same kernels, but the scalar chain differs (1/(4 n sqrt d) here vs autograd's mean -> sqrt): 1e-5 rel
-        # (and the partner terms are float atomics: summation order varies) -> 1e-5 of the gradient scale
         for got, want in ((al.grad, af.grad[lo:hi]), (bl.grad, bf.grad[lo:hi])):
             torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5 * float(want.abs().max()))
     # fused peer-memory all-reduce (upp_chamfer_fwd_sharded_f32) against the NCCL path: same loss to fp32 summation
@@ -69,7 +68,7 @@ def main():
                 nccl.backward()
                 assert torch.isfinite(fused), "peer wait timed out"
                 assert abs(fused.item() - nccl.item()) <= 1e-6 * abs(nccl.item()), (kind, it, fused.item(), nccl.item())
-                torch.testing.assert_close(gx, x2.grad, rtol=1e-4, atol=1e-5 * float(gx.abs().max()))  # float atomics
+                assert torch.equal(gx, x2.grad)  # same local kernels, deterministic backward: bit-equal
                 bits = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world)]
                 dist.all_gather(bits, fused.detach().view(torch.int32).reshape(1))
                 assert all(torch.equal(bits[0], v) for v in bits), "fused all-reduce must be bit-identical across ranks"
@@ -103,6 +102,48 @@ def main():
             torch.testing.assert_close(glob, ref, rtol=1e-6, atol=0)
         if rank == 0:
             print(f"fused peer all-reduce ok via {peers.how}: == NCCL (1e-6), bit-identical across ranks, graph replay x6, deferred finish x4")
+        peers.check()  # no exchange timed out
+    # gradient statistics (sum ||grad||^2 over the GLOBAL batch, exchanged inside the backward kernel) against
+    # torch.nn.utils.clip_grad_norm_'s total norm of the unsharded coordinate gradients (tools/runner_module.py:204);
+    # DDP-compatible scaling: grad_scale="ddp" makes the rank-AVERAGED gradient equal the unsharded one;
+    # an EMPTY shard (global batch smaller than the world) takes part in the exchange with zeros
+    for use_peers in ((peers, None) if peers is not None else (None,)):
+        for kind, mod in (("l2", upp_b200.ChamferDistanceL2()), ("l1", upp_b200.ChamferDistanceL1())):
+            af = (a.to(dev) + 0.003).requires_grad_(True)   # no exact-zero distances: L1 gradients finite
+            bf = b.to(dev).requires_grad_(True)
+            mod(af, bf).backward()
+            want_norm = torch.nn.utils.clip_grad_norm_([af, bf], max_norm=1e30)
+            al = (a[lo:hi].to(dev) + 0.003).requires_grad_(True)
+            bl = b[lo:hi].to(dev).requires_grad_(True)
+            st = parallel.GradStats()
+            loss = parallel.sharded_chamfer(al, bl, kind, n_global_clouds=B, peers=use_peers, stats=st)
+            loss.backward()
+            got_norm = st.total_norm()
+            assert abs(got_norm.item() - want_norm.item()) <= 1e-4 * want_norm.item(), (kind, got_norm.item(), want_norm.item())
+            bits = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(world)]
+            dist.all_gather(bits, st.sq_norm.view(torch.int32).clone())
+            assert all(torch.equal(bits[0], v) for v in bits) or use_peers is None, "fused statistics must be bit-identical across ranks"
+            again = parallel.GradStats()
+            al2 = (a[lo:hi].to(dev) + 0.003).requires_grad_(True)
+            parallel.sharded_chamfer(al2, b[lo:hi].to(dev), kind, n_global_clouds=B, peers=use_peers, stats=again).backward()
+            assert torch.equal(again.sq_norm, st.sq_norm) and torch.equal(al2.grad, al.grad), "deterministic backward + statistics"
+            # DDP semantics: average over ranks of the 'ddp'-scaled local gradients == unsharded gradient rows
+            al3 = (a[lo:hi].to(dev) + 0.003).requires_grad_(True)
+            parallel.sharded_chamfer(al3, b[lo:hi].to(dev), kind, n_global_clouds=B, peers=use_peers, grad_scale="ddp").backward()
+            torch.testing.assert_close(al3.grad / world, al.grad, rtol=1e-6, atol=0)
+            torch.testing.assert_close(al.grad, af.grad[lo:hi], rtol=1e-4, atol=1e-6 * float(af.grad.abs().max()))
+        # empty shard: 1 cloud in total, world ranks
+        lo1, hi1 = parallel.shard_bounds(1, rank, world)
+        e1 = a[:1][lo1:hi1].to(dev).requires_grad_(True)
+        e2 = b[:1][lo1:hi1].to(dev)
+        st = parallel.GradStats()
+        loss = parallel.sharded_chamfer(e1, e2, "l2", n_global_clouds=1, peers=use_peers, stats=st)
+        loss.backward()
+        want = upp_b200.ChamferDistanceL2()(a[:1].to(dev), b[:1].to(dev))
+        assert abs(loss.item() - want.item()) <= 1e-5 * want.item(), ("empty shard", rank, loss.item(), want.item())
+        assert e1.grad.shape[0] == hi1 - lo1 and torch.isfinite(st.sq_norm).all()
+    if peers is not None:
+        peers.check()
     # Group is per cloud: a shard's result equals the same rows of the full batch
     x = (torch.rand(B, 1024, 3, generator=g) * 2 - 1).to(dev)
     nb_f, ce_f = upp_b200.Group(64, 32)(x)
@@ -111,7 +152,8 @@ def main():
     ok = torch.ones(1, device=dev)
     dist.all_reduce(ok)
     if rank == 0:
-        print(f"multigpu ok: {int(ok.item())}/{world} ranks, sharded Chamfer L1/L2 loss and grads == unsharded (1e-5), Group shard-invariant (bit-equal)")
+        print(f"multigpu ok: {int(ok.item())}/{world} ranks, sharded Chamfer L1/L2 loss and grads == unsharded (1e-5), gradient statistics == "
+              f"clip_grad_norm_ total norm, ddp scaling, empty shard, Group shard-invariant (bit-equal)")
     dist.destroy_process_group()
 
 

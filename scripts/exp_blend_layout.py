@@ -1,6 +1,7 @@
 """Experiment: is the blend kernel bound by the 512-byte-strided output pattern?  Same output bytes (302 MB), same
 sources, but C = 128 (one channel chunk: every CTA writes whole rows, consecutive targets contiguous) against C = 1152."""
 import os
+os.environ.setdefault("UPP_TUNING", "1")  # the UPP_* variant switches below are honoured only with this set
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

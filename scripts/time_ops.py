@@ -3,6 +3,7 @@ Tuning aid; the numbers of record come from bench.py."""
 import argparse
 import json
 import os
+os.environ.setdefault("UPP_TUNING", "1")  # the UPP_* variant switches below are honoured only with this set
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -2,6 +2,7 @@
 (UPP_INTERP_TPT) and the one-launch kernel (UPP_INTERP_PATH=0).  CUDA-event timed, L2 flushed between runs."""
 import json
 import os
+os.environ.setdefault("UPP_TUNING", "1")  # the UPP_* variant switches below are honoured only with this set
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

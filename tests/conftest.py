@@ -10,6 +10,11 @@ for p in (PKG, os.path.join(PKG, "dropin"), ROOT):
         sys.path.insert(0, p)
 
 
+# the parity tests force every kernel variant through the UPP_* tuning switches; the library honours them only
+# under UPP_TUNING=1 (a stray switch in a user's environment never changes the product path)
+os.environ.setdefault("UPP_TUNING", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
