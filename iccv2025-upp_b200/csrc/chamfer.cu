@@ -715,6 +715,316 @@ __global__ void __launch_bounds__(256)
   idxB[static_cast<size_t>(b) * NB + k] = bi;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-pass forward, ONE kernel (round 2): chamfer_fwd_packed_kernel's distance loop, with the three things around
+// it folded in -- the key-workspace memset, the finalize launch and the atomics:
+//   * NO ATOMICS, NO PRESET.  A column's minimum over a CTA's 32*R rows is produced by exactly one warp (the CTA's
+//     warps take disjoint column groups), so the CTA owns the slot colpart[cloud][row block][column] and writes
+//     {ballot of the lanes holding the minimum, distance bits} with one plain 8-byte store.  (The RED.MIN.U64 it
+//     replaces was compiled to BSSY / BRA / MOV / REDG / BSYNC: 8 instructions per column and warp against 5, an L2
+//     atomic per column and row block, and a 0xFF memset of every key in front of the kernel.)  With several column
+//     chunks the row side does the same into rowpart[cloud][chunk][row].
+//   * THE FINALIZE RUNS INSIDE.  Tickets count the CTAs that have contributed to a (cloud, column chunk) and to a
+//     (cloud, row block); the CTA that draws the last ticket resolves those columns / rows itself: minimum over the
+//     partials (strict '<' in ascending row-block / chunk order = lowest index on ties), arg-min inside the winning span
+//     by recomputing its <= 16 distances, dist/idx written once.  This work overlaps the distance loops of the CTAs
+//     still running instead of waiting for the grid to drain behind a second launch.
+//   * THE SUMS, and the all-reduce over NVLink peer memory when the batch is sharded, close the same kernel: every
+//     finalizing CTA leaves {sum d, sum sqrt d} of its points in a fixed slot, and the CTA that draws the last global
+//     ticket adds the slots in index order (deterministic whichever CTA that is) and runs peer_allreduce4.
+//   * CG = 16: the row side keeps (best value, group) per 16 columns instead of 8 (one FSETP/FSEL/SEL per row and 16
+//     columns), the arg-min scan in the finalize covers 16 candidates.
+// Only the tickets (a few KB) are zeroed in front of the launch.
+struct ChFused {
+  const float* xyzA;
+  const float* xyzB;
+  int NA, NB, NA8, NB8, chunk, nchunks, RB;
+  float* distA;
+  int32_t* idxA;
+  float* distB;
+  int32_t* idxB;
+  uint2* colpart;      // [B][RB][NB8]   {ballot, distance bits}
+  uint2* rowpart;      // [B][nchunks][NA8] {column group base, distance bits}; unused when nchunks == 1
+  unsigned* tickets;   // [B * (RB + nchunks)] + 1 global, zero on entry
+  float2* partials;    // [B * (RB + nchunks)]  {sum d, sum sqrt d} of the points each finalizing CTA resolved
+  float* sums;         // nullable: 4 floats { d1, d2, sqrt d1, sqrt d2 }
+  int swapped;
+};
+
+template <int THREADS>
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* s_w) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_w[warp] = make_float2(a, b);
+  __syncthreads();
+  float2 r = make_float2(0.f, 0.f);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) { r.x += s_w[w].x; r.y += s_w[w].y; }
+  }
+  __syncthreads();
+  return r;  // valid in thread 0
+}
+
+template <int R, int WC, int CG, int MINB = 0>
+__global__ void __launch_bounds__(WC * 32, MINB)
+    chamfer_fwd_fused_kernel(const ChFused a, const PeerXchg px) {
+  static_assert(R % 2 == 0 && R <= 16, "rows are processed in packed pairs; the finalize scans at most 16 rows");
+  static_assert(CG == 8 || CG == 16, "column groups of 8 or 16");
+  constexpr int ROWS = 32 * R;
+  constexpr int THREADS = WC * 32;
+  constexpr int RP = R / 2;
+  static_assert(WC * ROWS * 8 <= kChTile * 12, "row-combine scratch must fit in the tile buffer");
+  __shared__ __align__(16) float s_ref[kChTile * 3];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ float2 s_w[WC];
+  __shared__ int s_flags[3];
+  __shared__ float s_x[1 + UPP_MAX_PEERS][4];
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);  // warp-uniform for the compiler
+  const int b = blockIdx.y, rb = blockIdx.x, z = blockIdx.z;
+  const int NA = a.NA, NB = a.NB;
+  const int c0 = z * a.chunk;
+  const int c1 = min(NB, c0 + a.chunk);
+  const float* ap = a.xyzA + static_cast<size_t>(b) * NA * 3;
+  const float* bp = a.xyzB + static_cast<size_t>(b) * NB * 3;
+  uint2* cpart = a.colpart + (static_cast<size_t>(b) * a.RB + rb) * a.NB8;
+  const int row0 = rb * ROWS + lane * R;
+
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned parity = 0;
+
+  f32x2 QX[RP], QY[RP], QZ[RP];
+  float best[R];
+  int bg[R];
+#pragma unroll
+  for (int rp = 0; rp < RP; ++rp) {
+    float c[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = row0 + 2 * rp + h;
+      const bool ok = j < NA;  // rows past the end are NaN: they never win a min
+#pragma unroll
+      for (int q = 0; q < 3; ++q) c[h][q] = ok ? __ldg(ap + 3 * j + q) : __int_as_float(0x7fc00000);
+    }
+    QX[rp] = pack2(c[0][0], c[1][0]);
+    QY[rp] = pack2(c[0][1], c[1][1]);
+    QZ[rp] = pack2(c[0][2], c[1][2]);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    best[r] = __int_as_float(0x7f800000);
+    bg[r] = 0;
+  }
+
+  for (int base = c0; base < c1; base += kChTile) {
+    const int tile = min(kChTile, c1 - base);
+    const int tileg = (tile + CG - 1) / CG * CG;
+    if (base > c0) __syncthreads();
+    // pad the last group with NaN: (q - NaN)^2 = NaN, and fminf() drops NaN operands
+    for (int i = tile * 3 + t; i < tileg * 3; i += THREADS) s_ref[i] = __int_as_float(0x7fc00000);
+    stage_points(s_ref, bp + static_cast<size_t>(base) * 3, tile, &s_bar, parity);
+
+    const int ngroups = tileg / CG;
+    for (int g = warp; g < ngroups; g += WC) {
+      const float4* s4 = reinterpret_cast<const float4*>(s_ref) + g * (CG * 3 / 4);
+      uint2* cbk = cpart + base + g * CG;
+      float m[R];
+#pragma unroll
+      for (int h = 0; h < CG / 2; ++h) {  // column pairs of the group
+        const float4 v0 = s4[(6 * h) >> 2];
+        const float4 v1 = s4[((6 * h) >> 2) + 1];
+        float ax, ay, az, bx, by, bz;
+        if ((h & 1) == 0) { ax = v0.x; ay = v0.y; az = v0.z; bx = v0.w; by = v1.x; bz = v1.y; }
+        else              { ax = v0.z; ay = v0.w; az = v1.x; bx = v1.y; by = v1.z; bz = v1.w; }
+        const f32x2 AX = pack2(ax, ax), AY = pack2(ay, ay), AZ = pack2(az, az);
+        const f32x2 BX = pack2(bx, bx), BY = pack2(by, by), BZ = pack2(bz, bz);
+        float ca = 0.f, cbm = 0.f;
+#pragma unroll
+        for (int rp = 0; rp < RP; ++rp) {
+          float a0, a1, b0, b1;
+          unpack2(dist2_yxz(sub2(QX[rp], AX), sub2(QY[rp], AY), sub2(QZ[rp], AZ)), a0, a1);
+          unpack2(dist2_yxz(sub2(QX[rp], BX), sub2(QY[rp], BY), sub2(QZ[rp], BZ)), b0, b1);
+          m[2 * rp] = h == 0 ? fminf(a0, b0) : fminf(fminf(m[2 * rp], a0), b0);
+          m[2 * rp + 1] = h == 0 ? fminf(a1, b1) : fminf(fminf(m[2 * rp + 1], a1), b1);
+          ca = rp == 0 ? fminf(a0, a1) : fminf(fminf(ca, a0), a1);
+          cbm = rp == 0 ? fminf(b0, b1) : fminf(fminf(cbm, b0), b1);
+        }
+        // column side: warp minimum of the (non-negative) float bits + which lanes hold it -- one plain store each
+        const unsigned ua = __float_as_uint(ca), ub = __float_as_uint(cbm);
+        const unsigned wa = redux_min_u32(ua), wb = redux_min_u32(ub);
+        const unsigned ma = __ballot_sync(0xffffffffu, ua == wa), mb = __ballot_sync(0xffffffffu, ub == wb);
+        cbk[2 * h] = make_uint2(ma, wa);
+        cbk[2 * h + 1] = make_uint2(mb, wb);
+      }
+      const int kk = base + g * CG;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (m[r] < best[r]) { best[r] = m[r]; bg[r] = kk; }
+    }
+  }
+
+  // ---- row side: combine the WC partials per row, then resolve (one chunk) or leave a partial (several) ----
+  __syncthreads();  // every warp is done reading the tile
+  float* s_best = s_ref;
+  int* s_bg = reinterpret_cast<int*>(s_ref + WC * ROWS);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    s_best[warp * ROWS + lane * R + r] = best[r];
+    s_bg[warp * ROWS + lane * R + r] = bg[r];
+  }
+  __syncthreads();
+  const bool direct = a.nchunks == 1;
+  float sd = 0.f, ss = 0.f;  // this thread's share of { sum d, sum sqrt d } of the rows resolved here
+  for (int rho = t; rho < ROWS; rho += THREADS) {
+    const int j = rb * ROWS + rho;
+    if (j >= NA) continue;
+    float bb = __int_as_float(0x7f800000);
+    int gg = 0;
+#pragma unroll
+    for (int w = 0; w < WC; ++w) {
+      const float v = s_best[w * ROWS + rho];
+      const int g = s_bg[w * ROWS + rho];
+      if (v < bb || (v == bb && g < gg)) { bb = v; gg = g; }
+    }
+    if (!direct) {
+      a.rowpart[(static_cast<size_t>(b) * a.nchunks + z) * a.NA8 + j] = make_uint2(static_cast<unsigned>(gg), __float_as_uint(bb));
+      continue;
+    }
+    const float px0 = __ldg(ap + 3 * j), py0 = __ldg(ap + 3 * j + 1), pz0 = __ldg(ap + 3 * j + 2);
+    int bi = gg;
+#pragma unroll
+    for (int u = CG - 1; u >= 0; --u) {  // independent (clamped) loads in flight, lowest match wins
+      const int kcol = min(gg + u, NB - 1);
+      const float* q = bp + static_cast<size_t>(kcol) * 3;
+      const float d = dist_yxz(__ldg(q) - px0, __ldg(q + 1) - py0, __ldg(q + 2) - pz0);
+      if (d == bb && gg + u < NB) bi = gg + u;
+    }
+    a.distA[static_cast<size_t>(b) * NA + j] = bb;
+    a.idxA[static_cast<size_t>(b) * NA + j] = bi;
+    sd += bb;
+    ss += __fsqrt_rn(bb);
+  }
+
+  // ---- tickets: am I the last contributor to this row block (over chunks) / to this column chunk (over row blocks)? ----
+  const unsigned slots = static_cast<unsigned>(a.RB + a.nchunks);
+  unsigned* tk = a.tickets + static_cast<size_t>(b) * slots;
+  __threadfence();   // this CTA's partial stores are visible device-wide before its tickets are drawn
+  __syncthreads();
+  if (t == 0) {
+    s_flags[0] = direct ? 1 : (atomicAdd(tk + rb, 1u) + 1u == static_cast<unsigned>(a.nchunks));
+    s_flags[1] = (atomicAdd(tk + a.RB + z, 1u) + 1u == static_cast<unsigned>(a.RB));
+    __threadfence();
+  }
+  __syncthreads();
+  const bool fin_rows = s_flags[0] != 0, fin_cols = s_flags[1] != 0;
+  int finished = 0;
+
+  if (fin_rows) {
+    if (!direct) {  // rows of this block: minimum over the chunks' partials, arg-min inside the winning group
+      for (int rho = t; rho < ROWS; rho += THREADS) {
+        const int j = rb * ROWS + rho;
+        if (j >= NA) continue;
+        unsigned bits = 0xffffffffu, gg = 0;
+        for (int zz = 0; zz < a.nchunks; ++zz) {
+          const uint2 e = __ldcg(a.rowpart + (static_cast<size_t>(b) * a.nchunks + zz) * a.NA8 + j);
+          if (e.y < bits) { bits = e.y; gg = e.x; }  // strict: the lower chunk (lower columns) keeps ties
+        }
+        const float px0 = __ldg(ap + 3 * j), py0 = __ldg(ap + 3 * j + 1), pz0 = __ldg(ap + 3 * j + 2);
+        int bi = static_cast<int>(gg);
+#pragma unroll
+        for (int u = CG - 1; u >= 0; --u) {
+          const int kcol = min(static_cast<int>(gg) + u, NB - 1);
+          const float* q = bp + static_cast<size_t>(kcol) * 3;
+          const float d = dist_yxz(__ldg(q) - px0, __ldg(q + 1) - py0, __ldg(q + 2) - pz0);
+          if (__float_as_uint(d) == bits && static_cast<int>(gg) + u < NB) bi = static_cast<int>(gg) + u;
+        }
+        const float dd = __uint_as_float(bits);
+        a.distA[static_cast<size_t>(b) * NA + j] = dd;
+        a.idxA[static_cast<size_t>(b) * NA + j] = bi;
+        sd += dd;
+        ss += __fsqrt_rn(dd);
+      }
+    }
+    if (a.sums != nullptr) {
+      const float2 tot = block_sum2<THREADS>(sd, ss, s_w);
+      if (t == 0) a.partials[static_cast<size_t>(b) * slots + rb] = tot;
+    }
+    ++finished;
+  }
+  if (fin_cols) {  // columns of this chunk: minimum over the row blocks' partials, arg-min inside the winning lane's R rows
+    float cd = 0.f, csq = 0.f;
+    for (int col = c0 + t; col < c1; col += THREADS) {
+      unsigned bits = 0xffffffffu, mask = 0u;
+      int wrb = 0;
+      for (int rr = 0; rr < a.RB; ++rr) {
+        const uint2 e = __ldcg(a.colpart + (static_cast<size_t>(b) * a.RB + rr) * a.NB8 + col);
+        if (e.y < bits) { bits = e.y; mask = e.x; wrb = rr; }  // strict: the lower row block keeps ties
+      }
+      const int j0 = wrb * ROWS + (__ffs(mask) - 1) * R;  // lowest lane holding the minimum = lowest rows
+      const float* q = bp + static_cast<size_t>(col) * 3;
+      const float rx = __ldg(q), ry = __ldg(q + 1), rz = __ldg(q + 2);
+      int bi = j0;
+#pragma unroll
+      for (int u = R - 1; u >= 0; --u) {
+        const int j = min(j0 + u, NA - 1);
+        const float* pr = ap + static_cast<size_t>(j) * 3;
+        const float d = dist_yxz(rx - __ldg(pr), ry - __ldg(pr + 1), rz - __ldg(pr + 2));
+        if (__float_as_uint(d) == bits && j0 + u < NA) bi = j0 + u;
+      }
+      const float dd = __uint_as_float(bits);
+      a.distB[static_cast<size_t>(b) * NB + col] = dd;
+      a.idxB[static_cast<size_t>(b) * NB + col] = bi;
+      cd += dd;
+      csq += __fsqrt_rn(dd);
+    }
+    if (a.sums != nullptr) {
+      const float2 tot = block_sum2<THREADS>(cd, csq, s_w);
+      if (t == 0) a.partials[static_cast<size_t>(b) * slots + a.RB + z] = tot;
+    }
+    ++finished;
+  }
+  if (a.sums == nullptr || finished == 0) return;
+
+  // ---- global ticket: the CTA that completes the last of the B * (RB + nchunks) finalizations adds the partials ----
+  const unsigned total = gridDim.y * slots;
+  if (t == 0) {
+    __threadfence();
+    s_flags[2] = (atomicAdd(a.tickets + static_cast<size_t>(gridDim.y) * slots, static_cast<unsigned>(finished)) +
+                  static_cast<unsigned>(finished) == total);
+  }
+  __syncthreads();
+  if (s_flags[2] == 0) return;
+  __threadfence();
+  // fixed order: thread t adds slots t, t + THREADS, ... per side; then a fixed-shape block sum
+  float2 side_sum[2];
+#pragma unroll
+  for (int sd2 = 0; sd2 < 2; ++sd2) {  // 0: cloud A (row slots), 1: cloud B (column slots)
+    float a0 = 0.f, a1 = 0.f;
+    const unsigned per = sd2 == 0 ? static_cast<unsigned>(a.RB) : static_cast<unsigned>(a.nchunks);
+    const unsigned off = sd2 == 0 ? 0u : static_cast<unsigned>(a.RB);
+    for (unsigned i = t; i < gridDim.y * per; i += THREADS) {
+      const float2 v = __ldcg(a.partials + static_cast<size_t>(i / per) * slots + off + i % per);
+      a0 += v.x;
+      a1 += v.y;
+    }
+    side_sum[sd2] = block_sum2<THREADS>(a0, a1, s_w);  // (valid in thread 0)
+  }
+  // output order { d1, d2, sqrt d1, sqrt d2 } of the CALLER's xyz1 / xyz2: cloud A is xyz1 unless the clouds were swapped
+  const float2 s1 = a.swapped ? side_sum[1] : side_sum[0], s2 = a.swapped ? side_sum[0] : side_sum[1];
+  float loc[4] = {s1.x, s2.x, s1.y, s2.y};
+  if (px.world > 1) peer_allreduce4(px, loc, s_x);  // sums of the WHOLE sharded batch, same bits on every rank
+  if (t == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a.sums[q] = loc[q];
+  }
+}
+
 // Deterministic whole-call sums { sum d1, sum d2, sum sqrt d1, sum sqrt d2 } -- the send buffer of
 // the one NCCL all-reduce the batch-sharded loss needs.  One thread-block CLUSTER of 8 CTAs: each
 // CTA reduces a fixed interleaved slice (4 independent accumulators per quantity keep loads in
@@ -794,10 +1104,10 @@ struct ChamferBwdOp {
   int b, Ns, No;
   __device__ __forceinline__ int entries() const { return No; }
   __device__ __forceinline__ int dst(int e) const { return __ldg(idx_other + static_cast<size_t>(b) * No + e); }
-  __device__ __forceinline__ void fetch(int e, float (&v)[3]) const {
+  __device__ __forceinline__ void fetch(int e, int j, float (&v)[3]) const {
     const size_t k = static_cast<size_t>(b) * No + e;
     const float* o = other + k * 3;
-    const float* a = self + (static_cast<size_t>(b) * Ns + __ldg(idx_other + k)) * 3;
+    const float* a = self + (static_cast<size_t>(b) * Ns + j) * 3;  // j == idx_other[k]: the destination itself
     const float g = __fmul_rn(__ldg(g_other + k), 2.0f);
     v[0] = -__fmul_rn(g, __ldg(o) - __ldg(a));
     v[1] = -__fmul_rn(g, __ldg(o + 1) - __ldg(a + 1));
@@ -828,14 +1138,10 @@ __global__ void __launch_bounds__(256)
   const int b = blockIdx.y;
   // blockIdx.x < blocks1: destinations are cloud 1's points; else cloud 2's (one grid, both sides)
   const bool first = static_cast<int>(blockIdx.x) < blocks1;
-  float sq;
-  if (first) {
-    ChamferBwdOp op{xyz1, xyz2, idx1, idx2, g1, g2, gx1, b, N, M};
-    sq = ordered_scatter_cta<2>(op, N, s_dst);
-  } else {
-    ChamferBwdOp op{xyz2, xyz1, idx2, idx1, g2, g1, gx2, b, M, N};
-    sq = ordered_scatter_cta<2>(op, M, s_dst, blocks1);
-  }
+  const ChamferBwdOp op{first ? xyz1 : xyz2, first ? xyz2 : xyz1, first ? idx1 : idx2, first ? idx2 : idx1,
+                        first ? g1 : g2,     first ? g2 : g1,     first ? gx1 : gx2,   b,
+                        first ? N : M,       first ? M : N};
+  float sq = ordered_scatter_cta<2>(op, op.Ns, s_dst, first ? 0 : blocks1);
   if (sq_partials == nullptr) return;
   // ---- gradient statistics: sum ||grad||^2 per side.  Fixed-shape block reduction -> one partial per CTA; the CTA that
   //      draws the last ticket adds the partials in CTA order (deterministic whichever CTA that is), then -- batch sharded
@@ -862,7 +1168,13 @@ __global__ void __launch_bounds__(256)
   float loc[4] = {0.f, 0.f, 0.f, 0.f};
   if (threadIdx.x == 0) {  // a few thousand partials at most: one thread, index order
     const volatile float* pp = sq_partials;
-    for (unsigned i = 0; i < ncta; ++i) loc[(i % gridDim.x) < static_cast<unsigned>(blocks1) ? 0 : 1] += pp[i];
+    float s1 = 0.f, s2 = 0.f;
+    for (unsigned i = 0; i < ncta; ++i) {
+      const float v = pp[i];
+      if ((i % gridDim.x) < static_cast<unsigned>(blocks1)) s1 += v; else s2 += v;
+    }
+    loc[0] = s1;
+    loc[1] = s2;
     *ticket = 0u;  // leave the ticket as it was found
   }
   if (px.world > 1) peer_allreduce4(px, loc, s_x);
@@ -901,17 +1213,6 @@ static void launch_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int 
   chamfer_fwd_kernel<R, THREADS><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, dist1, dist2, idx1, idx2);
 }
 
-size_t chamfer_fwd_workspace_bytes(int B, int N, int M) {
-  if (B <= 0 || N <= 0 || M <= 0) return 0;
-  // one 64-bit key per point of either cloud (the column side always merges by key, the row side
-  // when the columns are cut into chunks)
-  const size_t n8 = (static_cast<size_t>(N) + 7) & ~static_cast<size_t>(7);
-  const size_t m8 = (static_cast<size_t>(M) + 7) & ~static_cast<size_t>(7);
-  // + the ticket word (16 B) and one float2 partial per finalize CTA (2 sides x B x ceil(max/256))
-  const size_t ctas = 2 * static_cast<size_t>(B) * ((static_cast<size_t>(N > M ? N : M) + 255) / 256);
-  return static_cast<size_t>(B) * (n8 + m8) * 8 + 16 + ctas * 8;
-}
-
 // Column chunks for the packed kernel.  An SM keeps up to 5 of these CTAs resident and needs several of
 // them (one warp per scheduler each) to keep its FMA pipe fed, so the grid should hold at least one full
 // residency wave (5 x 148 items) and then fill whole waves.  B200 sweep (scripts/time_ops.py
@@ -931,6 +1232,59 @@ static int chamfer_pick_chunks(long items0, int NB, int per_sm = 5) {
     if (eff > best_eff + 0.03) { best_eff = eff; best = c; }  // fewest chunks within 3 % of the best fill
   }
   return best;
+}
+
+static int env_chunks() {
+  const char* v = tuning_env("UPP_CH_CHUNKS");  // tuning aid: force the number of column chunks
+  return v ? atoi(v) : 0;
+}
+
+// Plan of the fused single-kernel path (chamfer_fwd_fused_kernel<8, 4, 16>): rows = the larger cloud, columns = the
+// smaller one cut into chunks; one function serves the workspace query and the launch so that they always agree.
+struct ChFusedPlan {
+  int na, nb, na8, nb8, rowblocks, chunks, chunk;
+  size_t colpart, rowpart, partials, tickets, bytes;  // byte offsets / total
+};
+constexpr int kFusedR = 8, kFusedWC = 4, kFusedCG = 16;
+constexpr size_t kFusedWorkspaceCap = static_cast<size_t>(512) << 20;  // beyond this the keyed two-launch path runs
+
+static ChFusedPlan chamfer_fused_plan(int B, int N, int M) {
+  ChFusedPlan p;
+  p.na = N >= M ? N : M;
+  p.nb = N >= M ? M : N;
+  p.na8 = (p.na + 15) & ~15;
+  p.nb8 = (p.nb + 15) & ~15;  // column slots are written in whole groups of kFusedCG
+  p.rowblocks = (p.na + 32 * kFusedR - 1) / (32 * kFusedR);
+  const int fc = env_chunks();
+  int chunks = fc > 0 ? fc : chamfer_pick_chunks(static_cast<long>(B) * p.rowblocks, p.nb, 5);
+  p.chunk = ((p.nb + chunks - 1) / chunks + 63) & ~63;
+  p.chunks = (p.nb + p.chunk - 1) / p.chunk;
+  const size_t slots = static_cast<size_t>(B) * (p.rowblocks + p.chunks);
+  p.colpart = 0;
+  p.rowpart = p.colpart + static_cast<size_t>(B) * p.rowblocks * p.nb8 * 8;
+  p.partials = p.rowpart + (p.chunks > 1 ? static_cast<size_t>(B) * p.chunks * p.na8 * 8 : 0);
+  p.tickets = p.partials + slots * 8;
+  p.bytes = p.tickets + (slots + 4) * 4;
+  p.bytes = (p.bytes + 15) & ~static_cast<size_t>(15);
+  return p;
+}
+
+static size_t chamfer_keyed_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  // one 64-bit key per point of either cloud (the column side always merges by key, the row side
+  // when the columns are cut into chunks)
+  const size_t n8 = (static_cast<size_t>(N) + 7) & ~static_cast<size_t>(7);
+  const size_t m8 = (static_cast<size_t>(M) + 7) & ~static_cast<size_t>(7);
+  // + the ticket word (16 B) and one float2 partial per finalize CTA (2 sides x B x ceil(max/256))
+  const size_t ctas = 2 * static_cast<size_t>(B) * ((static_cast<size_t>(N > M ? N : M) + 255) / 256);
+  return static_cast<size_t>(B) * (n8 + m8) * 8 + 16 + ctas * 8;
+}
+
+size_t chamfer_fwd_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  const size_t keyed = chamfer_keyed_workspace_bytes(B, N, M);
+  const size_t fused = chamfer_fused_plan(B, N, M).bytes;
+  return fused <= kFusedWorkspaceCap && fused > keyed ? fused : keyed;
 }
 
 template <int R, int WC, int MINB = 0>
@@ -983,9 +1337,29 @@ static int launch_chamfer_both(const float* a, const float* bpts, int B, int NA,
   return UPP_OK;
 }
 
-static int env_chunks() {
-  const char* v = tuning_env("UPP_CH_CHUNKS");  // tuning aid: force the number of column chunks
-  return v ? atoi(v) : 0;
+
+// The fused single-kernel forward: tickets zeroed (a few KB), then ONE launch.
+static int launch_chamfer_fused(const float* a, const float* bpts, int B, const ChFusedPlan& p, float* dA, int32_t* iA,
+                                float* dB, int32_t* iB, void* ws, float* sums, bool swapped, const PeerXchg& px,
+                                cudaStream_t st) {
+  char* w = static_cast<char*>(ws);
+  ChFused f;
+  f.xyzA = a; f.xyzB = bpts;
+  f.NA = p.na; f.NB = p.nb; f.NA8 = p.na8; f.NB8 = p.nb8; f.chunk = p.chunk; f.nchunks = p.chunks; f.RB = p.rowblocks;
+  f.distA = dA; f.idxA = iA; f.distB = dB; f.idxB = iB;
+  f.colpart = reinterpret_cast<uint2*>(w + p.colpart);
+  f.rowpart = reinterpret_cast<uint2*>(w + p.rowpart);
+  f.partials = reinterpret_cast<float2*>(w + p.partials);
+  f.tickets = reinterpret_cast<unsigned*>(w + p.tickets);
+  f.sums = sums;
+  f.swapped = swapped ? 1 : 0;
+  const size_t slots = static_cast<size_t>(B) * (p.rowblocks + p.chunks);
+  cudaError_t e = cudaMemsetAsync(f.tickets, 0, (slots + 4) * 4, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  dim3 grid(p.rowblocks, B, p.chunks);
+  chamfer_fwd_fused_kernel<kFusedR, kFusedWC, kFusedCG><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+  count_launch();
+  return launch_status();
 }
 
 int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M, float* dist1,
@@ -1010,8 +1384,12 @@ int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M
     int32_t* iA = swap ? idx2 : idx1; int32_t* iB = swap ? idx1 : idx2;
     const long ctas8 = static_cast<long>(B) * ((na + 255) / 256);
     int rc;
-    // default: the packed kernel; 20..22 = the scalar single-pass kernel (A/B timing)
-    int pick = variant >= 20 ? variant : 30;
+    const ChFusedPlan plan = chamfer_fused_plan(B, N, M);
+    const bool fused_ok = plan.bytes <= kFusedWorkspaceCap && workspace_bytes >= plan.bytes && B <= 65535;
+    // default: the fused single-kernel path; 30 = the keyed two-launch packed path (round 1; also the fallback when the
+    // partial slots would not fit the workspace cap); 20..22 = the scalar single-pass kernel (A/B timing)
+    int pick = variant >= 20 ? variant : (fused_ok ? 50 : 30);
+    if (pick == 50 && !fused_ok) pick = 30;
     const int fc = env_chunks();
     (void)ctas8;
     switch (pick) {
@@ -1029,6 +1407,7 @@ int chamfer_fwd_launch(const float* xyz1, const float* xyz2, int B, int N, int M
       case 38: rc = launch_chamfer_packed<8, 4, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
       case 39: rc = launch_chamfer_packed<8, 4, 3>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
       case 40: rc = launch_chamfer_packed<8, 8, 3>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
+      case 50: rc = launch_chamfer_fused(a, c, B, plan, dA, iA, dB, iB, workspace, sums, swap, px, st); break;
       default: rc = launch_chamfer_packed<8, 4>(a, c, B, na, nb, dA, iA, dB, iB, workspace, fc, sums, swap, px, st); break;
     }
     if (rc != UPP_OK) return rc;
@@ -1078,7 +1457,9 @@ int chamfer_bwd_launch(const float* xyz1, const float* xyz2, const int32_t* idx1
   const ScatterGrid a = scatter_grid(N, M, 2), c = scatter_grid(M, N, 2);
   const int warps = a.warps > c.warps ? a.warps : c.warps;
   const int blocks1 = (N + warps * 64 - 1) / (warps * 64), blocks2 = (M + warps * 64 - 1) / (warps * 64);
-  const size_t smem = a.smem > c.smem ? a.smem : c.smem;
+  const int lmax = N > M ? N : M;  // the longer list sizes the staging area for both sides
+  const size_t smem = static_cast<size_t>(((lmax < kScatterTile ? lmax : kScatterTile) + 3) & ~3) * sizeof(int) +
+                      static_cast<size_t>(warps) * kScatterWarpBytes;
   unsigned* ticket = nullptr;
   float* partials = nullptr;
   if (sq_out != nullptr) {

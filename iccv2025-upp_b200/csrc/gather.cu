@@ -31,7 +31,7 @@ struct GatherGradOp {
   int b, c0, C, N, M;
   __device__ __forceinline__ int entries() const { return M; }
   __device__ __forceinline__ int dst(int e) const { return __ldg(idx + static_cast<size_t>(b) * M + e); }
-  __device__ __forceinline__ void fetch(int e, float (&v)[3]) const {
+  __device__ __forceinline__ void fetch(int e, int, float (&v)[3]) const {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       if (c0 + c < C) v[c] = __ldg(gout + (static_cast<size_t>(b) * C + c0 + c) * M + e);
@@ -84,7 +84,7 @@ struct GroupBwdOp {
     const int nk = G * k;
     return e < nk ? static_cast<int>(idx[static_cast<size_t>(b) * nk + e]) : __ldg(cidx + static_cast<size_t>(b) * G + (e - nk));
   }
-  __device__ __forceinline__ void fetch(int e, float (&v)[3]) const {
+  __device__ __forceinline__ void fetch(int e, int, float (&v)[3]) const {
     const int nk = G * k;
     if (e < nk) {
       const float* p = gnb + (static_cast<size_t>(b) * nk + e) * 3;
@@ -129,7 +129,7 @@ struct RowsScatterOp {
   int b, c0, C, N, M;
   __device__ __forceinline__ int entries() const { return M; }
   __device__ __forceinline__ int dst(int e) const { return __ldg(idx + static_cast<size_t>(b) * M + e); }
-  __device__ __forceinline__ void fetch(int e, float (&v)[3]) const {
+  __device__ __forceinline__ void fetch(int e, int, float (&v)[3]) const {
     const float* p = rows + (static_cast<size_t>(b) * M + e) * C + c0;
 #pragma unroll
     for (int c = 0; c < 3; ++c)

@@ -123,8 +123,10 @@ __global__ void __launch_bounds__(kGroupMaxThreads, 1)
     }
   } else {
     // ---- consumers: kNN + gather - centre for the centres as they appear ----
+    // consumer ids interleave the CTAs (consecutive centres go to different SMs): the last centres -- the ones whose
+    // kNN nothing overlaps any more -- then spread over all consumer SMs instead of queueing on one
     const int nc = cw0 + (static_cast<int>(cs) - 1) * W;
-    const int c = rank == 0 ? warp - NW : cw0 + (static_cast<int>(rank) - 1) * W + warp;
+    const int c = rank == 0 ? warp - NW : cw0 + warp * (static_cast<int>(cs) - 1) + (static_cast<int>(rank) - 1);
     if (c < nc && (rank != 0 || warp - NW < cw0)) {
       for (int j = c; j < G; j += nc) {
         int ci;

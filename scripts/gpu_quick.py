@@ -1,0 +1,82 @@
+"""Quick per-op timings on the GPU box (CUDA-graph replay, CUDA events): the ops changed in round 2, with their A/B switches."""
+import os
+import sys
+os.environ.setdefault("UPP_TUNING", "1")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "iccv2025-upp_b200"), ROOT):
+    sys.path.insert(0, p)
+import json  # noqa: E402
+import statistics  # noqa: E402
+import torch  # noqa: E402
+import upp_b200  # noqa: E402
+
+o = upp_b200.ops
+dev = torch.device("cuda:0")
+
+
+def timeit(fn, reps=20, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    ts = []
+    for it in range(iters + 3):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(s.elapsed_time(e) / reps * 1e3)
+    return round(statistics.median(ts), 2)
+
+
+def rec(name, us, **kw):
+    print(json.dumps(dict(op=name, us=us, **kw)), flush=True)
+
+
+def env(**kw):
+    for k, v in kw.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = str(v)
+
+
+g = torch.Generator().manual_seed(0)
+# Group: fused (cluster shapes) vs two launches
+for B, N, G, k in ((32, 1024, 64, 32), (128, 1024, 64, 32), (32, 2048, 128, 32), (32, 1096, 32, 16), (32, 64, 32, 8), (64, 1024, 64, 32), (16, 1024, 64, 32)):
+    x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+    for tag, kw in (("default", {}), ("two_launch", dict(UPP_GROUP_FUSED=0)), ("cs1", dict(UPP_GROUP_CLUSTER=1)), ("cs2", dict(UPP_GROUP_CLUSTER=2)),
+                    ("cs4", dict(UPP_GROUP_CLUSTER=4)), ("cs8_w8", dict(UPP_GROUP_CLUSTER=8, UPP_GROUP_WARPS=8)), ("cs4_w8", dict(UPP_GROUP_CLUSTER=4, UPP_GROUP_WARPS=8))):
+        env(**kw)
+        try:
+            rec(f"group B{B} N{N} G{G} k{k} [{tag}]", timeit(lambda: o.group(x, G, k)))
+        except Exception as ex:  # noqa: BLE001
+            rec(f"group B{B} N{N} G{G} k{k} [{tag}]", None, error=str(ex)[:80])
+        env(**{kk: None for kk in kw})
+# Chamfer forward: fused vs keyed, chunk choices
+for B, N, M in ((64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 32, 1024)):
+    a, b = torch.rand(B, N, 3, generator=g).to(dev), torch.rand(B, M, 3, generator=g).to(dev)
+    for tag, kw in (("fused", {}), ("keyed", dict(UPP_CH_VARIANT=30)), ("fused_c1", dict(UPP_CH_CHUNKS=1)), ("fused_c2", dict(UPP_CH_CHUNKS=2)),
+                    ("fused_c3", dict(UPP_CH_CHUNKS=3)), ("fused_c6", dict(UPP_CH_CHUNKS=6)), ("fused_c8", dict(UPP_CH_CHUNKS=8))):
+        env(**kw)
+        rec(f"chamfer_fwd B{B} {N}x{M} +sums [{tag}]", timeit(lambda: o.chamfer_forward(a, b, want_sums=True)))
+        env(**{kk: None for kk in kw})
+    d1, d2, i1, i2 = o.chamfer_forward(a, b)
+    g1, g2 = torch.rand_like(d1), torch.rand_like(d2)
+    rec(f"chamfer_bwd B{B} {N}x{M}", timeit(lambda: o.chamfer_backward(a, b, i1, i2, g1, g2)))
+    rec(f"chamfer_bwd+stats B{B} {N}x{M}", timeit(lambda: o.chamfer_backward(a, b, i1, i2, g1, g2, want_sqnorm=True)))
+# scatter-add backward kernels
+for B, N, G, k in ((32, 1024, 64, 32), (32, 64, 32, 8), (32, 2048, 128, 32)):
+    x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
+    nb, ce, idx, cidx = o.group(x, G, k)
+    gnb, gce = torch.randn_like(nb), torch.randn_like(ce)
+    rec(f"group_bwd B{B} N{N} G{G} k{k}", timeit(lambda: o.group_backward(gnb, gce, idx, cidx, N)))
+for B, N, M in ((32, 1228, 1024), (32, 1024, 256), (128, 8192, 1024)):
+    rows = torch.randn(B, M, 3, generator=g).to(dev)
+    idx = torch.stack([torch.randperm(N, generator=g)[:M] for _ in range(B)]).to(torch.int32).to(dev)
+    rec(f"rows_scatter_add B{B} N{N} M{M}", timeit(lambda: o.rows_scatter_add(rows, idx, N)))

@@ -246,10 +246,14 @@ CH_SHAPES = [  # (B, N, M)
 
 
 CH_KERNELS = {  # name -> tuning environment (read per launch by chamfer_fwd_launch)
-    "packed": {},                                                   # default: packed single pass, heuristic chunks
-    "packed_1chunk": {"UPP_CH_CHUNKS": "1"},                        # rows written directly
-    "packed_3chunks": {"UPP_CH_CHUNKS": "3"},                       # row side merged by key too
-    "packed_many_chunks": {"UPP_CH_CHUNKS": "32"},
+    "fused": {},                                                    # default: single kernel (partials + in-kernel finalize), heuristic chunks
+    "fused_1chunk": {"UPP_CH_CHUNKS": "1"},                         # rows resolved directly by the CTA that scanned them
+    "fused_3chunks": {"UPP_CH_CHUNKS": "3"},                        # row side through per-chunk partials too
+    "fused_many_chunks": {"UPP_CH_CHUNKS": "32"},
+    "packed": {"UPP_CH_VARIANT": "30"},                             # round-1 path: memset + packed kernel (RED.MIN keys) + finalize launch
+    "packed_1chunk": {"UPP_CH_VARIANT": "30", "UPP_CH_CHUNKS": "1"},
+    "packed_3chunks": {"UPP_CH_VARIANT": "30", "UPP_CH_CHUNKS": "3"},
+    "packed_many_chunks": {"UPP_CH_VARIANT": "30", "UPP_CH_CHUNKS": "32"},
     "packed_r4": {"UPP_CH_VARIANT": "31", "UPP_CH_CHUNKS": "2"},
     "packed_r6": {"UPP_CH_VARIANT": "33"},
     "packed_w8": {"UPP_CH_VARIANT": "32"},
