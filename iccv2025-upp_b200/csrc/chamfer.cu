@@ -767,7 +767,7 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* s_w) {
   return r;  // valid in thread 0
 }
 
-template <int R, int WC, int CG, int MINB = 0>
+template <int R, int WC, int CG, int MINB = 0, bool FOLD = true>
 __global__ void __launch_bounds__(WC * 32, MINB)
     chamfer_fwd_fused_kernel(const ChFused a, const PeerXchg px) {
   static_assert(R % 2 == 0 && R <= 16, "rows are processed in packed pairs; the finalize scans at most 16 rows");
@@ -911,14 +911,22 @@ __global__ void __launch_bounds__(WC * 32, MINB)
     ss += __fsqrt_rn(bb);
   }
 
+  if constexpr (!FOLD) {
+    // two-kernel form: chamfer_finalize3_kernel (next launch) resolves the partials and produces the sums; it counts its
+    // own CTAs with tickets[0], zeroed here (this kernel is complete before that one starts)
+    if (t == 0 && rb == 0 && b == 0 && z == 0) a.tickets[0] = 0u;
+    return;
+  }
   // ---- tickets: am I the last contributor to this row block (over chunks) / to this column chunk (over row blocks)? ----
   const unsigned slots = static_cast<unsigned>(a.RB + a.nchunks);
   unsigned* tk = a.tickets + static_cast<size_t>(b) * slots;
-  __threadfence();   // this CTA's partial stores are visible device-wide before its tickets are drawn
-  __syncthreads();
+  __syncthreads();  // every thread's partial stores are ordered before thread 0's fence (cumulative) ...
   if (t == 0) {
-    s_flags[0] = direct ? 1 : (atomicAdd(tk + rb, 1u) + 1u == static_cast<unsigned>(a.nchunks));
-    s_flags[1] = (atomicAdd(tk + a.RB + z, 1u) + 1u == static_cast<unsigned>(a.RB));
+    __threadfence();  // ... which makes them visible device-wide before the tickets are drawn: one fence per CTA, not 128
+    const unsigned r0 = direct ? 0u : atomicAdd(tk + rb, 1u);   // two independent round trips, issued back to back
+    const unsigned r1 = atomicAdd(tk + a.RB + z, 1u);
+    s_flags[0] = direct ? 1 : (r0 + 1u == static_cast<unsigned>(a.nchunks));
+    s_flags[1] = (r1 + 1u == static_cast<unsigned>(a.RB));
     __threadfence();
   }
   __syncthreads();
@@ -1146,7 +1154,7 @@ __global__ void __launch_bounds__(256)
   // ---- gradient statistics: sum ||grad||^2 per side.  Fixed-shape block reduction -> one partial per CTA; the CTA that
   //      draws the last ticket adds the partials in CTA order (deterministic whichever CTA that is), then -- batch sharded
   //      over GPUs -- all-reduces the two sums over NVLink peer memory like the forward's loss sums. ----
-  __shared__ float s_w[8];
+  __shared__ float s_w[8], s_w2[8];
   __shared__ bool s_last;
   __shared__ float s_x[1 + UPP_MAX_PEERS][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1165,22 +1173,126 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // fixed partition (thread t takes partials t, t + blockDim, ...) and a fixed-shape block sum: deterministic
+  float s1 = 0.f, s2 = 0.f;
+  for (unsigned i = threadIdx.x; i < ncta; i += blockDim.x) {
+    const float v = __ldcg(sq_partials + i);
+    if ((i % gridDim.x) < static_cast<unsigned>(blocks1)) s1 += v; else s2 += v;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  __syncthreads();
+  if (lane == 0) { s_w[warp] = s1; s_w2[warp] = s2; }
+  __syncthreads();
   float loc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (threadIdx.x == 0) {  // a few thousand partials at most: one thread, index order
-    const volatile float* pp = sq_partials;
-    float s1 = 0.f, s2 = 0.f;
-    for (unsigned i = 0; i < ncta; ++i) {
-      const float v = pp[i];
-      if ((i % gridDim.x) < static_cast<unsigned>(blocks1)) s1 += v; else s2 += v;
-    }
-    loc[0] = s1;
-    loc[1] = s2;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < nwarps; ++w) { loc[0] += s_w[w]; loc[1] += s_w2[w]; }
     *ticket = 0u;  // leave the ticket as it was found
   }
   if (px.world > 1) peer_allreduce4(px, loc, s_x);
   if (threadIdx.x == 0) {
     sq_out[0] = loc[0];
     sq_out[1] = loc[1];
+  }
+}
+
+// Second (and last) launch of the two-kernel form of the partial-slot path: one thread per point.
+//   blockIdx.z == 0 : columns (cloud B): minimum over the RB row-block partials {ballot, bits} (strict '<' in ascending
+//                     row-block order), arg-min among the R rows of the lowest lane holding it;
+//   blockIdx.z == 1 : rows (cloud A): minimum over the chunk partials {group base, bits}, arg-min among the CG columns of
+//                     the winning group -- or, with one chunk, distA as the main kernel wrote it (sums only).
+// Sums and the fused all-reduce exactly as chamfer_finalize2_kernel (ticketed last CTA, fixed order, peer_allreduce4).
+template <int R, int CG>
+__global__ void __launch_bounds__(256)
+    chamfer_finalize3_kernel(const ChFused a, const PeerXchg px) {
+  __shared__ float2 s_w[8];
+  __shared__ bool s_last;
+  __shared__ float s_x[1 + UPP_MAX_PEERS][4];
+  constexpr int ROWS = 32 * R;
+  const int side = blockIdx.z;  // 0: B (columns), 1: A (rows)
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NA = a.NA, NB = a.NB;
+  const float* ap = a.xyzA + static_cast<size_t>(b) * NA * 3;
+  const float* bp = a.xyzB + static_cast<size_t>(b) * NB * 3;
+  float d = 0.f;
+  bool live = false;
+  if (side == 0 && k < NB) {
+    live = true;
+    unsigned bits = 0xffffffffu, mask = 0u;
+    int wrb = 0;
+    for (int rr = 0; rr < a.RB; ++rr) {
+      const uint2 e = __ldg(a.colpart + (static_cast<size_t>(b) * a.RB + rr) * a.NB8 + k);
+      if (e.y < bits) { bits = e.y; mask = e.x; wrb = rr; }
+    }
+    const int j0 = wrb * ROWS + (__ffs(mask) - 1) * R;
+    const float* q = bp + static_cast<size_t>(k) * 3;
+    const float rx = __ldg(q), ry = __ldg(q + 1), rz = __ldg(q + 2);
+    int bi = j0;
+#pragma unroll
+    for (int u = R - 1; u >= 0; --u) {
+      const int j = min(j0 + u, NA - 1);
+      const float* pr = ap + static_cast<size_t>(j) * 3;
+      const float dd = dist_yxz(rx - __ldg(pr), ry - __ldg(pr + 1), rz - __ldg(pr + 2));
+      if (__float_as_uint(dd) == bits && j0 + u < NA) bi = j0 + u;
+    }
+    d = __uint_as_float(bits);
+    a.distB[static_cast<size_t>(b) * NB + k] = d;
+    a.idxB[static_cast<size_t>(b) * NB + k] = bi;
+  } else if (side == 1 && k < NA) {
+    live = true;
+    if (a.nchunks == 1) {
+      d = a.distA[static_cast<size_t>(b) * NA + k];
+    } else {
+      unsigned bits = 0xffffffffu, gg = 0;
+      for (int zz = 0; zz < a.nchunks; ++zz) {
+        const uint2 e = __ldg(a.rowpart + (static_cast<size_t>(b) * a.nchunks + zz) * a.NA8 + k);
+        if (e.y < bits) { bits = e.y; gg = e.x; }
+      }
+      const float px0 = __ldg(ap + 3 * k), py0 = __ldg(ap + 3 * k + 1), pz0 = __ldg(ap + 3 * k + 2);
+      int bi = static_cast<int>(gg);
+#pragma unroll
+      for (int u = CG - 1; u >= 0; --u) {
+        const int kcol = min(static_cast<int>(gg) + u, NB - 1);
+        const float* q = bp + static_cast<size_t>(kcol) * 3;
+        const float dd = dist_yxz(__ldg(q) - px0, __ldg(q + 1) - py0, __ldg(q + 2) - pz0);
+        if (__float_as_uint(dd) == bits && static_cast<int>(gg) + u < NB) bi = static_cast<int>(gg) + u;
+      }
+      d = __uint_as_float(bits);
+      a.distA[static_cast<size_t>(b) * NA + k] = d;
+      a.idxA[static_cast<size_t>(b) * NA + k] = bi;
+    }
+  }
+  if (a.sums == nullptr) return;
+  const unsigned per_side = gridDim.x * gridDim.y;
+  const unsigned cta = side * per_side + blockIdx.y * gridDim.x + blockIdx.x;
+  const float2 part = block_sum2_256(d, live ? __fsqrt_rn(d) : 0.f, s_w);
+  if (threadIdx.x == 0) {
+    a.partials[cta] = part;
+    __threadfence();
+    s_last = (atomicAdd(a.tickets, 1u) + 1u == per_side * gridDim.z);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float2 side_sum[2];
+#pragma unroll
+  for (int sd = 0; sd < 2; ++sd) {
+    float a0 = 0.f, a1 = 0.f;
+    const volatile float2* pp = a.partials + sd * per_side;
+    for (unsigned i = threadIdx.x; i < per_side; i += 256) {
+      a0 += pp[i].x;
+      a1 += pp[i].y;
+    }
+    side_sum[sd] = block_sum2_256(a0, a1, s_w);  // (valid in thread 0)
+  }
+  // side 1 = cloud A = the caller's xyz1 unless the clouds were swapped; output { d1, d2, sqrt d1, sqrt d2 }
+  const float2 s1 = a.swapped ? side_sum[0] : side_sum[1], s2 = a.swapped ? side_sum[1] : side_sum[0];
+  float loc[4] = {s1.x, s2.x, s1.y, s2.y};
+  if (px.world > 1) peer_allreduce4(px, loc, s_x);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a.sums[q] = loc[q];
   }
 }
 
@@ -1263,7 +1375,8 @@ static ChFusedPlan chamfer_fused_plan(int B, int N, int M) {
   p.colpart = 0;
   p.rowpart = p.colpart + static_cast<size_t>(B) * p.rowblocks * p.nb8 * 8;
   p.partials = p.rowpart + (p.chunks > 1 ? static_cast<size_t>(B) * p.chunks * p.na8 * 8 : 0);
-  p.tickets = p.partials + slots * 8;
+  const size_t fin_ctas = 2 * static_cast<size_t>(B) * ((static_cast<size_t>(p.na) + 255) / 256);  // two-kernel form
+  p.tickets = p.partials + (slots > fin_ctas ? slots : fin_ctas) * 8;
   p.bytes = p.tickets + (slots + 4) * 4;
   p.bytes = (p.bytes + 15) & ~static_cast<size_t>(15);
   return p;
@@ -1354,10 +1467,37 @@ static int launch_chamfer_fused(const float* a, const float* bpts, int B, const 
   f.sums = sums;
   f.swapped = swapped ? 1 : 0;
   const size_t slots = static_cast<size_t>(B) * (p.rowblocks + p.chunks);
-  cudaError_t e = cudaMemsetAsync(f.tickets, 0, (slots + 4) * 4, st);
-  if (e != cudaSuccess) return static_cast<int>(e);
+  if (tuning_env_int("UPP_CH_FUSED", 0) >= 1 && tuning_env_int("UPP_CH_FUSED", 0) <= 4) {  // folded forms count contributors
+    cudaError_t e = cudaMemsetAsync(f.tickets, 0, (slots + 4) * 4, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   dim3 grid(p.rowblocks, B, p.chunks);
-  chamfer_fwd_fused_kernel<kFusedR, kFusedWC, kFusedCG><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+  // default: the two-kernel form (distance kernel without an epilogue, then one finalize launch at full occupancy).
+  // Folding the finalize into the distance kernel (tickets, last contributor resolves) was built and measured slower:
+  // its CTAs hold their SM slots through latency-bound tails (B64 2048^2 + sums: keyed 92.3 us, folded 97-112 us,
+  // two-kernel slots 88-92 us; profiles/r02_quick_ops.jsonl).  UPP_CH_FUSED: 1 = folded cg8 6 CTAs/SM, 2 = folded cg16
+  // 5/SM, 3 = folded cg8 5/SM, 4 = folded cg16 6/SM, 5 = two-kernel cg16, 6 = two-kernel cg8 capped for 6/SM (tuning / tests).
+  const int v = tuning_env_int("UPP_CH_FUSED", 0);
+  const bool fold = v >= 1 && v <= 4;
+  if (fold) {
+    if (v == 1) chamfer_fwd_fused_kernel<kFusedR, kFusedWC, 8, 6><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+    else if (v == 2) chamfer_fwd_fused_kernel<kFusedR, kFusedWC, 16, 0><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+    else if (v == 3) chamfer_fwd_fused_kernel<kFusedR, kFusedWC, 8, 0><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+    else chamfer_fwd_fused_kernel<kFusedR, kFusedWC, 16, 6><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+    count_launch();
+    return launch_status();
+  }
+  const int cg = v == 5 ? 16 : 8;
+  if (v == 5) chamfer_fwd_fused_kernel<kFusedR, kFusedWC, 16, 6, false><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+  else if (v == 6) chamfer_fwd_fused_kernel<kFusedR, kFusedWC, 8, 6, false><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+  else chamfer_fwd_fused_kernel<kFusedR, kFusedWC, 8, 0, false><<<grid, kFusedWC * 32, 0, st>>>(f, px);
+  count_launch();
+  int rc = launch_status();
+  if (rc != UPP_OK) return rc;
+  const bool rows_too = p.chunks > 1 || sums != nullptr;
+  dim3 fgrid(((rows_too ? p.na : p.nb) + 255) / 256, B, rows_too ? 2 : 1);
+  if (cg == 16) chamfer_finalize3_kernel<kFusedR, 16><<<fgrid, 256, 0, st>>>(f, px);
+  else chamfer_finalize3_kernel<kFusedR, 8><<<fgrid, 256, 0, st>>>(f, px);
   count_launch();
   return launch_status();
 }
@@ -1458,8 +1598,7 @@ int chamfer_bwd_launch(const float* xyz1, const float* xyz2, const int32_t* idx1
   const int warps = a.warps > c.warps ? a.warps : c.warps;
   const int blocks1 = (N + warps * 64 - 1) / (warps * 64), blocks2 = (M + warps * 64 - 1) / (warps * 64);
   const int lmax = N > M ? N : M;  // the longer list sizes the staging area for both sides
-  const size_t smem = static_cast<size_t>(((lmax < kScatterTile ? lmax : kScatterTile) + 3) & ~3) * sizeof(int) +
-                      static_cast<size_t>(warps) * kScatterWarpBytes;
+  const size_t smem = scatter_smem(lmax, warps, 2);
   unsigned* ticket = nullptr;
   float* partials = nullptr;
   if (sq_out != nullptr) {

@@ -93,8 +93,15 @@ struct GroupBwdOp {
       const int g = e - nk;
       const float* p = gnb + (static_cast<size_t>(b) * G + g) * k * 3;
       float sx = 0.f, sy = 0.f, sz = 0.f;
-      for (int j = 0; j < k; ++j) {
-        sx = __fadd_rn(sx, __ldg(p + 3 * j)); sy = __fadd_rn(sy, __ldg(p + 3 * j + 1)); sz = __fadd_rn(sz, __ldg(p + 3 * j + 2));
+      for (int j0 = 0; j0 < k; j0 += 8) {  // 24 independent loads in flight, then the adds in j order
+        float t[8][3];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) t[u][c] = j0 + u < k ? __ldg(p + 3 * (j0 + u) + c) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (j0 + u < k) { sx = __fadd_rn(sx, t[u][0]); sy = __fadd_rn(sy, t[u][1]); sz = __fadd_rn(sz, t[u][2]); }
       }
       v[0] = -sx; v[1] = -sy; v[2] = -sz;
       if (gcenter) {

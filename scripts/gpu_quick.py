@@ -61,8 +61,11 @@ for B, N, G, k in ((32, 1024, 64, 32), (128, 1024, 64, 32), (32, 2048, 128, 32),
 # Chamfer forward: fused vs keyed, chunk choices
 for B, N, M in ((64, 2048, 2048), (32, 1024, 1024), (64, 2048, 8192), (64, 32, 1024)):
     a, b = torch.rand(B, N, 3, generator=g).to(dev), torch.rand(B, M, 3, generator=g).to(dev)
-    for tag, kw in (("fused", {}), ("keyed", dict(UPP_CH_VARIANT=30)), ("fused_c1", dict(UPP_CH_CHUNKS=1)), ("fused_c2", dict(UPP_CH_CHUNKS=2)),
-                    ("fused_c3", dict(UPP_CH_CHUNKS=3)), ("fused_c6", dict(UPP_CH_CHUNKS=6)), ("fused_c8", dict(UPP_CH_CHUNKS=8))):
+    for tag, kw in (("slots", {}), ("keyed", dict(UPP_CH_VARIANT=30)), ("folded cg8 6/SM", dict(UPP_CH_FUSED=1)), ("slots cg16", dict(UPP_CH_FUSED=5)),
+                    ("slots cg8 5/SM", dict(UPP_CH_FUSED=6)), ("slots_c1", dict(UPP_CH_CHUNKS=1)), ("slots_c2", dict(UPP_CH_CHUNKS=2)),
+                    ("slots_c3", dict(UPP_CH_CHUNKS=3)), ("slots_c4", dict(UPP_CH_CHUNKS=4)), ("slots_c5", dict(UPP_CH_CHUNKS=5)), ("slots_c6", dict(UPP_CH_CHUNKS=6)),
+                    ("slots_c8", dict(UPP_CH_CHUNKS=8)), ("slots cg8 5/SM c4", dict(UPP_CH_FUSED=6, UPP_CH_CHUNKS=4)),
+                    ("slots cg16 c4", dict(UPP_CH_FUSED=5, UPP_CH_CHUNKS=4))):
         env(**kw)
         rec(f"chamfer_fwd B{B} {N}x{M} +sums [{tag}]", timeit(lambda: o.chamfer_forward(a, b, want_sums=True)))
         env(**{kk: None for kk in kw})

@@ -16,6 +16,14 @@ for _ in range(4):
         a, b = torch.rand(64, 2048, 3, generator=g).to(dev), torch.rand(64, 2048, 3, generator=g).to(dev)
         out = ops.chamfer_forward(a, b)
         ops.chamfer_backward(a, b, out[2], out[3], torch.rand_like(out[0]), torch.rand_like(out[1]))
+    elif what == "chamfer_bwd_small":  # Completion-Prompter training shape 32 predicted vs 1024 (runner_pretask.py:220)
+        a, b = torch.rand(64, 32, 3, generator=g).to(dev), torch.rand(64, 1024, 3, generator=g).to(dev)
+        out = ops.chamfer_forward(a, b)
+        ops.chamfer_backward(a, b, out[2], out[3], torch.rand_like(out[0]), torch.rand_like(out[1]))
+    elif what == "group":  # C1: single-launch Group + its backward
+        x = (torch.rand(32, 1024, 3, generator=g) * 2 - 1).to(dev)
+        nb, ce, idx, cidx = ops.group(x, 64, 32)
+        ops.group_backward(torch.randn_like(nb), torch.randn_like(ce), idx, cidx, 1024)
     elif what == "fps":
         ops.fps((torch.rand(32, 1228, 3, generator=g) * 2 - 1).to(dev), 1024)
     elif what == "fps8k":

@@ -246,10 +246,16 @@ CH_SHAPES = [  # (B, N, M)
 
 
 CH_KERNELS = {  # name -> tuning environment (read per launch by chamfer_fwd_launch)
-    "fused": {},                                                    # default: single kernel (partials + in-kernel finalize), heuristic chunks
-    "fused_1chunk": {"UPP_CH_CHUNKS": "1"},                         # rows resolved directly by the CTA that scanned them
-    "fused_3chunks": {"UPP_CH_CHUNKS": "3"},                        # row side through per-chunk partials too
-    "fused_many_chunks": {"UPP_CH_CHUNKS": "32"},
+    "slots": {},                                                    # default: plain-store partial slots (no atomics, no memset) + one finalize launch
+    "slots_1chunk": {"UPP_CH_CHUNKS": "1"},                         # rows resolved directly by the CTA that scanned them
+    "slots_3chunks": {"UPP_CH_CHUNKS": "3"},                        # row side through per-chunk partials too
+    "slots_many_chunks": {"UPP_CH_CHUNKS": "32"},
+    "slots_cg16": {"UPP_CH_FUSED": "5", "UPP_CH_CHUNKS": "3"},      # row-side groups of 16 columns
+    "slots_cg8_5persm": {"UPP_CH_FUSED": "6"},
+    "folded": {"UPP_CH_FUSED": "1"},                                # finalize + sums folded into the distance kernel (tickets)
+    "folded_1chunk": {"UPP_CH_FUSED": "4", "UPP_CH_CHUNKS": "1"},
+    "folded_3chunks": {"UPP_CH_FUSED": "2", "UPP_CH_CHUNKS": "3"},
+    "folded_many_chunks": {"UPP_CH_FUSED": "3", "UPP_CH_CHUNKS": "32"},
     "packed": {"UPP_CH_VARIANT": "30"},                             # round-1 path: memset + packed kernel (RED.MIN keys) + finalize launch
     "packed_1chunk": {"UPP_CH_VARIANT": "30", "UPP_CH_CHUNKS": "1"},
     "packed_3chunks": {"UPP_CH_VARIANT": "30", "UPP_CH_CHUNKS": "3"},
