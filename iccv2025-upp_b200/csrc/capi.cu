@@ -78,6 +78,7 @@ int group_gather_launch(const float*, const float*, const int64_t*, int, int, in
 int rows_scatter_add_launch(const float*, const int32_t*, int, int, int, int, float*, cudaStream_t);
 int group_bwd_launch(const float*, const float*, const int64_t*, const int32_t*, int, int, int, int,
                      float*, cudaStream_t);
+int crop_split_launch(const float*, const float*, int, int, int, int, float*, float*, int32_t*, cudaStream_t);
 int group_fused_launch(const float*, int, int, int, int, float*, float*, int64_t*, int32_t*, cudaStream_t);
 
 int knn_points_launch(const float*, const float*, int, int, int, int, float*, int64_t*, float*, cudaStream_t);
@@ -289,6 +290,16 @@ int upp_group_bwd_f32(const float* grad_nb, const float* grad_center, const int6
   UPP_REQUIRE(grad_xyz != nullptr);
   UPP_REQUIRE(static_cast<size_t>(B) * G == 0 || (grad_nb && idx && center_idx));
   return group_bwd_launch(grad_nb, grad_center, idx, center_idx, B, N, G, k, grad_xyz, S(stream));
+}
+
+int upp_crop_split_f32(const float* xyz, const float* viewpoints, int B, int n, int num_crop, int padding_zeros,
+                       float* crop_out, float* input_out, int32_t* order_out, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && n >= 0 && num_crop >= 0 && num_crop <= n);
+  if (B == 0 || n == 0) return UPP_OK;
+  UPP_REQUIRE(xyz && viewpoints);
+  UPP_REQUIRE(num_crop == 0 || crop_out);
+  UPP_REQUIRE((padding_zeros ? n : n - num_crop) == 0 || input_out);
+  return crop_split_launch(xyz, viewpoints, B, n, num_crop, padding_zeros ? 1 : 0, crop_out, input_out, order_out, S(stream));
 }
 
 int upp_knn_points_f32(const float* p1, const float* p2, int B, int N1, int N2, int K, float* dist2_out,

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "upp_chamfer_bwd_stats_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp, _vp],
     "upp_group_f32": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "upp_group_bwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "upp_crop_split_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "upp_knn_points_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "upp_interp_fwd_f32": [_vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "upp_interp_bwd_workspace_bytes": [_i, _i, _i, _i, _i],

@@ -5,27 +5,51 @@
   random_dropping       utils/misc.py:308-315    (KITTI fine-tuning: FPS to a random size, zero-padded to 2048)
 
 The reference's seprate_point_cloud walks the batch in a Python loop and, per cloud, sorts the points by
-distance to a random viewpoint, crops, and calls fps() on (1, n - num_crop, 3) and (1, num_crop, 3): 2*B
-one-CTA FPS launches per training step (tools/runner_module.py:131, tools/runner_pretask.py:179,
+distance to a random viewpoint, crops, and calls fps() on (1, n - num_crop, 3) and (1, num_crop, 3): per training step
+B x (norm + argsort + gathers) and 2*B one-CTA FPS launches (tools/runner_module.py:131, tools/runner_pretask.py:179,
 tools/runner_unify_seg.py:212).  num_crop is drawn ONCE per call, so every cloud of the batch has the same two
-lengths: here the sort, the gathers and the two FPS calls run once for the whole batch (two B-CTA launches).
-The random viewpoints are drawn exactly as the reference draws them (one torch.randn(1,1,3) per cloud from the
-CPU generator, random.sample for a list of fixed points), so a seeded run selects the same crops.
+lengths: here the whole batch is ONE crop launch (upp_crop_split_f32: distances, in-shared-memory sort, split, both
+gathers) plus two batched FPS launches.  The random viewpoints are drawn exactly as the reference draws them (one
+torch.randn(1,1,3) per cloud from the CPU generator, random.sample for a list of fixed points), so a seeded run selects
+the same crops; they reach the device in one copy.
 """
 import random
 
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from .modules import fps
 
 __all__ = ["fps", "seprate_point_cloud", "random_dropping"]
 
 
+def _draw_viewpoints(batch, fixed_points=None):
+    """The reference's per-cloud viewpoint draws (utils/misc.py:224-231), in its order, consuming the CPU torch generator
+    and Python's `random` exactly as its loop does -> (batch, 3) float32 on the CPU.  Random viewpoints are normalised
+    in ONE F.normalize over the stacked draws (bit-identical to normalising each draw on its own: the norm is a
+    three-term sum per row either way; tests/test_host.py checks it)."""
+    draws = []
+    for _ in range(batch):
+        if fixed_points is None:
+            draws.append(torch.randn(1, 1, 3))
+        else:
+            if isinstance(fixed_points, list):
+                fixed_point = random.sample(fixed_points, 1)[0]
+            else:
+                fixed_point = fixed_points
+            draws.append(fixed_point.reshape(1, 1, 3).to("cpu", torch.float32))
+    centers = torch.cat(draws, 0)
+    if fixed_points is None:
+        centers = F.normalize(centers, p=2, dim=-1)
+    return centers.reshape(batch, 3)
+
+
 def seprate_point_cloud(xyz, num_points, crop, fixed_points=None, padding_zeros=False, sample_points=1024,
                         incomplete_shape=True):
     """Same signature, return convention and RNG consumption as the reference function:
-    -> (input_data (B, n_in, 3), crop_data (B, n_crop, 3)), both contiguous; (xyz, None) when crop == num_points."""
+    -> (input_data (B, n_in, 3), crop_data (B, n_crop, 3)), both contiguous; (xyz, None) when crop == num_points.
+    xyz must be a CUDA tensor (the reference moves its viewpoints with .cuda(); there is no CPU path here)."""
     _, n, c = xyz.shape
     assert n == num_points
     assert c == 3
@@ -36,30 +60,20 @@ def seprate_point_cloud(xyz, num_points, crop, fixed_points=None, padding_zeros=
     else:
         num_crop = crop
     B = xyz.shape[0]
-    centers = []
-    for _ in range(B):  # per-cloud draws, in the reference's order
-        if fixed_points is None:
-            center = F.normalize(torch.randn(1, 1, 3), p=2, dim=-1)
+    centers = _draw_viewpoints(B, fixed_points).to(xyz.device, non_blocking=True)  # ONE host-to-device copy
+    pts = xyz.contiguous().float()
+    if n <= 8192:
+        input_data, crop_data = ops.crop_split(pts, centers, num_crop, padding_zeros=padding_zeros)
+    else:  # beyond the crop kernel's shared-memory sort: the same computation on torch's CUDA kernels
+        dist = torch.norm(centers.view(B, 1, 1, 3) - pts.unsqueeze(1), p=2, dim=-1)
+        idx = torch.argsort(dist, dim=-1, descending=False, stable=True)[:, 0]
+        take = lambda ix: torch.gather(pts, 1, ix.unsqueeze(-1).expand(-1, -1, 3))  # noqa: E731
+        crop_data = take(idx[:, :num_crop])
+        if padding_zeros:
+            input_data = pts.clone()
+            input_data.scatter_(1, idx[:, :num_crop].unsqueeze(-1).expand(-1, -1, 3), crop_data * 0)
         else:
-            if isinstance(fixed_points, list):
-                fixed_point = random.sample(fixed_points, 1)[0]
-            else:
-                fixed_point = fixed_points
-            center = fixed_point.reshape(1, 1, 3)
-        centers.append(center)
-    if all(c.device.type == "cpu" for c in centers):  # the usual case: ONE host-to-device copy instead of B
-        centers = torch.cat(centers, 0).to(xyz.device, xyz.dtype)                       # (B,1,3)
-    else:
-        centers = torch.cat([c.to(xyz.device, xyz.dtype) for c in centers], 0)
-    distance_matrix = torch.norm(centers.unsqueeze(2) - xyz.unsqueeze(1), p=2, dim=-1)  # (B,1,n)
-    idx = torch.argsort(distance_matrix, dim=-1, descending=False)[:, 0]                # (B,n)
-    take = lambda ix: torch.gather(xyz, 1, ix.unsqueeze(-1).expand(-1, -1, 3))  # noqa: E731
-    crop_data = take(idx[:, :num_crop])
-    if padding_zeros:
-        input_data = xyz.clone()
-        input_data.scatter_(1, idx[:, :num_crop].unsqueeze(-1).expand(-1, -1, 3), 0.0)
-    else:
-        input_data = take(idx[:, num_crop:])
+            input_data = take(idx[:, num_crop:])
     if isinstance(crop, list):
         input_data = fps(input_data, sample_points)[0]
         crop_data = fps(crop_data, sample_points)[0]

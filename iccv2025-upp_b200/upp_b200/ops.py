@@ -340,6 +340,28 @@ def knn_points(p1, p2, K, want_nn=False):
     return d, i, nn
 
 
+def crop_split(xyz, viewpoints, num_crop, padding_zeros=False, want_order=False):
+    """The crop of misc.seprate_point_cloud (utils/misc.py:232-239) for the whole batch in one launch:
+    xyz (B,n,3), viewpoints (B,3) -> (input (B,n-num_crop,3) or (B,n,3) when padding_zeros, crop (B,num_crop,3)[, order (B,n) int32])."""
+    _xyz("xyz", xyz)
+    _need("viewpoints", viewpoints, torch.float32, 2)
+    B, n, _ = xyz.shape
+    if tuple(viewpoints.shape) != (B, 3):
+        raise ValueError(f"viewpoints must be ({B}, 3), got {tuple(viewpoints.shape)}")
+    num_crop = int(num_crop)
+    if not 0 <= num_crop <= n:
+        raise ValueError(f"num_crop={num_crop} must be in [0, n={n}]")
+    dev = xyz.device
+    crop = torch.empty((B, num_crop, 3), dtype=torch.float32, device=dev)
+    inp = torch.empty((B, n if padding_zeros else n - num_crop, 3), dtype=torch.float32, device=dev)
+    order = torch.empty((B, n), dtype=torch.int32, device=dev) if want_order else None
+    with _on(xyz):
+        rc = _lib.load().upp_crop_split_f32(_ptr(xyz), _ptr(viewpoints), B, n, num_crop, 1 if padding_zeros else 0,
+                                            _ptr(crop), _ptr(inp), _ptr(order), _stream(xyz))
+    _lib.check(rc, "upp_crop_split_f32")
+    return (inp, crop, order) if want_order else (inp, crop)
+
+
 def peer_allreduce_finish(peers, device):
     """upp_peer_allreduce_finish_f32: second half of a deferred exchange -> global sums (4 floats)."""
     import ctypes

@@ -237,6 +237,20 @@ UPP_API int upp_knn_points_f32(const float* p1, const float* p2, int B, int N1, 
                        float* dist2_out, int64_t* idx_out, float* nn_out, upp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Viewpoint crop of a batch of clouds.
+ * Replaces the per-cloud body of misc.seprate_point_cloud  utils/misc.py:232-239
+ *   (torch.norm(center - points) -> torch.argsort -> idx[:num_crop] / idx[num_crop:] gathers), called once per training
+ *   step from tools/runner_module.py:131, tools/runner_pretask.py:179, tools/runner_unify_seg.py:212.
+ * xyz (B,n,3), viewpoints (B,3) -> crop_out (B,num_crop,3): the num_crop points nearest to the cloud's viewpoint, nearest
+ * first; input_out: the remaining points in ascending distance (B,n-num_crop,3), or -- padding_zeros != 0 -- the cloud in
+ * its original order with the cropped rows multiplied by zero (B,n,3).  order_out (nullable, (B,n) int32): the full
+ * ascending order.  Equal distances keep the lower point index first (a stable sort).  Distance: sqrt_rn of
+ * fma(dz,dz,fma(dy,dy,dx*dx)), d* = viewpoint - point.  One launch for the batch; n <= 8192 (UPP_ERR_UNSUPPORTED beyond).
+ */
+UPP_API int upp_crop_split_f32(const float* xyz, const float* viewpoints, int B, int n, int num_crop, int padding_zeros,
+                       float* crop_out, float* input_out, int32_t* order_out, upp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * k-nearest inverse-distance feature interpolation.
  * Replaces the pure-torch body of
  *   propagate(xyz1, xyz2, points1, points2, de_neighbors, dist_e)   models/Point_MAE_unify.py:22-48

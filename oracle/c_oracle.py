@@ -209,3 +209,26 @@ def knn_points(p1, p2, K):
     if rc != 0:
         raise ValueError(f"knn_points: K={K} must be in [1, N2={N2}]")
     return D, I
+
+
+def crop_order(xyz, centers):
+    """Ascending order of every cloud's points by distance to its viewpoint (reference utils/misc.py:232-233:
+    torch.norm(center - points) -> torch.argsort), stable.  xyz (B,n,3), centers (B,3) -> (B,n) int32."""
+    xyz, centers = _f32(xyz), _f32(centers)
+    B, n, _ = xyz.shape
+    order = np.empty((B, n), np.int32)
+    lib().upp_oracle_crop_order(_p(xyz, _f32p), _p(centers, _f32p), ctypes.c_int(B), ctypes.c_int(n), _p(order, _i32p))
+    return order
+
+
+def crop_split(xyz, centers, num_crop, padding_zeros=False):
+    """misc.seprate_point_cloud's crop (utils/misc.py:232-239) -> (input_data, crop_data)."""
+    xyz = _f32(xyz)
+    order = crop_order(xyz, centers).astype(np.int64)
+    crop = np.take_along_axis(xyz, order[:, :num_crop, None], 1)
+    if padding_zeros:
+        inp = xyz.copy()
+        np.put_along_axis(inp, order[:, :num_crop, None].repeat(3, -1), crop * np.float32(0), 1)
+    else:
+        inp = np.take_along_axis(xyz, order[:, num_crop:, None], 1)
+    return inp, crop

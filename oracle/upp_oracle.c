@@ -514,3 +514,32 @@ ORACLE_API void upp_oracle_interp_bwd(const float* gout, const float* feat2, con
   for (size_t i = 0; i < (size_t)B * S * 3; ++i) gxyz2[i] = (float)g2[i];
   free(gf); free(g2); free(dot);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Viewpoint crop order of misc.seprate_point_cloud (reference utils/misc.py:232-233):
+ *   distance_matrix = torch.norm(center - points, p=2, dim=-1);  idx = torch.argsort(distance_matrix)
+ * restated as: d = sqrtf(fma(dz,dz,fma(dy,dy,dx*dx))) with d* = center - point (the sum of squares in x, y, z order,
+ * then the square root), ascending, equal distances keep the lower point index first (stable).  order (B,n) int32.
+ * Pinned by tests/golden/golden_seprate.npz (the reference's own function run unmodified). */
+static int crop_key_cmp(const void* a, const void* b) {
+  const unsigned long long x = *(const unsigned long long*)a, y = *(const unsigned long long*)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+ORACLE_API void upp_oracle_crop_order(const float* xyz, const float* centers, int B, int n, int32_t* order) {
+  unsigned long long* keys = (unsigned long long*)malloc((size_t)(n > 0 ? n : 1) * sizeof(unsigned long long));
+  for (int b = 0; b < B; ++b) {
+    const float* p = xyz + (size_t)b * n * 3;
+    const float cx = centers[3 * b], cy = centers[3 * b + 1], cz = centers[3 * b + 2];
+    for (int i = 0; i < n; ++i) {
+      const float dx = cx - p[3 * i], dy = cy - p[3 * i + 1], dz = cz - p[3 * i + 2];
+      const float d = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+      uint32_t bits;
+      memcpy(&bits, &d, 4);
+      keys[i] = ((unsigned long long)bits << 32) | (unsigned)i;
+    }
+    qsort(keys, (size_t)n, sizeof(unsigned long long), crop_key_cmp);
+    for (int i = 0; i < n; ++i) order[(size_t)b * n + i] = (int32_t)(keys[i] & 0xffffffffull);
+  }
+  free(keys);
+}

@@ -83,3 +83,26 @@ for B, N, M in ((32, 1228, 1024), (32, 1024, 256), (128, 8192, 1024)):
     rows = torch.randn(B, M, 3, generator=g).to(dev)
     idx = torch.stack([torch.randperm(N, generator=g)[:M] for _ in range(B)]).to(torch.int32).to(dev)
     rec(f"rows_scatter_add B{B} N{N} M{M}", timeit(lambda: o.rows_scatter_add(rows, idx, N)))
+
+# seprate_point_cloud as the runners call it (B32, 8192 points, crop in [2048, 4096] -> both sides resampled to 1024)
+import random  # noqa: E402
+xyz = (torch.rand(32, 8192, 3, generator=g) * 2 - 1).to(dev)
+for crop in (2048, [2048, 4096]):
+    def run():
+        random.seed(1)
+        torch.manual_seed(1)
+        return upp_b200.misc.seprate_point_cloud(xyz, 8192, crop, sample_points=1024)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    import time  # noqa: E402
+    ts = []
+    for _ in range(20):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run()
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e6)
+    rec(f"seprate_point_cloud B32 N8192 crop{crop} -> 1024 + 1024 (eager, wall clock incl. host RNG)", round(statistics.median(ts), 1))
+c = torch.nn.functional.normalize(torch.randn(32, 3, generator=g), dim=-1).to(dev)
+rec("crop_split B32 N8192 crop2048", timeit(lambda: o.crop_split(xyz, c, 2048)))

@@ -176,14 +176,31 @@ def test_bench_reference_arm_contract():
 
 
 def test_seprate_point_cloud_host_logic_matches_reference_golden():
-    """The crop / gather / RNG logic of the batched mirror (no FPS on these cases -> runs without a GPU)."""
+    """The HOST half of the batched mirror, without a GPU: the viewpoints drawn by upp_b200.misc._draw_viewpoints consume
+    the RNGs exactly as the reference's per-cloud loop does (the crop the oracle computes from them equals the golden
+    produced by the reference's own function, same seeds), and the one-shot normalisation is bit-equal to the reference's
+    per-draw F.normalize."""
     import random
+    import torch.nn.functional as F
     import upp_b200
+    from oracle import c_oracle as O
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_seprate.npz"))
-    xyz = torch.from_numpy(g["xyz"])
-    for case, kw in (("padding", dict(crop=128, padding_zeros=True, sample_points=1024)),
-                     ("no_fps", dict(crop=128, incomplete_shape=False))):
+    xyz = g["xyz"]
+    B = xyz.shape[0]
+    views = [torch.Tensor([1, 1, 1]), torch.Tensor([-1, 1, 0]), torch.Tensor([0, -1, 1])]
+    for case, kw, crop, pad in (("padding", {}, 128, True), ("no_fps", {}, 128, False),
+                                ("view_list", dict(fixed_points=views), 150, False)):
         random.seed(11)
         torch.manual_seed(11)
-        a, b = upp_b200.misc.seprate_point_cloud(xyz, 512, **kw)
-        assert np.array_equal(a.numpy(), g[case + "_input"]) and np.array_equal(b.numpy(), g[case + "_crop"])
+        centers = upp_b200.misc._draw_viewpoints(B, **kw).numpy()
+        inp, crp = O.crop_split(xyz, centers, crop, padding_zeros=pad)
+        if case != "view_list":  # (that case resamples with FPS afterwards: only its crop order is checked on the GPU)
+            assert np.array_equal(inp, g[case + "_input"]) and np.array_equal(crp, g[case + "_crop"])
+    torch.manual_seed(3)
+    draws = [torch.randn(1, 1, 3) for _ in range(64)]
+    torch.manual_seed(3)
+    got = upp_b200.misc._draw_viewpoints(64)
+    want = torch.cat([F.normalize(d, p=2, dim=-1) for d in draws], 0).reshape(64, 3)
+    assert torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        upp_b200.misc.seprate_point_cloud(torch.from_numpy(xyz), 512, 128)  # CPU tensors: no fallback
