@@ -84,6 +84,8 @@ int group_fused_launch(const float*, int, int, int, int, float*, float*, int64_t
 int knn_points_launch(const float*, const float*, int, int, int, int, float*, int64_t*, float*, cudaStream_t);
 int interp_fwd_launch(const float*, const float*, const float*, const float*, float, float, int, int, int, int,
                       int, float*, int32_t*, float*, float*, cudaStream_t);
+int interp_blend_launch(const float*, const float*, float, const int32_t*, const float*, int, int, int, int, int, float*,
+                        cudaStream_t);
 int interp_bwd_launch(const float*, const int32_t*, const float*, const float*, const float*, const float*,
                       const float*, float, float, int, int, int, int, int, float*, float*, float*, float*,
                       void*, size_t, cudaStream_t);
@@ -321,6 +323,25 @@ int upp_interp_fwd_f32(const float* xyz1, const float* xyz2, const float* feat2,
   UPP_REQUIRE(C == 0 || (feat2 && out));
   return interp_fwd_launch(xyz1, xyz2, feat2, base, alpha, eps, B, N, S, C, k, out, idx, weight, dist,
                            static_cast<cudaStream_t>(stream));  // (the size S shadows the helper here)
+}
+
+int upp_interp_select_f32(const float* xyz1, const float* xyz2, float eps, int B, int N, int S, int k, int32_t* idx,
+                          float* weight, float* dist, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && S >= 0);
+  UPP_REQUIRE(k >= 1 && k <= S && k <= 32);
+  if (B == 0 || N == 0) return UPP_OK;
+  UPP_REQUIRE(xyz1 && xyz2 && idx && weight);
+  return interp_fwd_launch(xyz1, xyz2, nullptr, nullptr, 1.0f, eps, B, N, S, 0, k, nullptr, idx, weight, dist,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int upp_interp_blend_f32(const float* feat2, const float* base, float alpha, const int32_t* idx, const float* weight,
+                         int B, int N, int S, int C, int k, float* out, upp_stream_t stream) {
+  UPP_REQUIRE(B >= 0 && N >= 0 && S >= 1 && C >= 0);
+  UPP_REQUIRE(k >= 1 && k <= S && k <= 32);
+  if (B == 0 || N == 0 || C == 0) return UPP_OK;
+  UPP_REQUIRE(feat2 && idx && weight && out);
+  return interp_blend_launch(feat2, base, alpha, idx, weight, B, N, S, C, k, out, static_cast<cudaStream_t>(stream));
 }
 
 size_t upp_interp_bwd_workspace_bytes(int B, int N, int S, int C, int k) {

@@ -310,8 +310,18 @@ __global__ void __launch_bounds__(kSelThreads)
       pi[j] = __shfl_xor_sync(0xffffffffu, bi[j], x);
     }
     const bool partner_lower = (q & x) != 0;
+    // a lower-indexed partner's entries go BEFORE equal distances: inserted last to first, so that two of its own
+    // entries with equal distance keep their (index) order; a higher-indexed partner's go after equals, first to last
 #pragma unroll
-    for (int j = 0; j < K; ++j) topk_insert<K>(bd, bi, pd[j], pi[j], partner_lower);
+    for (int j = 0; j < K; ++j) {
+      const int jj = partner_lower ? K - 1 - j : j;
+      float pdj = pd[0];
+      int pij = pi[0];
+#pragma unroll
+      for (int u = 1; u < K; ++u)
+        if (u == jj) { pdj = pd[u]; pij = pi[u]; }
+      topk_insert<K>(bd, bi, pdj, pij, partner_lower);
+    }
   }
   if (!active || q != 0) return;
   // weights: dist_recip = 1/(d + eps); weight = dist_recip / sum(dist_recip)  (sum in neighbour order)
@@ -1116,6 +1126,46 @@ static int blend_pick_spans(long items0, int N) {
   return static_cast<int>(want < 1 ? 1 : (want > smax ? smax : want));
 }
 
+// The shared-memory blend over a 2-D TMA tile of the source features (second launch of the two-phase forward, and the
+// whole of a forward that REUSES a cached selection).
+static int launch_blend(const CUtensorMap& fmap, const float* base, float alpha, const int32_t* idx, const float* weight,
+                        int B, int N, int S, int C, int k, float* out, cudaStream_t st) {
+  const int chunks = C >= kBlendCh ? C / kBlendCh : 1;
+  const int chw = min(C, kBlendCh);  // channels of a staged row
+  const char* wv = tuning_env("UPP_BLEND_WARPS");  // tuning aid: 8 or 16 warps per CTA
+  const int nwb = (wv && atoi(wv) == 8) ? 8 : 16;
+  const int kk = (k == 3 || k == 4 || k == 8 || k == 16) ? k : 0;  // the instantiated neighbour counts; 0 = run-time loop
+  const size_t bsmem = ((static_cast<size_t>(S) * chw * sizeof(float) + 15) & ~static_cast<size_t>(15)) +
+                       static_cast<size_t>(nwb) * blend_tw(kk) * k * 8;
+  const char* sv2 = tuning_env("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
+  const int spans = sv2 ? max(1, atoi(sv2)) : blend_pick_spans(static_cast<long>(chunks) * B, N);
+  const int span = ((N + spans - 1) / spans + 1) & ~1;  // whole pairs of targets (a warp blends two per trip)
+  dim3 bgrid(chunks, (N + span - 1) / span, B);
+#define UPP_BLEND(K_, W_)                                                                                               \
+  do {                                                                                                                   \
+    if (bsmem > 40 * 1024) {                                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(interp_blend_kernel<K_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                           static_cast<int>(bsmem));                                                     \
+      if (e != cudaSuccess) return static_cast<int>(e);                                                                  \
+    }                                                                                                                    \
+    interp_blend_kernel<K_, W_><<<bgrid, W_ * kWarp, bsmem, st>>>(fmap, base, alpha, idx, weight, N, S, C, k, span, out); \
+  } while (0)
+#define UPP_BLEND_K(W_)              \
+  do {                               \
+    if (k == 3) UPP_BLEND(3, W_);    \
+    else if (k == 4) UPP_BLEND(4, W_); \
+    else if (k == 8) UPP_BLEND(8, W_); \
+    else if (k == 16) UPP_BLEND(16, W_); \
+    else UPP_BLEND(0, W_);           \
+  } while (0)
+  if (nwb == 8) UPP_BLEND_K(8);
+  else UPP_BLEND_K(16);
+#undef UPP_BLEND_K
+#undef UPP_BLEND
+  count_launch();
+  return launch_status();
+}
+
 int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, const float* base, float alpha,
                       float eps, int B, int N, int S, int C, int k, float* out, int32_t* idx, float* weight,
                       float* distk, cudaStream_t st) {
@@ -1141,7 +1191,8 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   // UPP_INTERP_SELECT (test aid): 0 = never the thread-per-target selection, 1 = whenever k <= 4 and S <= 1024
   const char* sv = tuning_env("UPP_INTERP_SELECT");
   const int senv = sv ? atoi(sv) : -1;
-  const bool thread_select = two_phase && sel_ok && senv != 0 && (senv == 1 || static_cast<long>(B) * N >= 4096);
+  // (C == 0: a selection-only call, upp_interp_select_f32 -- the fast selection whenever it applies)
+  const bool thread_select = (two_phase || C == 0) && sel_ok && senv != 0 && (senv == 1 || static_cast<long>(B) * N >= 4096);
   if (thread_select) {
     const char* tv = tuning_env("UPP_INTERP_TPT");  // tuning aid: threads per target (1, 2, 4)
     const int tpt = tv ? atoi(tv) : 1;
@@ -1192,38 +1243,73 @@ int interp_fwd_launch(const float* xyz1, const float* xyz2, const float* feat2, 
   int rc = launch_status();
   if (rc != UPP_OK || !two_phase) return rc;
 
-  const int chunks = C >= kBlendCh ? C / kBlendCh : 1;
-  const int chw = min(C, kBlendCh);  // channels of a staged row
-  const char* wv = tuning_env("UPP_BLEND_WARPS");  // tuning aid: 8 or 16 warps per CTA
-  const int nwb = (wv && atoi(wv) == 8) ? 8 : 16;
-  const int kk = (k == 3 || k == 4 || k == 8 || k == 16) ? k : 0;  // the instantiated neighbour counts; 0 = run-time loop
-  const size_t bsmem = ((static_cast<size_t>(S) * chw * sizeof(float) + 15) & ~static_cast<size_t>(15)) +
-                       static_cast<size_t>(nwb) * blend_tw(kk) * k * 8;
-  const char* sv2 = tuning_env("UPP_BLEND_SPANS");  // tuning aid: force the number of target spans per (cloud, chunk)
-  const int spans = sv2 ? max(1, atoi(sv2)) : blend_pick_spans(static_cast<long>(chunks) * B, N);
-  const int span = ((N + spans - 1) / spans + 1) & ~1;  // whole pairs of targets (a warp blends two per trip)
-  dim3 bgrid(chunks, (N + span - 1) / span, B);
-#define UPP_BLEND(K_, W_)                                                                                               \
-  do {                                                                                                                   \
-    if (bsmem > 40 * 1024) {                                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(interp_blend_kernel<K_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                           static_cast<int>(bsmem));                                                     \
-      if (e != cudaSuccess) return static_cast<int>(e);                                                                  \
-    }                                                                                                                    \
-    interp_blend_kernel<K_, W_><<<bgrid, W_ * kWarp, bsmem, st>>>(fmap, base, alpha, idx, weight, N, S, C, k, span, out); \
-  } while (0)
-#define UPP_BLEND_K(W_)              \
-  do {                               \
-    if (k == 3) UPP_BLEND(3, W_);    \
-    else if (k == 4) UPP_BLEND(4, W_); \
-    else if (k == 8) UPP_BLEND(8, W_); \
-    else if (k == 16) UPP_BLEND(16, W_); \
-    else UPP_BLEND(0, W_);           \
-  } while (0)
-  if (nwb == 8) UPP_BLEND_K(8);
-  else UPP_BLEND_K(16);
-#undef UPP_BLEND_K
-#undef UPP_BLEND
+  return launch_blend(fmap, base, alpha, idx, weight, B, N, S, C, k, out, st);
+}
+
+// Forward from a CACHED selection (the SA-units call propagate six times on identical geometry,
+// models/Point_MAE_pretask_dev.py:298 -- the selection is paid once, every later call is this blend alone).
+// Generic shapes: one warp per target reads its k saved {index, weight} pairs and runs the gather of the one-launch
+// kernel (same helper, same arithmetic order: bit-identical output); wide / narrow-chunk shapes take the shared-memory
+// blend kernel exactly as the two-phase forward does.
+template <bool VEC4>
+__global__ void __launch_bounds__(kKnnWarps * kWarp)
+    interp_apply_kernel(const float* __restrict__ feat2, const float* __restrict__ base, float alpha,
+                        const int32_t* __restrict__ idx, const float* __restrict__ weight, int N, int S, int C, int k,
+                        float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * kKnnWarps + warp;
+  if (n >= N) return;  // whole warp
+  const size_t row = static_cast<size_t>(b) * N + n;
+  int li = 0;
+  float w = 0.f;
+  if (lane < k) {
+    li = __ldg(idx + row * k + lane);
+    w = __ldg(weight + row * k + lane);
+  }
+  const float* fb = feat2 + static_cast<size_t>(b) * S * C;
+  float* orow = out + row * C;
+  const float* brow = base ? base + row * C : nullptr;
+  if (VEC4) {
+    int cs = 0;
+    for (; cs + kInterpCB * 128 <= C; cs += kInterpCB * 128)
+      interp_gather_blocks<kInterpCB, false>(fb, brow, orow, C, cs, k, w, li, alpha);
+    for (; cs < C; cs += 128) interp_gather_blocks<1, true>(fb, brow, orow, C, cs, k, w, li, alpha);
+  } else {
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      float acc = 0.f;
+      for (int j = 0; j < k; ++j) {
+        const float wj = __shfl_sync(0xffffffffu, w, j);
+        const int ij = __shfl_sync(0xffffffffu, li, j);
+        if (c < C) acc = __fadd_rn(acc, __fmul_rn(__ldg(fb + static_cast<size_t>(ij) * C + c), wj));
+      }
+      if (c < C) {
+        float o = __fmul_rn(alpha, acc);
+        if (brow) o = __fadd_rn(__ldg(brow + c), o);
+        orow[c] = o;
+      }
+    }
+  }
+}
+
+int interp_blend_launch(const float* feat2, const float* base, float alpha, const int32_t* idx, const float* weight,
+                        int B, int N, int S, int C, int k, float* out, cudaStream_t st) {
+  const bool vec4 = (C % 4 == 0) && aligned16(feat2, out, base);
+  const int env = interp_path_env();
+  const bool blend_ok = vec4 && C > 0 && (C % kBlendCh == 0 || C < kBlendCh) && S <= kBlendMaxS && B <= 65535;
+  // the staged-tile blend pays from a few thousand targets per launch on; below that the per-target gather is cheaper
+  bool tiled = blend_ok && (env == 1 || (env < 0 && static_cast<long>(B) * N >= 8192 && N >= 256));
+  CUtensorMap fmap;
+  if (tiled && make_tmap_2d_f32(&fmap, feat2, static_cast<uint64_t>(C), static_cast<uint64_t>(B) * S,
+                                static_cast<uint64_t>(C) * sizeof(float), static_cast<uint32_t>(min(C, kBlendCh)),
+                                static_cast<uint32_t>(S)) != UPP_OK)
+    tiled = false;
+  if (tiled) return launch_blend(fmap, base, alpha, idx, weight, B, N, S, C, k, out, st);
+  dim3 grid((N + kKnnWarps - 1) / kKnnWarps, B);
+  if (vec4) interp_apply_kernel<true><<<grid, kKnnWarps * kWarp, 0, st>>>(feat2, base, alpha, idx, weight, N, S, C, k, out);
+  else interp_apply_kernel<false><<<grid, kKnnWarps * kWarp, 0, st>>>(feat2, base, alpha, idx, weight, N, S, C, k, out);
   count_launch();
   return launch_status();
 }

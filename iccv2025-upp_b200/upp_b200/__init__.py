@@ -21,7 +21,8 @@ _lib.load()  # fail loudly, at import, if the CUDA library is missing
 from . import chamfer, metrics, misc, ops, parallel, pointnet2_utils  # noqa: E402,F401
 from .knn import KNN  # noqa: E402,F401
 from .modules import (ChamferDistanceL1, ChamferDistanceL2, ChamferDistanceL2_split,  # noqa: E402,F401
-                      ChamferFunction, Group, fps, interpolate_features, knn_points, propagate)
+                      ChamferFunction, Group, Selection, fps, interpolate_features, knn_points, propagate,
+                      select_neighbors)
 
 __version__ = "0.1.0"
 launch_count = _lib.launch_count

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "upp_crop_split_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "upp_knn_points_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "upp_interp_fwd_f32": [_vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "upp_interp_select_f32": [_vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "upp_interp_blend_f32": [_vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "upp_interp_bwd_workspace_bytes": [_i, _i, _i, _i, _i],
     "upp_interp_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
 }

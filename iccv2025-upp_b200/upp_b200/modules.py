@@ -148,13 +148,39 @@ class ChamferDistanceL1(_ChamferBase):
         return (torch.mean(torch.sqrt(dist1)) + torch.mean(torch.sqrt(dist2))) / 2
 
 
+class Selection:
+    """A kept neighbour selection: (idx, weight, dist) of `k` nearest sources per target for one (xyz1, xyz2) pair.
+    Pass it to propagate / interpolate_features (`selection=`) to pay for the selection once when several calls share
+    their geometry -- the six SA-unit propagate calls of one forward (models/Point_MAE_pretask_dev.py:298), the feature
+    propagation levels of the segmentation head."""
+    __slots__ = ("idx", "weight", "dist", "k", "eps")
+
+    def __init__(self, idx, weight, dist, k, eps):
+        self.idx, self.weight, self.dist, self.k, self.eps = idx, weight, dist, int(k), float(eps)
+
+
+def select_neighbors(xyz1, xyz2, k, eps):
+    """Selection + inverse-distance weights of propagate / the feature-propagation interpolation alone
+    (upp_interp_select_f32) -> Selection.  k is clipped to the number of sources, as the reference's slice does."""
+    k = min(int(k), xyz2.shape[1])
+    idx, w, d = ops.interp_select(xyz1.detach().contiguous(), xyz2.detach().contiguous(), k, eps)
+    return Selection(idx, w, d, k, eps)
+
+
 class _Interpolate(Function):
     """out = (base or 0) + alpha * sum_j w_j points2[idx_j]; differentiable w.r.t. points2, base and -- through the
-    weights, as autograd is through the reference's square_distance -- xyz1 / xyz2."""
+    weights, as autograd is through the reference's square_distance -- xyz1 / xyz2.  `sel`: a Selection made for the
+    same (xyz1, xyz2, k, eps): the forward is then the blend alone."""
 
     @staticmethod
-    def forward(ctx, xyz1, xyz2, points2, base, k, eps, alpha):
-        out, idx, w, d = ops.interp_forward(xyz1, xyz2, points2, k, eps, base=base, alpha=alpha)
+    def forward(ctx, xyz1, xyz2, points2, base, k, eps, alpha, sel=None):
+        if sel is None:
+            out, idx, w, d = ops.interp_forward(xyz1, xyz2, points2, k, eps, base=base, alpha=alpha)
+        else:
+            if sel.k != k or sel.eps != float(eps) or tuple(sel.idx.shape[:2]) != tuple(xyz1.shape[:2]):
+                raise ValueError("selection was made for a different (xyz1, k, eps)")
+            idx, w, d = sel.idx, sel.weight, sel.dist
+            out = ops.interp_blend(points2, idx, w, base=base, alpha=alpha)
         ctx.save_for_backward(xyz1, xyz2, points2, idx, w, d)
         ctx.eps, ctx.alpha, ctx.has_base = float(eps), float(alpha), base is not None
         return out
@@ -168,28 +194,50 @@ class _Interpolate(Function):
         gp2, g1, g2 = ops.interp_backward(grad_out, idx, w, points2.size(1), alpha=ctx.alpha, xyz_terms=terms)
         return (g1 if ctx.needs_input_grad[0] else None, g2 if ctx.needs_input_grad[1] else None,
                 gp2 if ctx.needs_input_grad[2] else None,
-                grad_out if (ctx.has_base and ctx.needs_input_grad[3]) else None, None, None, None)
+                grad_out if (ctx.has_base and ctx.needs_input_grad[3]) else None, None, None, None, None)
 
 
-def interpolate_features(xyz1, xyz2, points2, k, eps=1e-4):
+def interpolate_features(xyz1, xyz2, points2, k, eps=1e-4, selection=None):
     """The interpolation of PointNetFeaturePropagation.forward: xyz1 (B,N,3), xyz2 (B,S,3), points2 (B,S,D)
     -> (B,N,D).  S == 1 repeats the single source row, as the reference does; k is clipped to S like the
-    reference's slice `[:, :, :k]`."""
+    reference's slice `[:, :, :k]`.  selection: a Selection from select_neighbors(xyz1, xyz2, k, eps) to reuse."""
     B, N, _ = xyz1.shape
     S = xyz2.shape[1]
     if S == 1:
         return points2.repeat(1, N, 1)
     return _Interpolate.apply(xyz1.contiguous(), xyz2.contiguous(), points2.contiguous(), None,
-                              min(int(k), S), float(eps), 1.0)
+                              min(int(k), S), float(eps), 1.0, selection)
 
 
-def propagate(xyz1, xyz2, points1, points2, de_neighbors=64, dist_e=1e-8):
+def _propagate_wide(xyz1, xyz2, points1, points2, k, eps):
+    """More than 32 neighbours (only the reference's DEFAULT de_neighbors=64 on clouds of more than 32 sources gets here;
+    its call sites pass 6 or 8): the reference's formulation on torch's CUDA kernels -- square_distance, full sort,
+    first k, inverse-distance weights, gather -- so that the mirror runs whatever its signature advertises."""
+    B, N, _ = xyz1.shape
+    d = -2 * torch.matmul(xyz1, xyz2.permute(0, 2, 1))
+    d = d + torch.sum(xyz1 ** 2, -1).view(B, N, 1) + torch.sum(xyz2 ** 2, -1).view(B, 1, -1)
+    d, idx = d.sort(dim=-1)
+    d, idx = d[:, :, :k], idx[:, :, :k]
+    r = 1.0 / (d + eps)
+    w = r / torch.sum(r, dim=2, keepdim=True)
+    picked = torch.gather(points2.unsqueeze(1).expand(-1, N, -1, -1), 2, idx.unsqueeze(-1).expand(-1, -1, -1, points2.shape[-1]))
+    return points1 + 0.3 * torch.sum(picked * w.view(B, N, k, 1), dim=2)
+
+
+def propagate(xyz1, xyz2, points1, points2, de_neighbors=64, dist_e=1e-8, selection=None):
     """points1 + 0.3 * (inverse-distance interpolation of points2 over the de_neighbors nearest of xyz2);
-    same signature and defaults as the reference function.  de_neighbors is clipped to S like the reference's
-    slice; more than 32 neighbours is outside what the kernel covers (the UPP configs use 3..16) and raises."""
+    same signature and defaults as the reference function (models/Point_MAE_unify.py:22-48).  de_neighbors is clipped to
+    S like the reference's slice.  Up to 32 neighbours (the UPP configs use 3..16) run on the interpolation kernels; more
+    -- the bare default on a cloud of more than 32 sources -- on the reference's own torch formulation (GPU).
+    selection: a Selection from select_neighbors(xyz1, xyz2, de_neighbors, dist_e) to reuse across calls."""
     S = xyz2.shape[1]
+    k = min(int(de_neighbors), S)
+    if k > 32:
+        if selection is not None:
+            raise ValueError("a kept Selection covers at most 32 neighbours")
+        return _propagate_wide(xyz1, xyz2, points1, points2, k, float(dist_e))
     return _Interpolate.apply(xyz1.contiguous(), xyz2.contiguous(), points2.contiguous(), points1.contiguous(),
-                              min(int(de_neighbors), S), float(dist_e), 0.3)
+                              k, float(dist_e), 0.3, selection)
 
 
 _KNN = collections.namedtuple("KNN", "dists idx knn")  # pytorch3d's return type

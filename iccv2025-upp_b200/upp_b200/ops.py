@@ -283,6 +283,49 @@ def interp_forward(xyz1, xyz2, points2, k, eps, base=None, alpha=1.0, want_dist=
     return out, idx, w, d
 
 
+def interp_select(xyz1, xyz2, k, eps, want_dist=True):
+    """Selection half of interp_forward alone (upp_interp_select_f32): -> idx (B,N,k) int32, weight (B,N,k), dist (B,N,k)."""
+    _xyz("xyz1", xyz1)
+    _xyz("xyz2", xyz2)
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    if xyz2.shape[0] != B:
+        raise ValueError("xyz1 and xyz2 must have the same batch size")
+    k = int(k)
+    if not 1 <= k <= min(S, 32):
+        raise ValueError(f"k={k} must be in [1, min(S={S}, 32)]")
+    dev = xyz1.device
+    idx = torch.empty((B, N, k), dtype=torch.int32, device=dev)
+    w = torch.empty((B, N, k), dtype=torch.float32, device=dev)
+    d = torch.empty((B, N, k), dtype=torch.float32, device=dev) if want_dist else None
+    with _on(xyz1):
+        rc = _lib.load().upp_interp_select_f32(_ptr(xyz1), _ptr(xyz2), float(eps), B, N, S, k, _ptr(idx), _ptr(w), _ptr(d), _stream(xyz1))
+    _lib.check(rc, "upp_interp_select_f32")
+    return idx, w, d
+
+
+def interp_blend(points2, idx, weight, base=None, alpha=1.0):
+    """Blend half of interp_forward from a saved selection (upp_interp_blend_f32): -> out (B,N,C), bit-identical to what
+    interp_forward returns for the same inputs."""
+    _need("points2", points2, torch.float32, 3)
+    _need("idx", idx, torch.int32, 3)
+    _need("weight", weight, torch.float32, 3)
+    B, S, C = points2.shape
+    N, k = idx.shape[1], idx.shape[2]
+    if idx.shape[0] != B or tuple(weight.shape) != tuple(idx.shape):
+        raise ValueError("selection does not match points2")
+    if base is not None:
+        _need("base", base, torch.float32, 3)
+        if tuple(base.shape) != (B, N, C):
+            raise ValueError(f"base must be {(B, N, C)}, got {tuple(base.shape)}")
+    out = torch.empty((B, N, C), dtype=torch.float32, device=points2.device)
+    with _on(points2):
+        rc = _lib.load().upp_interp_blend_f32(_ptr(points2), _ptr(base), float(alpha), _ptr(idx), _ptr(weight), B, N, S, C, k,
+                                              _ptr(out), _stream(points2))
+    _lib.check(rc, "upp_interp_blend_f32")
+    return out
+
+
 def interp_backward(grad_out, idx, weight, S, alpha=1.0, xyz_terms=None):
     """Gradients of interp_forward: grad_points2 (B,S,C) always; with xyz_terms = (dist, points2, xyz1, xyz2, eps)
     also grad_xyz1 (B,N,3), grad_xyz2 (B,S,3) (the path through the weights).  Deterministic, no atomics."""

@@ -268,6 +268,18 @@ UPP_API int upp_interp_fwd_f32(const float* xyz1, const float* xyz2, const float
                        float alpha, float eps, int B, int N, int S, int C, int k, float* out,
                        int32_t* idx, float* weight, float* dist, upp_stream_t stream);
 
+/* The two halves of upp_interp_fwd_f32 as separate calls, so that a caller can keep a selection and pay for it once:
+ * the SA-units of the Rectification Prompter call propagate six times per forward on IDENTICAL geometry
+ * (models/Point_MAE_pretask_dev.py:298), and every PointNetFeaturePropagation call of one forward shares its xyz pair.
+ *   upp_interp_select_f32  xyz1, xyz2 -> idx (B,N,k) int32, weight (B,N,k), dist (B,N,k, nullable): selection + weights only
+ *   upp_interp_blend_f32   out (B,N,C) = (base ? base : 0) + alpha * sum_j weight_j * feat2[idx_j] from a saved selection
+ * select followed by blend produces bit-identical output to upp_interp_fwd_f32 (same kernels / same arithmetic order);
+ * upp_interp_bwd_f32 takes the same saved selection. */
+UPP_API int upp_interp_select_f32(const float* xyz1, const float* xyz2, float eps, int B, int N, int S, int k,
+                          int32_t* idx, float* weight, float* dist, upp_stream_t stream);
+UPP_API int upp_interp_blend_f32(const float* feat2, const float* base, float alpha, const int32_t* idx,
+                         const float* weight, int B, int N, int S, int C, int k, float* out, upp_stream_t stream);
+
 /* Backward of the interpolation (deterministic, no atomics).
  * grad_feat2 (B,S,C) is OVERWRITTEN with alpha * sum_{(n,j): idx = s} weight * grad_out[b,n,:].
  * Coordinate gradients (through the weights) are produced when gd_workspace (B*N*k floats) is given:

@@ -676,6 +676,65 @@ def test_interp_backward_streamed_matches_source_side_kernel(U, O, dev, monkeypa
     np.testing.assert_allclose(new.cpu().numpy(), o_gp2, rtol=1e-4, atol=1e-5 * scale)
 
 
+@pytest.mark.parametrize("tpt", ["1", "2", "4"])
+def test_interp_thread_select_duplicate_sources_keep_index_order(U, O, dev, monkeypatch, tpt):
+    """Sources that coincide (exactly equal distances inside one partner list of the multi-thread merge): the lower source
+    index must come first whatever the number of threads per target."""
+    g = torch.Generator().manual_seed(9)
+    x2 = torch.rand(2, 64, 3, generator=g) * 2 - 1
+    x2[:, 1::2] = x2[:, 0::2]               # every source duplicated: pairs of equal distances everywhere
+    x2[:, 40:44] = x2[:, 8:9]               # and a run of five coincident sources across the parts
+    x1 = torch.rand(2, 300, 3, generator=g) * 2 - 1
+    p2 = torch.randn(2, 64, 128, generator=g)
+    monkeypatch.setenv("UPP_INTERP_PATH", "1")
+    monkeypatch.setenv("UPP_INTERP_SELECT", "1")
+    monkeypatch.setenv("UPP_INTERP_TPT", tpt)
+    for k in (2, 3, 4):
+        out, idx, w, d = U.ops.interp_forward(x1.to(dev), x2.to(dev), p2.to(dev), k, 1e-4)
+        o_out, o_idx, o_w, o_d = O.interp_fwd(x1.numpy(), x2.numpy(), p2.numpy(), k, 1e-4)
+        assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(w.cpu().numpy(), o_w)
+
+
+def test_interp_selection_reuse_is_bit_identical(U, O, dev):
+    """upp_interp_select_f32 + upp_interp_blend_f32 (a kept Selection, SURVEY 8f row 1: six SA-unit propagate calls on the
+    same geometry) against the one-shot forward: bit-identical outputs, one launch per reuse, gradients unchanged."""
+    g = torch.Generator().manual_seed(14)
+    for (B, N, S, C, k, eps, with_base) in [(3, 64, 32, 384, 8, 1e-3, True), (2, 2048, 128, 1152, 3, 1e-4, False), (2, 1096, 32, 96, 16, 1e-3, True),
+                                            (2, 100, 40, 10, 5, 1e-8, True), (4, 2100, 64, 256, 6, 1e-3, False)]:
+        x1, x2 = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev), (torch.rand(B, S, 3, generator=g) * 2 - 1).to(dev)
+        feats = [torch.randn(B, S, C, generator=g).to(dev) for _ in range(3)]
+        base = torch.randn(B, N, C, generator=g).to(dev) if with_base else None
+        sel = U.select_neighbors(x1, x2, k, eps)
+        for f in feats:
+            want, idx, w, d = U.ops.interp_forward(x1, x2, f, k, eps, base=base, alpha=0.3 if with_base else 1.0)
+            n0 = U.launch_count()
+            got = U.ops.interp_blend(f, sel.idx, sel.weight, base=base, alpha=0.3 if with_base else 1.0)
+            assert U.launch_count() - n0 == 1
+            assert torch.equal(sel.idx, idx) and torch.equal(sel.weight, w) and torch.equal(sel.dist, d)
+            assert torch.equal(got, want)
+    # through the mirrors, with autograd
+    x1, x2 = (torch.rand(2, 200, 3, generator=g) * 2 - 1).to(dev), (torch.rand(2, 48, 3, generator=g) * 2 - 1).to(dev)
+    p1 = torch.randn(2, 200, 64, generator=g).to(dev)
+    sel = U.select_neighbors(x1, x2, 8, 1e-3)
+    for _ in range(2):
+        p2a = torch.randn(2, 48, 64, generator=g).to(dev).requires_grad_(True)
+        p2b = p2a.detach().clone().requires_grad_(True)
+        a = U.propagate(x1, x2, p1, p2a, de_neighbors=8, dist_e=1e-3, selection=sel)
+        b = U.propagate(x1, x2, p1, p2b, de_neighbors=8, dist_e=1e-3)
+        assert torch.equal(a, b)
+        go = torch.randn_like(a)
+        a.backward(go)
+        b.backward(go)
+        assert torch.equal(p2a.grad, p2b.grad)
+    with pytest.raises(ValueError):
+        U.propagate(x1, x2, p1, p2a, de_neighbors=6, dist_e=1e-3, selection=sel)
+    # the reference's default de_neighbors=64 on more than 32 sources: served (torch formulation), not refused
+    from oracle import torch_formulation as T
+    wide = U.propagate(x1, x2, p1, p2a.detach())
+    want = p1.cpu() + 0.3 * T.interpolate(x1.cpu(), x2.cpu(), p2a.detach().cpu(), 48, 1e-8)
+    torch.testing.assert_close(wide.cpu(), want, rtol=1e-3, atol=1e-3)
+
+
 def test_golden_reference_propagate_and_feature_propagation(U, dev):
     """The reference's own propagate / PointNetFeaturePropagation outputs and float64 autograd gradients
     (tests/golden/golden_interp.npz) against the drop-in functions, autograd included."""
