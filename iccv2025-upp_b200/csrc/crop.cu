@@ -7,7 +7,8 @@
 //   * the cloud staged once in shared memory (TMA bulk copy);
 //   * one 64-bit key per point, (bits of the Euclidean distance << 32) | point index -- distances are non-negative, so
 //     the unsigned key order is (distance, index): exactly a STABLE ascending sort on the distance;
-//   * an in-shared-memory bitonic sort of the keys (8192 keys: 64 KB, 91 compare-exchange stages);
+//   * a bitonic sort of the keys: 8 keys per thread in registers, distances up to 128 by warp shuffles, only the
+//     distances >= 256 through shared memory (8192 keys: 64 KB, 21 barrier-separated passes for the 91 stages);
 //   * the split at num_crop and both gathers straight into the two FPS input buffers (or, padding_zeros, the cloud
 //     with its cropped rows multiplied by zero, as the reference does).
 // The two FPS calls of the whole batch follow as two launches (the larger side on clusters of CTAs, fps.cu).
@@ -50,18 +51,67 @@ __global__ void __launch_bounds__(kCropThreads, 1)
     s_key[i] = key;
   }
   __syncthreads();
-  // bitonic sort, ascending
-  for (int size = 2; size <= npow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = t; i < (npow2 >> 1); i += kCropThreads) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const unsigned long long a = s_key[lo], c = s_key[hi];
-        const bool up = (lo & size) == 0;
-        if ((a > c) == up) {
-          s_key[lo] = c;
-          s_key[hi] = a;
+  // ---- bitonic sort, ascending.  A thread owns 8 consecutive keys, a warp 256: every compare-exchange at distance
+  //      <= 128 stays inside a warp (distances 8..128: lane-xor shuffles, 4 / 2 / 1: registers), so only distances
+  //      >= 256 go through shared memory with a CTA barrier: 21 barrier-separated passes for 8192 keys instead of 91.
+  const int lane = t & 31;
+  const int e0 = t * 8;                      // first key of this thread
+  const bool owner = e0 < npow2;             // whole warps (npow2 is a multiple of 256)
+  auto warp_pass = [&](unsigned long long (&v)[8], int size) {   // distances min(size/2, 128) ... 1 of the merge `size`
+    for (int stride = min(size >> 1, 128); stride >= 8; stride >>= 1) {
+      const int lx = stride >> 3;
+      const bool keep_min = ((lane & lx) == 0) == ((e0 & size) == 0);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lx);
+        v[r] = ((v[r] < o) == keep_min) ? v[r] : o;  // one 64-bit compare + one select (keys are distinct)
+      }
+    }
+#pragma unroll
+    for (int stride = 4; stride >= 1; stride >>= 1) {
+      if (stride <= (size >> 1)) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if ((r & stride) == 0) {
+            const bool up = ((e0 + r) & size) == 0;
+            const unsigned long long x = v[r], y = v[r | stride];
+            const bool keep = (x < y) == up;
+            v[r] = keep ? x : y;
+            v[r | stride] = keep ? y : x;
+          }
         }
+      }
+    }
+  };
+  {
+    unsigned long long v[8];
+    if (owner) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = s_key[e0 + r];
+      for (int size = 2; size <= 256; size <<= 1) warp_pass(v, size);   // (npow2 >= 256)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) s_key[e0 + r] = v[r];
+    }
+    __syncthreads();
+    for (int size = 512; size <= npow2; size <<= 1) {
+      for (int stride = size >> 1; stride >= 256; stride >>= 1) {
+        for (int i = t; i < (npow2 >> 1); i += kCropThreads) {
+          const int lo_i = 2 * i - (i & (stride - 1));
+          const int hi_i = lo_i + stride;
+          const unsigned long long x = s_key[lo_i], y = s_key[hi_i];
+          const bool up = (lo_i & size) == 0;
+          const bool keep = (x < y) == up;
+          s_key[lo_i] = keep ? x : y;
+          s_key[hi_i] = keep ? y : x;
+        }
+        __syncthreads();
+      }
+      if (owner) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = s_key[e0 + r];
+        warp_pass(v, size);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s_key[e0 + r] = v[r];
       }
       __syncthreads();
     }
@@ -91,7 +141,7 @@ __global__ void __launch_bounds__(kCropThreads, 1)
 int crop_split_launch(const float* xyz, const float* centers, int B, int n, int num_crop, int padding_zeros,
                       float* crop_out, float* input_out, int32_t* order_out, cudaStream_t st) {
   if (n > kCropMaxPoints) return UPP_ERR_UNSUPPORTED;
-  int npow2 = 32;
+  int npow2 = 256;  // a warp sorts blocks of 256 keys in registers
   while (npow2 < n) npow2 <<= 1;
   const size_t smem = static_cast<size_t>(npow2) * 8 + static_cast<size_t>(n) * 12 + 16;
   if (smem > 40 * 1024) {

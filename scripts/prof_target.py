@@ -30,6 +30,15 @@ for _ in range(4):
         ops.fps((torch.rand(128, 8192, 3, generator=g) * 2 - 1).to(dev), 1024)
     elif what == "fps_cluster":  # seprate_point_cloud's large side: B x 6144 -> 1024 on clusters of 4 CTAs
         ops.fps((torch.rand(32, 6144, 3, generator=g) * 2 - 1).to(dev), 1024)
+    elif what == "fps_cluster2":  # the 2-CTA cluster shape the dispatcher never picks (A/B: why it loses)
+        os.environ["UPP_TUNING"], os.environ["UPP_FPS_CLUSTER"] = "1", "2"
+        ops.fps((torch.rand(32, 6144, 3, generator=g) * 2 - 1).to(dev), 1024)
+    elif what == "fps_cluster8":  # C4 sharded over 8 GPUs: 16 clouds of 8192 points per GPU
+        ops.fps((torch.rand(16, 8192, 3, generator=g) * 2 - 1).to(dev), 1024)
+    elif what == "crop":
+        x = (torch.rand(32, 8192, 3, generator=g) * 2 - 1).to(dev)
+        c = torch.nn.functional.normalize(torch.randn(32, 3, generator=g), dim=-1).to(dev)
+        ops.crop_split(x, c, 2048)
     elif what == "knn":
         r = (torch.rand(32, 1024, 3, generator=g) * 2 - 1).to(dev)
         ops.knn(r, r[:, :64].contiguous(), 32)
