@@ -1136,6 +1136,7 @@ struct ChamferBwdOp {
   }
 };
 
+template <int Q>
 __global__ void __launch_bounds__(256)
     chamfer_bwd_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                        const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2,
@@ -1149,7 +1150,7 @@ __global__ void __launch_bounds__(256)
   const ChamferBwdOp op{first ? xyz1 : xyz2, first ? xyz2 : xyz1, first ? idx1 : idx2, first ? idx2 : idx1,
                         first ? g1 : g2,     first ? g2 : g1,     first ? gx1 : gx2,   b,
                         first ? N : M,       first ? M : N};
-  float sq = ordered_scatter_cta<2>(op, op.Ns, s_dst, first ? 0 : blocks1);
+  float sq = ordered_scatter_cta<Q>(op, op.Ns, s_dst, first ? 0 : blocks1);
   if (sq_partials == nullptr) return;
   // ---- gradient statistics: sum ||grad||^2 per side.  Fixed-shape block reduction -> one partial per CTA; the CTA that
   //      draws the last ticket adds the partials in CTA order (deterministic whichever CTA that is), then -- batch sharded
@@ -1583,8 +1584,8 @@ int peer_finish_launch(const upp_peer_exchange* peers, float* global_sums, cudaS
 
 size_t chamfer_bwd_stats_workspace_bytes(int B, int N, int M) {
   if (B <= 0 || N <= 0 || M <= 0) return 0;
-  // ticket (16 B) + one float per CTA; CTAs per cloud <= ceil(N / 64) + ceil(M / 64) (one-warp CTAs at worst)
-  return 16 + static_cast<size_t>(B) * ((N + 63) / 64 + (M + 63) / 64 + 2) * sizeof(float);
+  // ticket (16 B) + one float per CTA; CTAs per cloud <= ceil(N / 32) + ceil(M / 32) (one-warp CTAs, one destination per lane, at worst)
+  return 16 + static_cast<size_t>(B) * ((N + 31) / 32 + (M + 31) / 32 + 2) * sizeof(float);
 }
 
 // sq_out == nullptr: plain backward.  Otherwise sq_out[0..1] = sum ||grad_xyz1||^2, sum ||grad_xyz2||^2 (over all ranks
@@ -1594,11 +1595,13 @@ int chamfer_bwd_launch(const float* xyz1, const float* xyz2, const int32_t* idx1
                        float* sq_out, void* workspace, size_t workspace_bytes, const upp_peer_exchange* peers,
                        cudaStream_t st) {
   // one grid for both sides: the same CTA shape serves both (the smaller side just needs fewer CTAs)
-  const ScatterGrid a = scatter_grid(N, M, 2), c = scatter_grid(M, N, 2);
+  const int q = scatter_pick_q(B, N + M);
+  const ScatterGrid a = scatter_grid(N, M, q), c = scatter_grid(M, N, q);
   const int warps = a.warps > c.warps ? a.warps : c.warps;
-  const int blocks1 = (N + warps * 64 - 1) / (warps * 64), blocks2 = (M + warps * 64 - 1) / (warps * 64);
+  const int per = warps * 32 * q;
+  const int blocks1 = (N + per - 1) / per, blocks2 = (M + per - 1) / per;
   const int lmax = N > M ? N : M;  // the longer list sizes the staging area for both sides
-  const size_t smem = scatter_smem(lmax, warps, 2);
+  const size_t smem = scatter_smem(lmax, warps, q);
   unsigned* ticket = nullptr;
   float* partials = nullptr;
   if (sq_out != nullptr) {
@@ -1608,8 +1611,12 @@ int chamfer_bwd_launch(const float* xyz1, const float* xyz2, const int32_t* idx1
     cudaError_t e = cudaMemsetAsync(ticket, 0, 16, st);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  chamfer_bwd_kernel<<<dim3(blocks1 + blocks2, B), warps * 32, smem, st>>>(xyz1, xyz2, idx1, idx2, g1, g2, N, M, blocks1,
-                                                                          gx1, gx2, partials, ticket, sq_out, make_px(peers));
+  if (q == 1)
+    chamfer_bwd_kernel<1><<<dim3(blocks1 + blocks2, B), warps * 32, smem, st>>>(xyz1, xyz2, idx1, idx2, g1, g2, N, M, blocks1,
+                                                                               gx1, gx2, partials, ticket, sq_out, make_px(peers));
+  else
+    chamfer_bwd_kernel<2><<<dim3(blocks1 + blocks2, B), warps * 32, smem, st>>>(xyz1, xyz2, idx1, idx2, g1, g2, N, M, blocks1,
+                                                                               gx1, gx2, partials, ticket, sq_out, make_px(peers));
   count_launch();
   return launch_status();
 }

@@ -202,13 +202,17 @@ __device__ __forceinline__ unsigned cluster_nctarank() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
-// plain 32-bit store into the shared memory of CTA `rank`-mapped address (mapa result)
-__device__ __forceinline__ void st_cluster_u32(uint32_t remote_addr, int v) {
-  asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
+// Flag-style publish / poll of one 32-bit word in (distributed) shared memory, both sides ATOMIC so that the pair is a
+// synchronising access in the memory model (and in compute-sanitizer racecheck) rather than a racing store / load:
+//   publisher: red.max into the word of CTA `rank`-mapped address (mapa result) -- fire and forget, the slot starts at -1
+//              and receives a value >= 0 exactly once;
+//   poller:    atom.max with -1, i.e. an atomic read.
+__device__ __forceinline__ void publish_cluster_s32(uint32_t remote_addr, int v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.max.s32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ int ld_volatile_shared_s32(const int* p) {
+__device__ __forceinline__ int poll_shared_s32(const int* p) {
   int v;
-  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  asm volatile("atom.relaxed.cluster.shared::cta.max.s32 %0, [%1], -1;" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
 

@@ -44,12 +44,13 @@ struct GatherGradOp {
   }
 };
 
+template <int Q>
 __global__ void __launch_bounds__(256)
     gather_points_grad_kernel(const float* __restrict__ gout, const int32_t* __restrict__ idx, int C, int N, int M,
                               float* __restrict__ gfeat) {
   extern __shared__ int s_dst[];
   GatherGradOp op{gout, idx, gfeat, static_cast<int>(blockIdx.y), static_cast<int>(blockIdx.z) * 3, C, N, M};
-  ordered_scatter_cta<2>(op, N, s_dst);
+  ordered_scatter_cta<Q>(op, N, s_dst);
 }
 
 // neighborhood[b,g,j,:] = xyz[b, idx[b,g,j], :] - center[b,g,:]   (one thread per neighbour)
@@ -93,14 +94,14 @@ struct GroupBwdOp {
       const int g = e - nk;
       const float* p = gnb + (static_cast<size_t>(b) * G + g) * k * 3;
       float sx = 0.f, sy = 0.f, sz = 0.f;
-      for (int j0 = 0; j0 < k; j0 += 8) {  // 24 independent loads in flight, then the adds in j order
-        float t[8][3];
+      for (int j0 = 0; j0 < k; j0 += 16) {  // 48 independent loads in flight, then the adds in j order
+        float t[16][3];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 16; ++u)
 #pragma unroll
           for (int c = 0; c < 3; ++c) t[u][c] = j0 + u < k ? __ldg(p + 3 * (j0 + u) + c) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 16; ++u)
           if (j0 + u < k) { sx = __fadd_rn(sx, t[u][0]); sy = __fadd_rn(sy, t[u][1]); sz = __fadd_rn(sz, t[u][2]); }
       }
       v[0] = -sx; v[1] = -sy; v[2] = -sz;
@@ -117,13 +118,14 @@ struct GroupBwdOp {
   }
 };
 
+template <int Q>
 __global__ void __launch_bounds__(256)
     group_bwd_kernel(const float* __restrict__ gnb, const float* __restrict__ gcenter,
                      const int64_t* __restrict__ idx, const int32_t* __restrict__ cidx, int N, int G,
                      int k, float* __restrict__ gxyz) {
   extern __shared__ int s_dst[];
   GroupBwdOp op{gnb, gcenter, idx, cidx, gxyz, static_cast<int>(blockIdx.y), N, G, k};
-  ordered_scatter_cta<2>(op, N, s_dst);
+  ordered_scatter_cta<Q>(op, N, s_dst);
 }
 
 // grad[b, idx[b,j], :] += rows[b,j,:]  (row-major / channel-last; the gradient of the coordinate gather fused
@@ -151,12 +153,13 @@ struct RowsScatterOp {
   }
 };
 
+template <int Q>
 __global__ void __launch_bounds__(256)
     rows_scatter_add_kernel(const float* __restrict__ rows, const int32_t* __restrict__ idx, int N, int M, int C,
                             float* __restrict__ grad) {
   extern __shared__ int s_dst[];
   RowsScatterOp op{rows, idx, grad, static_cast<int>(blockIdx.y), static_cast<int>(blockIdx.z) * 3, C, N, M};
-  ordered_scatter_cta<2>(op, N, s_dst);
+  ordered_scatter_cta<Q>(op, N, s_dst);
 }
 
 static int grid_for(size_t total, int per_block) {
@@ -178,8 +181,10 @@ int gather_grad_launch(const float* gout, const int32_t* idx, int B, int C, int 
                        float* gfeat, cudaStream_t st) {
   if (static_cast<size_t>(B) * C * N == 0) return UPP_OK;
   // every destination is written exactly once (zero where nothing lands): no memset, no atomics
-  const ScatterGrid g = scatter_grid(N, M, 2);
-  gather_points_grad_kernel<<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(gout, idx, C, N, M, gfeat);
+  const int q = scatter_pick_q(B * ((C + 2) / 3), N);
+  const ScatterGrid g = scatter_grid(N, M, q);
+  if (q == 1) gather_points_grad_kernel<1><<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(gout, idx, C, N, M, gfeat);
+  else gather_points_grad_kernel<2><<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(gout, idx, C, N, M, gfeat);
   count_launch();
   return launch_status();
 }
@@ -187,8 +192,10 @@ int gather_grad_launch(const float* gout, const int32_t* idx, int B, int C, int 
 int rows_scatter_add_launch(const float* rows, const int32_t* idx, int B, int N, int M, int C, float* grad,
                             cudaStream_t st) {
   if (static_cast<size_t>(B) * N * C == 0) return UPP_OK;
-  const ScatterGrid g = scatter_grid(N, M, 2);
-  rows_scatter_add_kernel<<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(rows, idx, N, M, C, grad);
+  const int q = scatter_pick_q(B * ((C + 2) / 3), N);
+  const ScatterGrid g = scatter_grid(N, M, q);
+  if (q == 1) rows_scatter_add_kernel<1><<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(rows, idx, N, M, C, grad);
+  else rows_scatter_add_kernel<2><<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(rows, idx, N, M, C, grad);
   count_launch();
   return launch_status();
 }
@@ -205,8 +212,10 @@ int group_gather_launch(const float* xyz, const float* center, const int64_t* id
 int group_bwd_launch(const float* gnb, const float* gcenter, const int64_t* idx, const int32_t* cidx,
                      int B, int N, int G, int k, float* gxyz, cudaStream_t st) {
   if (static_cast<size_t>(B) * N == 0) return UPP_OK;
-  const ScatterGrid g = scatter_grid(N, G * k + G, 2);
-  group_bwd_kernel<<<dim3(g.blocks, B), g.warps * 32, g.smem, st>>>(gnb, gcenter, idx, cidx, N, G, k, gxyz);
+  const int q = scatter_pick_q(B, N);
+  const ScatterGrid g = scatter_grid(N, G * k + G, q);
+  if (q == 1) group_bwd_kernel<1><<<dim3(g.blocks, B), g.warps * 32, g.smem, st>>>(gnb, gcenter, idx, cidx, N, G, k, gxyz);
+  else group_bwd_kernel<2><<<dim3(g.blocks, B), g.warps * 32, g.smem, st>>>(gnb, gcenter, idx, cidx, N, G, k, gxyz);
   count_launch();
   return launch_status();
 }

@@ -7,10 +7,10 @@
 //   * every CTA of the cluster stages the cloud once (TMA bulk copy);
 //   * the first NW warps of CTA 0 are the PRODUCER: the register-resident FPS chain of fps_blk_kernel (blocked ownership,
 //     packed fp32x2 updates, REDUX arg-max, one named barrier among the NW warps per round).  When round j has picked
-//     its point, lanes 0..CS-1 of warp 0 store the index into slot j of EVERY CTA's centre table (one st.shared::cluster
-//     each) and the chain goes on -- nothing waits;
+//     its point, lanes 0..CS-1 of warp 0 publish the index into slot j of EVERY CTA's centre table (one fire-and-forget
+//     red.shared::cluster each) and the chain goes on -- nothing waits;
 //   * every other warp of the cluster is a CONSUMER: consumer c serves centres c, c + NC, c + 2 NC, ...; it polls slot j
-//     of its own CTA's table (shared-memory load, back-off by nanosleep), then runs the warp top-k of topk.cuh against
+//     of its own CTA's table (one lane, atomic read, back-off by nanosleep), then runs the warp top-k of topk.cuh against
 //     the staged cloud and writes centre j's outputs: neighbourhood (already centre-subtracted), centre, indices.
 // So the kNN of the first centres runs while the FPS chain is still producing the later ones; the launch ends one kNN
 // query after the last FPS round instead of a whole kNN kernel after it.  With few clouds (B * CS <= 148) the CTAs ask
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kGroupMaxThreads, 1)
             if (v[w + stride] > v[w]) { v[w] = v[w + stride]; ix[w] = ix[w + stride]; }  // strict: lower warp on ties
         sel = ix[0];
       }
-      if (warp == 0 && static_cast<unsigned>(lane) < cs) st_cluster_u32(table + 4u * static_cast<unsigned>(j), sel);
+      if (warp == 0 && static_cast<unsigned>(lane) < cs) publish_cluster_s32(table + 4u * static_cast<unsigned>(j), sel);
       cx = s_xyz[3 * sel];
       cy = s_xyz[3 * sel + 1];
       cz = s_xyz[3 * sel + 2];
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kGroupMaxThreads, 1)
       for (int j = c; j < G; j += nc) {
         int ci;
         do {
-          ci = __shfl_sync(0xffffffffu, ld_volatile_shared_s32(s_cidx + j), 0);
+          ci = __shfl_sync(0xffffffffu, (lane == 0 ? poll_shared_s32(s_cidx + j) : 0), 0);
           if (ci < 0) __nanosleep(40);
         } while (ci < 0);
         const float qx = s_xyz[3 * ci], qy = s_xyz[3 * ci + 1], qz = s_xyz[3 * ci + 2];

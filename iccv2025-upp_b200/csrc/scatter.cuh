@@ -66,26 +66,38 @@ __device__ __forceinline__ float ordered_scatter_cta(const Op& op, int N, int* s
   }
   __syncwarp();
   int count = 0;  // queued hits (warp-uniform)
-  auto flush = [&](int n) {  // the first n (<= 32) queued hits
-    float v[3] = {0.f, 0.f, 0.f};
-    int rel = -1 - lane;  // idle lanes: distinct negative keys, never matched
-    if (lane < n) {
-      const int2 h = s_q[lane];
-      rel = h.y;
-      op.fetch(h.x, j0 + rel, v);
-    }
-    const unsigned same = __match_any_sync(0xffffffffu, rel);
-    const int rank = __popc(same & lanes_below);          // position among the hits of this flush with my destination
+  // The values of a flushed batch are CONSUMED one flush later: the 32 loads issued here stay in flight while the scan
+  // goes on (it needs shared memory only), so their latency is hidden behind the next scan steps instead of stalling
+  // the warp once per batch.
+  float pv[3] = {0.f, 0.f, 0.f};  // pending batch: this lane's fetched value ...
+  int prel = -1 - lane;           // ... and its destination (negative: none; distinct keys so that nothing matches)
+  bool pending = false;           // warp-uniform
+  auto consume = [&]() {
+    if (!pending) return;
+    const unsigned same = __match_any_sync(0xffffffffu, prel);
+    const int rank = __popc(same & lanes_below);          // position among the hits of this batch with my destination
     const int rounds = redux_max_s32(rank) + 1;
     for (int r = 0; r < rounds; ++r) {
-      if (lane < n && rank == r) {
-        float* a = s_acc + rel * 3;
-        a[0] = __fadd_rn(a[0], v[0]);
-        a[1] = __fadd_rn(a[1], v[1]);
-        a[2] = __fadd_rn(a[2], v[2]);
+      if (prel >= 0 && rank == r) {
+        float* a = s_acc + prel * 3;
+        a[0] = __fadd_rn(a[0], pv[0]);
+        a[1] = __fadd_rn(a[1], pv[1]);
+        a[2] = __fadd_rn(a[2], pv[2]);
       }
       __syncwarp();
     }
+    pending = false;
+  };
+  auto flush = [&](int n) {  // the first n (<= 32) queued hits
+    consume();
+    pv[0] = pv[1] = pv[2] = 0.f;
+    prel = -1 - lane;
+    if (lane < n) {
+      const int2 h = s_q[lane];
+      prel = h.y;
+      op.fetch(h.x, j0 + prel, pv);
+    }
+    pending = true;
     // the hits behind the flushed ones move to the front of the queue
     int2 keep = make_int2(0, 0);
     if (lane + 32 < count) keep = s_q[lane + 32];
@@ -97,7 +109,14 @@ __device__ __forceinline__ float ordered_scatter_cta(const Op& op, int N, int* s
   for (int base = 0; base < L; base += kScatterTile) {
     const int tile = min(kScatterTile, L - base);
     if (base > 0) __syncthreads();
-    for (int e = threadIdx.x; e < tile; e += blockDim.x) s_dst[e] = op.dst(base + e);
+    for (int e = threadIdx.x; e < tile; e += 8 * blockDim.x) {  // 8 independent loads in flight per thread
+      int d[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) d[u] = e + u * blockDim.x < tile ? op.dst(base + e + u * blockDim.x) : 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (e + u * blockDim.x < tile) s_dst[e + u * blockDim.x] = d[u];
+    }
     __syncthreads();
     if (!warp_live) continue;
     for (int e0 = 0; e0 < tile; e0 += 128) {
@@ -123,6 +142,7 @@ __device__ __forceinline__ float ordered_scatter_cta(const Op& op, int N, int* s
   float sq = 0.f;
   if (!warp_live) return sq;
   if (count > 0) flush(count);
+  consume();
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     const int j = j0 + lane + 32 * q;
@@ -144,10 +164,12 @@ inline size_t scatter_smem(int L, int warps, int Q) {
   const int list_cap = ((L < kScatterTile ? (L < 0 ? 0 : L) : kScatterTile) + 3) & ~3;
   return static_cast<size_t>(list_cap) * sizeof(int) + static_cast<size_t>(warps) * scatter_warp_bytes(Q);
 }
+// destinations per lane: 2 when the batch fills the GPU anyway (half the scan work), 1 when warps are scarce (latency)
+inline int scatter_pick_q(int B, int N) { return static_cast<long>(B) * ((N + 63) / 64) >= 148L * 16 ? 2 : 1; }
 inline ScatterGrid scatter_grid(int N, int L, int Q) {
   const int need = (N + 32 * Q - 1) / (32 * Q);  // warps per cloud
   ScatterGrid g;
-  g.warps = need < 8 ? (need < 1 ? 1 : need) : 8;
+  g.warps = need < 8 ? (need < 1 ? 1 : need) : (Q == 1 ? 4 : 8);
   g.blocks = (need + g.warps - 1) / g.warps;
   if (g.blocks < 1) g.blocks = 1;
   g.smem = scatter_smem(L, g.warps, Q);
