@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <vector>
+
 #include "upp_geom.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -210,10 +213,54 @@ __device__ __forceinline__ unsigned cluster_nctarank() {
 __device__ __forceinline__ void publish_cluster_s32(uint32_t remote_addr, int v) {
   asm volatile("red.relaxed.cluster.shared::cluster.max.s32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
 }
+// (the plain-store / volatile-load flavour of the same hand-off, kept for A/B timing: UPP_GROUP_SYNC=0)
+__device__ __forceinline__ void st_cluster_s32(uint32_t remote_addr, int v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile_shared_s32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 __device__ __forceinline__ int poll_shared_s32(const int* p) {
   int v;
   asm volatile("atom.relaxed.cluster.shared::cta.max.s32 %0, [%1], -1;" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
+}
+
+// How many clusters of `cs` CTAs of this kernel can be resident at once with `smem` bytes of dynamic shared memory per
+// CTA (cudaOccupancyMaxActiveClusters; cached per configuration).  The GPC sizes of a B200 differ from chip to chip
+// (floor-sweeping), so "32 clusters of 4 whole-SM CTAs fit on 148 SMs" holds on one board and not on the next: a
+// cluster that does not fit runs as a second wave and the launch takes twice as long.
+template <class Kern>
+static int max_active_clusters(Kern kern, int cs, int threads, size_t smem) {
+  struct Key { int cs, threads; size_t smem; int n; };
+  static std::mutex mu;
+  static std::vector<Key> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Key& k : cache)
+    if (k.cs == cs && k.threads == threads && k.smem == smem) return k.n;
+  int n = 0;
+  if (smem <= 40 * 1024 ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(cs) * 148);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+      (void)cudaGetLastError();
+      n = 0;
+    }
+  }
+  cache.push_back({cs, threads, smem, n});
+  return n;
 }
 
 // ---- host-side launch check -----------------------------------------------------------

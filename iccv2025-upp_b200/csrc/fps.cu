@@ -771,8 +771,11 @@ static int launch_fps_cluster(const float* xyz, int B, int N, int M, int Nc, int
   // as for one CTA per cloud: while every CTA can have an SM of its own, keep throughput kernels off that SM --
   // up to 4 CTAs per cluster (measured: a cluster of 8 CTAs asking for the whole 227 KB each is not placed at all)
   const size_t need = static_cast<size_t>(N) * 3 * sizeof(float);
-  const size_t smem = CS <= 4 ? fps_smem_request(need, B * CS) : need;
   auto kern = fps_cluster_kernel<CS, NW, P2>;
+  size_t smem = CS <= 4 ? fps_smem_request(need, B * CS) : need;
+  // ... but only if ALL B whole-SM clusters fit at once on this very GPU (GPC sizes differ from chip to chip): a cluster
+  // left over runs as a second wave and doubles the launch
+  if (smem > need && max_active_clusters(kern, CS, NW * 32, smem) < B) smem = need;
   if (smem > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);

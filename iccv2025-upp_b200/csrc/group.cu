@@ -32,7 +32,7 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 
 template <int NW, int P2, int SLOTS>
 __global__ void __launch_bounds__(kGroupMaxThreads, 1)
-    group_fused_kernel(const float* __restrict__ xyz, int N, int G, int k, int cw0, float* __restrict__ nb_out,
+    group_fused_kernel(const float* __restrict__ xyz, int N, int G, int k, int cw0, int atomic_sync, float* __restrict__ nb_out,
                        float* __restrict__ center_out, int64_t* __restrict__ idx_out,
                        int32_t* __restrict__ cidx_out) {
   constexpr int P = 2 * P2;
@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(kGroupMaxThreads, 1)
             if (v[w + stride] > v[w]) { v[w] = v[w + stride]; ix[w] = ix[w + stride]; }  // strict: lower warp on ties
         sel = ix[0];
       }
-      if (warp == 0 && static_cast<unsigned>(lane) < cs) publish_cluster_s32(table + 4u * static_cast<unsigned>(j), sel);
+      if (warp == 0 && static_cast<unsigned>(lane) < cs) {
+        if (atomic_sync & 1) publish_cluster_s32(table + 4u * static_cast<unsigned>(j), sel);
+        else st_cluster_s32(table + 4u * static_cast<unsigned>(j), sel);
+      }
       cx = s_xyz[3 * sel];
       cy = s_xyz[3 * sel + 1];
       cz = s_xyz[3 * sel + 2];
@@ -130,9 +133,14 @@ __global__ void __launch_bounds__(kGroupMaxThreads, 1)
     if (c < nc && (rank != 0 || warp - NW < cw0)) {
       for (int j = c; j < G; j += nc) {
         int ci;
+        const int sleep_ns = (atomic_sync >> 4) & 0xff;  // tuning: UPP_GROUP_SYNC bits 4..11
+        const bool all_lanes = (atomic_sync & 2) != 0;   //         bit 1: every lane polls (plain flavour only)
         do {
-          ci = __shfl_sync(0xffffffffu, (lane == 0 ? poll_shared_s32(s_cidx + j) : 0), 0);
-          if (ci < 0) __nanosleep(40);
+          int v = 0;
+          if (all_lanes) v = ld_volatile_shared_s32(s_cidx + j);
+          else if (lane == 0) v = (atomic_sync & 1) ? poll_shared_s32(s_cidx + j) : ld_volatile_shared_s32(s_cidx + j);
+          ci = __shfl_sync(0xffffffffu, v, 0);
+          if (ci < 0 && sleep_ns > 0) __nanosleep(sleep_ns);
         } while (ci < 0);
         const float qx = s_xyz[3 * ci], qy = s_xyz[3 * ci + 1], qz = s_xyz[3 * ci + 2];
         DistDirect dist;
@@ -174,19 +182,32 @@ constexpr size_t kExclusiveSmemG = 232448 - 2048;  // 227 KB opt-in limit minus 
 
 template <int NW, int P2, int SLOTS>
 static int launch_group_fused(const float* xyz, int B, int N, int G, int k, float* nb, float* center, int64_t* idx,
-                              int32_t* cidx, int cs, int warps, cudaStream_t st) {
+                              int32_t* cidx, int cs_forced, int warps, cudaStream_t st) {
   const size_t need = static_cast<size_t>((3 * N + 3) & ~3) * sizeof(float) + static_cast<size_t>(G) * sizeof(int);
-  // few clouds: every CTA of every cluster gets an SM of its own (see fps.cu: a throughput CTA beside the FPS warps
-  // stretches every round)
-  // (clusters of up to 4 CTAs: a cluster of 8 CTAs asking for 227 KB each is not placed at all, see fps.cu)
-  const bool exclusive = cs <= 4 && static_cast<long>(B) * cs <= kNumSMsG && need < kExclusiveSmemG &&
-                         tuning_env_int("UPP_FPS_SHARE_SM", 0) != 1;
-  const size_t smem = exclusive ? kExclusiveSmemG : need;
   auto kern = group_fused_kernel<NW, P2, SLOTS>;
+  const bool may_reserve = need < kExclusiveSmemG && tuning_env_int("UPP_FPS_SHARE_SM", 0) != 1;
+  // Cluster size: the consumers of a cloud want SMs of their own (the FPS warps are latency-bound, see fps.cu), so the
+  // largest cluster of 4 / 3 / 2 whole-SM CTAs of which ALL B fit at once; failing that one CTA per cloud with producer
+  // and consumers side by side (many clouds: the SMs are full either way).  Clusters of 8 measured slower (B16: 20.6 us
+  // with 4, 22.7 with 8) and are only reachable through UPP_GROUP_CLUSTER.
+  int cs = 1;
+  bool exclusive = false;
+  if (cs_forced > 0) {
+    cs = cs_forced;
+    exclusive = may_reserve && cs <= 4 && cs > 1 && max_active_clusters(kern, cs, warps * 32, kExclusiveSmemG) >= B;
+  } else if (may_reserve) {
+    for (int tryc = 4; tryc >= 2; --tryc) {
+      if ((tryc - 1) * warps >= 2 * G && tryc > 2) continue;  // far more consumer warps than centres: a smaller cluster
+      if (max_active_clusters(kern, tryc, warps * 32, kExclusiveSmemG) >= B) { cs = tryc; exclusive = true; break; }
+    }
+  }
+  if (cs == 1 && cs_forced <= 0 && B > kNumSMsG && warps > 8) warps = 8;  // several clouds per SM
+  const size_t smem = exclusive ? kExclusiveSmemG : need;
   if (smem > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
   }
+  if (warps <= NW) return UPP_ERR_UNSUPPORTED;
   const int cw0 = cs > 1 ? 0 : warps - NW;  // consumers beside the producer only when the cluster is one CTA
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(B) * cs);
@@ -200,7 +221,10 @@ static int launch_group_fused(const float* xyz, int B, int N, int G, int k, floa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, N, G, k, cw0, nb, center, idx, cidx);
+  // hand-off flavour: bit 0 atomic publish / poll (else plain store + volatile load), bit 1 every lane polls,
+  // bits 4.. back-off in ns while a centre is not there yet (default: atomics, 40 ns)
+  const int atomic_sync = tuning_env_int("UPP_GROUP_SYNC", 1 | (40 << 4));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, N, G, k, cw0, atomic_sync, nb, center, idx, cidx);
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return launch_status();
@@ -220,15 +244,11 @@ int group_fused_launch(const float* xyz, int B, int N, int G, int k, float* nb, 
   if (tuning_env_int("UPP_GROUP_FUSED", 1) == 0) return UPP_ERR_UNSUPPORTED;  // A/B: the two-launch path
   const FpsBlkConfig c = fps_pick_blk(N, B);
   if (c.nw > 4 || c.p2 > 8 || static_cast<long>(c.nw) * 64 * c.p2 < N) return UPP_ERR_UNSUPPORTED;
-  // cluster size: as many consumer CTAs per cloud as the GPU has SMs for (2 / 4 / 8 CTAs per cluster), none beyond
-  // what G centres can use; UPP_GROUP_CLUSTER forces it (tests / tuning)
-  int cs = 1;
-  for (int tryc = 8; tryc >= 2; tryc >>= 1)
-    if (static_cast<long>(B) * tryc <= kNumSMsG) { cs = tryc; break; }
-  int warps = (cs == 1 && B > kNumSMsG) ? 8 : 16;
-  while (cs > 2 && (cs / 2 - 1) * warps >= G) cs >>= 1;  // more consumers than centres: shrink the cluster
+  // cluster size: chosen per launch from the occupancy of this very GPU (launch_group_fused); UPP_GROUP_CLUSTER /
+  // UPP_GROUP_WARPS force it (tests / tuning)
   const int forced = tuning_env_int("UPP_GROUP_CLUSTER", 0);
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) cs = forced;
+  const int cs = (forced == 1 || forced == 2 || forced == 3 || forced == 4 || forced == 8) ? forced : 0;
+  int warps = 16;
   const int fw = tuning_env_int("UPP_GROUP_WARPS", 0);
   if (fw == 8 || fw == 16) warps = fw;
   if (warps <= c.nw) return UPP_ERR_UNSUPPORTED;

@@ -4,9 +4,30 @@ torch is used for device memory, streams and autograd only; every computation be
 libupp_geom.so kernel.  Argument rules follow the ops these replace (file:line in each
 docstring): CUDA-only, fp32, contiguous; violations raise instead of printing.
 """
+import functools
+import os
+
 import torch
 
 from . import _lib
+
+# SURVEY.md 5 (tracing): UPP_NVTX=1 wraps every op in an NVTX range named after its C-ABI entry point, so that the ops
+# line up with the kernels in an nsys / ncu timeline.  Off by default: a range push / pop costs ~1 us of host time per op.
+_NVTX = os.environ.get("UPP_NVTX") == "1"
+
+
+def _traced(fn):
+    if not _NVTX:
+        return fn
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        torch.cuda.nvtx.range_push("upp_b200." + fn.__name__)
+        try:
+            return fn(*a, **k)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return wrapper
 
 
 def _stream(t):
@@ -59,6 +80,7 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+@_traced
 def fps(xyz, npoint, want_centers=False):
     """Farthest point sampling; replaces pointnet2_utils.furthest_point_sample (utils/misc.py:18)
     and, with want_centers, also the gather of utils/misc.py:19.
@@ -81,6 +103,7 @@ def fps(xyz, npoint, want_centers=False):
     return (idx, centers) if want_centers else idx
 
 
+@_traced
 def gather(features, idx):
     """features (B,C,N) f32, idx (B,M) int32 -> (B,C,M); replaces gather_operation fwd (utils/misc.py:19)."""
     _need("features", features, torch.float32, 3)
@@ -96,6 +119,7 @@ def gather(features, idx):
     return out
 
 
+@_traced
 def gather_grad(grad_out, idx, N):
     """grad_out (B,C,M), idx (B,M) int32 -> grad_features (B,C,N) (scatter-add)."""
     _need("grad_out", grad_out, torch.float32, 3)
@@ -108,6 +132,7 @@ def gather_grad(grad_out, idx, N):
     return g
 
 
+@_traced
 def rows_scatter_add(grad_rows, idx, N):
     """grad_rows (B,M,C), idx (B,M) int32 -> (B,N,C): gradient of the row-major gather rows = x[b, idx[b,j], :]
     (what misc.fps returns as fps_data)."""
@@ -121,6 +146,7 @@ def rows_scatter_add(grad_rows, idx, N):
     return g
 
 
+@_traced
 def knn(ref, query, k, want_dist=True):
     """ref (B,N,3), query (B,Q,3) -> D (B,Q,k) f32 Euclidean ascending, I (B,Q,k) int64;
     replaces KNN(k, transpose_mode=True).forward (models/Point_MAE_unify.py:69)."""
@@ -143,6 +169,7 @@ def knn(ref, query, k, want_dist=True):
     return D, I
 
 
+@_traced
 def chamfer_forward(xyz1, xyz2, want_sums=False):
     """chamfer.forward (extensions/chamfer_dist/chamfer.cu:147-171):
     -> [dist1 (B,N), dist2 (B,M) f32 squared, idx1, idx2 int32] (+ 4-float partial sums)."""
@@ -170,6 +197,7 @@ def chamfer_forward(xyz1, xyz2, want_sums=False):
     return [d1, d2, i1, i2] + ([sums] if want_sums else [])
 
 
+@_traced
 def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, want_sqnorm=False, peers=None):
     """chamfer.backward (extensions/chamfer_dist/chamfer.cu:203-229) -> [grad_xyz1, grad_xyz2].
     grad_dist* may arrive non-contiguous (expanded scalars from mean/sqrt backward); they are
@@ -213,6 +241,7 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2, want_sqnorm
     return [gx1, gx2]
 
 
+@_traced
 def group(xyz, num_group, group_size):
     """Fused Group divider (models/Point_MAE_unify.py:58-92):
     -> neighborhood (B,G,k,3), center (B,G,3), idx (B,G,k) int64 local, center_idx (B,G) int32."""
@@ -236,6 +265,7 @@ def group(xyz, num_group, group_size):
     return nb, ce, idx, cidx
 
 
+@_traced
 def group_backward(grad_nb, grad_center, idx, center_idx, N):
     """Gradient of the fused Group w.r.t. xyz -> (B,N,3)."""
     _need("grad_nb", grad_nb, torch.float32, 4)
@@ -252,6 +282,7 @@ def group_backward(grad_nb, grad_center, idx, center_idx, N):
     return gx
 
 
+@_traced
 def interp_forward(xyz1, xyz2, points2, k, eps, base=None, alpha=1.0, want_dist=True):
     """k-nearest inverse-distance interpolation of points2 (B,S,C) from xyz2 (B,S,3) onto xyz1 (B,N,3):
     the body of propagate (models/Point_MAE_unify.py:22-48) and of PointNetFeaturePropagation's
@@ -283,6 +314,7 @@ def interp_forward(xyz1, xyz2, points2, k, eps, base=None, alpha=1.0, want_dist=
     return out, idx, w, d
 
 
+@_traced
 def interp_select(xyz1, xyz2, k, eps, want_dist=True):
     """Selection half of interp_forward alone (upp_interp_select_f32): -> idx (B,N,k) int32, weight (B,N,k), dist (B,N,k)."""
     _xyz("xyz1", xyz1)
@@ -304,6 +336,7 @@ def interp_select(xyz1, xyz2, k, eps, want_dist=True):
     return idx, w, d
 
 
+@_traced
 def interp_blend(points2, idx, weight, base=None, alpha=1.0):
     """Blend half of interp_forward from a saved selection (upp_interp_blend_f32): -> out (B,N,C), bit-identical to what
     interp_forward returns for the same inputs."""
@@ -326,6 +359,7 @@ def interp_blend(points2, idx, weight, base=None, alpha=1.0):
     return out
 
 
+@_traced
 def interp_backward(grad_out, idx, weight, S, alpha=1.0, xyz_terms=None):
     """Gradients of interp_forward: grad_points2 (B,S,C) always; with xyz_terms = (dist, points2, xyz1, xyz2, eps)
     also grad_xyz1 (B,N,3), grad_xyz2 (B,S,3) (the path through the weights).  Deterministic, no atomics."""
@@ -359,6 +393,7 @@ def interp_backward(grad_out, idx, weight, S, alpha=1.0, xyz_terms=None):
     return gp2, g1, g2
 
 
+@_traced
 def knn_points(p1, p2, K, want_nn=False):
     """pytorch3d.ops.knn_points convention (models/Point_MAE_pretask_dev.py:680): p1 (B,N1,3) queries,
     p2 (B,N2,3) references -> dists (B,N1,K) f32 SQUARED ascending, idx (B,N1,K) int64 [, nn (B,N1,K,3)]."""
@@ -383,6 +418,7 @@ def knn_points(p1, p2, K, want_nn=False):
     return d, i, nn
 
 
+@_traced
 def crop_split(xyz, viewpoints, num_crop, padding_zeros=False, want_order=False):
     """The crop of misc.seprate_point_cloud (utils/misc.py:232-239) for the whole batch in one launch:
     xyz (B,n,3), viewpoints (B,3) -> (input (B,n-num_crop,3) or (B,n,3) when padding_zeros, crop (B,num_crop,3)[, order (B,n) int32])."""
@@ -405,6 +441,7 @@ def crop_split(xyz, viewpoints, num_crop, padding_zeros=False, want_order=False)
     return (inp, crop, order) if want_order else (inp, crop)
 
 
+@_traced
 def peer_allreduce_finish(peers, device):
     """upp_peer_allreduce_finish_f32: second half of a deferred exchange -> global sums (4 floats)."""
     import ctypes
@@ -415,6 +452,7 @@ def peer_allreduce_finish(peers, device):
     return sums
 
 
+@_traced
 def peer_allreduce(peers, local4=None, defer=False):
     """upp_peer_allreduce_f32: SUM all-reduce of 4 floats over the mapped peer buffers (local4 None: zeros -- what a rank
     with an EMPTY shard contributes).  -> global sums (4 floats), or the local ones when defer=True."""
@@ -429,6 +467,7 @@ def peer_allreduce(peers, local4=None, defer=False):
     return out
 
 
+@_traced
 def chamfer_forward_sharded(xyz1, xyz2, peers, defer=False):
     """upp_chamfer_fwd_sharded_f32: chamfer.forward of this rank's clouds, fused with the all-reduce of its sums
     over NVLink peer memory.  `peers` is a parallel.PeerExchange.  -> [dist1, dist2, idx1, idx2, global_sums].

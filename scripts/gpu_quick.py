@@ -50,7 +50,9 @@ g = torch.Generator().manual_seed(0)
 # Group: fused (cluster shapes) vs two launches
 for B, N, G, k in ((32, 1024, 64, 32), (128, 1024, 64, 32), (32, 2048, 128, 32), (32, 1096, 32, 16), (32, 64, 32, 8), (64, 1024, 64, 32), (16, 1024, 64, 32)):
     x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)
-    for tag, kw in (("default", {}), ("two_launch", dict(UPP_GROUP_FUSED=0)), ("cs1", dict(UPP_GROUP_CLUSTER=1)), ("cs2", dict(UPP_GROUP_CLUSTER=2)),
+    for tag, kw in (("default", {}), ("plain all-lanes sleep40", dict(UPP_GROUP_SYNC=2 | (40 << 4))), ("plain lane0 sleep40", dict(UPP_GROUP_SYNC=0 | (40 << 4))),
+                    ("plain lane0 spin", dict(UPP_GROUP_SYNC=0)), ("atomic spin", dict(UPP_GROUP_SYNC=1)), ("atomic sleep100", dict(UPP_GROUP_SYNC=1 | (100 << 4))),
+                    ("atomic sleep20", dict(UPP_GROUP_SYNC=1 | (20 << 4))), ("two_launch", dict(UPP_GROUP_FUSED=0)), ("cs1", dict(UPP_GROUP_CLUSTER=1)), ("cs2", dict(UPP_GROUP_CLUSTER=2)), ("cs3", dict(UPP_GROUP_CLUSTER=3)),
                     ("cs4", dict(UPP_GROUP_CLUSTER=4)), ("cs8_w8", dict(UPP_GROUP_CLUSTER=8, UPP_GROUP_WARPS=8)), ("cs4_w8", dict(UPP_GROUP_CLUSTER=4, UPP_GROUP_WARPS=8))):
         env(**kw)
         try:

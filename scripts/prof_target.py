@@ -39,6 +39,11 @@ for _ in range(4):
         x = (torch.rand(32, 8192, 3, generator=g) * 2 - 1).to(dev)
         c = torch.nn.functional.normalize(torch.randn(32, 3, generator=g), dim=-1).to(dev)
         ops.crop_split(x, c, 2048)
+    elif what == "scatter":  # the two remaining gather-gradient shapes of the default step + the channel-first gather grad
+        rows = torch.randn(32, 1024, 3, generator=g).to(dev)
+        idx = torch.stack([torch.randperm(1228, generator=g)[:1024] for _ in range(32)]).to(torch.int32).to(dev)
+        ops.rows_scatter_add(rows, idx, 1228)
+        ops.gather_grad(rows.transpose(1, 2).contiguous(), idx, 1228)
     elif what == "knn":
         r = (torch.rand(32, 1024, 3, generator=g) * 2 - 1).to(dev)
         ops.knn(r, r[:, :64].contiguous(), 32)

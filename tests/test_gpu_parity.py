@@ -911,6 +911,7 @@ GROUP_KERNELS = {  # name -> tuning environment (read per launch by group_fused_
     "fused_cluster1": {"UPP_GROUP_CLUSTER": "1"},                 # producer and consumers in one CTA
     "fused_cluster1_w8": {"UPP_GROUP_CLUSTER": "1", "UPP_GROUP_WARPS": "8"},
     "fused_cluster2": {"UPP_GROUP_CLUSTER": "2"},                 # consumers on their own SMs, centres published over DSMEM
+    "fused_cluster3": {"UPP_GROUP_CLUSTER": "3"},
     "fused_cluster4": {"UPP_GROUP_CLUSTER": "4"},
     "fused_cluster8": {"UPP_GROUP_CLUSTER": "8", "UPP_GROUP_WARPS": "8"},
     "two_launch": {"UPP_GROUP_FUSED": "0"},                       # fps_launch + knn_launch (round-1 path)
