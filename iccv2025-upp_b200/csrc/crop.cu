@@ -15,7 +15,7 @@
 // Distance: sqrt_rn(fma(dz,dz,fma(dy,dy,dx*dx))) with d* = viewpoint - point -- torch.norm's sum of squares in x,y,z
 // order followed by the square root; the ordering is what matters, and the golden fixtures made by the reference's
 // own function (tests/golden/golden_seprate.npz) pin it.
-#include "common.cuh"
+#include "bitonic.cuh"
 
 namespace upp {
 
@@ -51,71 +51,8 @@ __global__ void __launch_bounds__(kCropThreads, 1)
     s_key[i] = key;
   }
   __syncthreads();
-  // ---- bitonic sort, ascending.  A thread owns 8 consecutive keys, a warp 256: every compare-exchange at distance
-  //      <= 128 stays inside a warp (distances 8..128: lane-xor shuffles, 4 / 2 / 1: registers), so only distances
-  //      >= 256 go through shared memory with a CTA barrier: 21 barrier-separated passes for 8192 keys instead of 91.
-  const int lane = t & 31;
-  const int e0 = t * 8;                      // first key of this thread
-  const bool owner = e0 < npow2;             // whole warps (npow2 is a multiple of 256)
-  auto warp_pass = [&](unsigned long long (&v)[8], int size) {   // distances min(size/2, 128) ... 1 of the merge `size`
-    for (int stride = min(size >> 1, 128); stride >= 8; stride >>= 1) {
-      const int lx = stride >> 3;
-      const bool keep_min = ((lane & lx) == 0) == ((e0 & size) == 0);
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lx);
-        v[r] = ((v[r] < o) == keep_min) ? v[r] : o;  // one 64-bit compare + one select (keys are distinct)
-      }
-    }
-#pragma unroll
-    for (int stride = 4; stride >= 1; stride >>= 1) {
-      if (stride <= (size >> 1)) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          if ((r & stride) == 0) {
-            const bool up = ((e0 + r) & size) == 0;
-            const unsigned long long x = v[r], y = v[r | stride];
-            const bool keep = (x < y) == up;
-            v[r] = keep ? x : y;
-            v[r | stride] = keep ? y : x;
-          }
-        }
-      }
-    }
-  };
-  {
-    unsigned long long v[8];
-    if (owner) {
-#pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = s_key[e0 + r];
-      for (int size = 2; size <= 256; size <<= 1) warp_pass(v, size);   // (npow2 >= 256)
-#pragma unroll
-      for (int r = 0; r < 8; ++r) s_key[e0 + r] = v[r];
-    }
-    __syncthreads();
-    for (int size = 512; size <= npow2; size <<= 1) {
-      for (int stride = size >> 1; stride >= 256; stride >>= 1) {
-        for (int i = t; i < (npow2 >> 1); i += kCropThreads) {
-          const int lo_i = 2 * i - (i & (stride - 1));
-          const int hi_i = lo_i + stride;
-          const unsigned long long x = s_key[lo_i], y = s_key[hi_i];
-          const bool up = (lo_i & size) == 0;
-          const bool keep = (x < y) == up;
-          s_key[lo_i] = keep ? x : y;
-          s_key[hi_i] = keep ? y : x;
-        }
-        __syncthreads();
-      }
-      if (owner) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = s_key[e0 + r];
-        warp_pass(v, size);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) s_key[e0 + r] = v[r];
-      }
-      __syncthreads();
-    }
-  }
+  // bitonic sort, ascending (bitonic.cuh: 8 keys per thread in registers, shuffles up to distance 128, shared memory beyond)
+  bitonic_sort_cta<unsigned long long, 8>(s_key, npow2);
   // split + gathers
   const int n_in = n - num_crop;
   float* crop_b = crop_out + static_cast<size_t>(b) * num_crop * 3;

@@ -47,6 +47,16 @@ def env(**kw):
 
 
 g = torch.Generator().manual_seed(0)
+# large-cloud FPS: Morton buckets + exact pruning vs the plain kernels (one CTA per cloud / clusters of CTAs)
+for B, N, M in ((128, 8192, 1024), (16, 8192, 1024), (32, 6144, 1024), (32, 4096, 1024), (32, 2500, 300), (64, 8192, 128)):
+    x = (torch.randn(B, N, 3, generator=g) * 0.35)
+    x = x - x.mean(1, keepdim=True)
+    x = (x / x.norm(dim=2).max(dim=1)[0].view(-1, 1, 1)).to(dev)
+    for tag, kw in (("default", {}), ("pruned nw8", dict(UPP_FPS_PRUNED=1)), ("pruned nw4", dict(UPP_FPS_PRUNED=1, UPP_FPS_PRUNED_NW=4)),
+                    ("pruned nw16", dict(UPP_FPS_PRUNED=1, UPP_FPS_PRUNED_NW=16)), ("one CTA per cloud", dict(UPP_FPS_CLUSTER=0))):
+        env(**kw)
+        rec(f"fps B{B} N{N} M{M} [{tag}]", timeit(lambda: o.fps(x, M, True), reps=5, iters=5))
+        env(**{kk: None for kk in kw})
 # Group: fused (cluster shapes) vs two launches
 for B, N, G, k in ((32, 1024, 64, 32), (128, 1024, 64, 32), (32, 2048, 128, 32), (32, 1096, 32, 16), (32, 64, 32, 8), (64, 1024, 64, 32), (16, 1024, 64, 32)):
     x = (torch.rand(B, N, 3, generator=g) * 2 - 1).to(dev)

@@ -40,7 +40,11 @@ FPS_SHAPES = [  # (B, N, M)  -- SURVEY.md Appendix A census + edges
 
 
 FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
-    "default": {},                                                        # v2, heuristic warps x pairs
+    "default": {},                                                        # heuristic: v2 warps x pairs; large clouds: clusters / deferred search
+    "pruned": {"UPP_FPS_PRUNED": "1"},                                    # Morton buckets + exact pruning (experiment, N > 2048)
+    "pruned_from_256": {"UPP_FPS_PRUNED": "1", "UPP_FPS_PRUNED_MIN": "255"},  # ... forced onto small clouds too
+    "pruned_nw4": {"UPP_FPS_PRUNED": "1", "UPP_FPS_PRUNED_NW": "4", "UPP_FPS_PRUNED_MIN": "255"},
+    "pruned_nw16": {"UPP_FPS_PRUNED": "1", "UPP_FPS_PRUNED_NW": "16"},
     "v2_nw1": {"UPP_FPS_NW": "1", "UPP_FPS_P2": "8"},                     # single warp, no barrier (N <= 512)
     "v2_nw2": {"UPP_FPS_NW": "2", "UPP_FPS_P2": "8"},                     # (N <= 1024)
     "v2_nw4_redux": {"UPP_FPS_NW": "4", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1"},
@@ -109,6 +113,29 @@ def test_fps_exact_ties_lowest_index(U, O, dev, fps_kernel):
     xyz = torch.cat([grid, grid.flip(1)], 0).contiguous()
     got = U.ops.fps(xyz.to(dev), 100).cpu().numpy()
     assert np.array_equal(got, O.fps(xyz.numpy(), 100))
+
+
+def test_fps_pruned_large_lattice_ties_and_degenerate_clouds(U, O, dev, fps_kernel):
+    """Large clouds (the Morton-bucket kernel by default): a 16^3 lattice (thousands of exactly equal distances: the
+    arg-max must resolve to the lowest ORIGINAL index although the kernel works on a sorted copy), a cloud of duplicates,
+    a flat cloud (one axis constant), every point inside the skip radius, and M > N."""
+    ax = torch.arange(16, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3) * 0.25 + 0.5
+    perm = torch.randperm(4096, generator=torch.Generator().manual_seed(3))
+    xyz = torch.cat([grid, grid[:, perm]], 0).contiguous()
+    assert np.array_equal(U.ops.fps(xyz.to(dev), 300).cpu().numpy(), O.fps(xyz.numpy(), 300))
+    dup = cube(2, 3000, 8)
+    dup[:, 1500:] = dup[:, :1500]
+    assert np.array_equal(U.ops.fps(dup.to(dev), 200).cpu().numpy(), O.fps(dup.numpy(), 200))
+    flat = cube(2, 2600, 9)
+    flat[..., 2] = 0.25
+    assert np.array_equal(U.ops.fps(flat.to(dev), 100).cpu().numpy(), O.fps(flat.numpy(), 100))
+    tiny = cube(1, 2300, 10) * 0.01
+    assert np.array_equal(U.ops.fps(tiny.to(dev), 40).cpu().numpy(), O.fps(tiny.numpy(), 40))
+    small = cube(1, 2100, 11)
+    assert np.array_equal(U.ops.fps(small.to(dev), 2200).cpu().numpy(), O.fps(small.numpy(), 2200))
+    idx, cen = U.ops.fps(xyz.to(dev), 64, True)
+    assert torch.equal(cen.cpu(), torch.gather(xyz, 1, idx.cpu().long()[..., None].expand(-1, -1, 3)))
 
 
 def test_fps_duplicates_all_skipped_and_m_gt_n(U, O, dev):
