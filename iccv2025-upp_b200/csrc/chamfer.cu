@@ -1611,12 +1611,12 @@ int chamfer_bwd_launch(const float* xyz1, const float* xyz2, const int32_t* idx1
     cudaError_t e = cudaMemsetAsync(ticket, 0, 16, st);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  if (q == 1)
-    chamfer_bwd_kernel<1><<<dim3(blocks1 + blocks2, B), warps * 32, smem, st>>>(xyz1, xyz2, idx1, idx2, g1, g2, N, M, blocks1,
-                                                                               gx1, gx2, partials, ticket, sq_out, make_px(peers));
-  else
-    chamfer_bwd_kernel<2><<<dim3(blocks1 + blocks2, B), warps * 32, smem, st>>>(xyz1, xyz2, idx1, idx2, g1, g2, N, M, blocks1,
-                                                                               gx1, gx2, partials, ticket, sq_out, make_px(peers));
+  const PeerXchg px = make_px(peers);
+  cudaError_t le = q == 1 ? launch_pdl(chamfer_bwd_kernel<1>, dim3(blocks1 + blocks2, B), dim3(warps * 32), smem, st, xyz1, xyz2, idx1, idx2,
+                                       g1, g2, N, M, blocks1, gx1, gx2, partials, ticket, sq_out, px)
+                          : launch_pdl(chamfer_bwd_kernel<2>, dim3(blocks1 + blocks2, B), dim3(warps * 32), smem, st, xyz1, xyz2, idx1, idx2,
+                                       g1, g2, N, M, blocks1, gx1, gx2, partials, ticket, sq_out, px);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return launch_status();
 }

@@ -263,6 +263,37 @@ static int max_active_clusters(Kern kern, int cs, int threads, size_t smem) {
   return n;
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------
+// The chains on this path are runs of short DEPENDENT kernels (FPS -> FPS -> Group -> Group -> four gradient kernels in
+// the UPP step), each edge costing ~2.4 us of launch latency in a CUDA graph.  A kernel launched with the programmatic
+// stream-serialization attribute may start (be scheduled, run its prologue) while its predecessor is still running; it
+// calls pdl_wait() before it touches anything the predecessor wrote (griddepcontrol.wait returns when the prerequisite
+// grids have completed and their memory is visible).  pdl_trigger() lets this grid's own dependents start early; it is
+// issued first thing, which is always safe because they wait the same way.  Kernels launched WITHOUT the attribute
+// execute both instructions as no-ops, and a predecessor that never triggers (a torch kernel) simply releases its
+// dependents when it exits.
+// MEASURED AND LEFT OFF (round 2, bench.py headline step, two runs each): device-resident 0.2859 -> 0.2887 ms without it
+// (-1 %), but the end-to-end arm -- H2D copies and autograd's backward thread in the same graph -- went from 0.324 to
+// 0.376 ms with it: dependents that are resident early and parked in griddepcontrol.wait hold whole-SM shared-memory
+// reservations the other branches of the step are waiting for.  UPP_PDL=1 (under UPP_TUNING=1) turns it on for A/B.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class Kern, class... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tuning_env_int("UPP_PDL", 0) == 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // ---- host-side launch check -----------------------------------------------------------
 inline int launch_status() {
   cudaError_t e = cudaGetLastError();

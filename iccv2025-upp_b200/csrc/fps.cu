@@ -316,11 +316,13 @@ __global__ void __launch_bounds__(NW * 32)
   int32_t* out = idx_out + static_cast<size_t>(b) * M;
   float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
 
+  pdl_trigger();  // (programmatic dependent launch, common.cuh: the next kernel of the chain may be scheduled now)
   if (t == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_wait();     // the cloud may come from the kernel in front of this one
   unsigned parity = 0;
   stage_points(s_xyz, p, N, &s_bar, parity);
 
@@ -729,7 +731,8 @@ static int launch_fps_blk(const float* xyz, int B, int N, int M, int32_t* idx, f
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  kern<<<B, NW * 32, smem, st>>>(xyz, N, M, idx, centers);
+  cudaError_t le = launch_pdl(kern, dim3(B), dim3(NW * 32), smem, st, xyz, N, M, idx, centers);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return launch_status();
 }

@@ -183,8 +183,9 @@ int gather_grad_launch(const float* gout, const int32_t* idx, int B, int C, int 
   // every destination is written exactly once (zero where nothing lands): no memset, no atomics
   const int q = scatter_pick_q(B * ((C + 2) / 3), N);
   const ScatterGrid g = scatter_grid(N, M, q);
-  if (q == 1) gather_points_grad_kernel<1><<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(gout, idx, C, N, M, gfeat);
-  else gather_points_grad_kernel<2><<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(gout, idx, C, N, M, gfeat);
+  cudaError_t le = q == 1 ? launch_pdl(gather_points_grad_kernel<1>, dim3(g.blocks, B, (C + 2) / 3), dim3(g.warps * 32), g.smem, st, gout, idx, C, N, M, gfeat)
+                          : launch_pdl(gather_points_grad_kernel<2>, dim3(g.blocks, B, (C + 2) / 3), dim3(g.warps * 32), g.smem, st, gout, idx, C, N, M, gfeat);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return launch_status();
 }
@@ -194,8 +195,9 @@ int rows_scatter_add_launch(const float* rows, const int32_t* idx, int B, int N,
   if (static_cast<size_t>(B) * N * C == 0) return UPP_OK;
   const int q = scatter_pick_q(B * ((C + 2) / 3), N);
   const ScatterGrid g = scatter_grid(N, M, q);
-  if (q == 1) rows_scatter_add_kernel<1><<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(rows, idx, N, M, C, grad);
-  else rows_scatter_add_kernel<2><<<dim3(g.blocks, B, (C + 2) / 3), g.warps * 32, g.smem, st>>>(rows, idx, N, M, C, grad);
+  cudaError_t le = q == 1 ? launch_pdl(rows_scatter_add_kernel<1>, dim3(g.blocks, B, (C + 2) / 3), dim3(g.warps * 32), g.smem, st, rows, idx, N, M, C, grad)
+                          : launch_pdl(rows_scatter_add_kernel<2>, dim3(g.blocks, B, (C + 2) / 3), dim3(g.warps * 32), g.smem, st, rows, idx, N, M, C, grad);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return launch_status();
 }
@@ -214,8 +216,9 @@ int group_bwd_launch(const float* gnb, const float* gcenter, const int64_t* idx,
   if (static_cast<size_t>(B) * N == 0) return UPP_OK;
   const int q = scatter_pick_q(B, N);
   const ScatterGrid g = scatter_grid(N, G * k + G, q);
-  if (q == 1) group_bwd_kernel<1><<<dim3(g.blocks, B), g.warps * 32, g.smem, st>>>(gnb, gcenter, idx, cidx, N, G, k, gxyz);
-  else group_bwd_kernel<2><<<dim3(g.blocks, B), g.warps * 32, g.smem, st>>>(gnb, gcenter, idx, cidx, N, G, k, gxyz);
+  cudaError_t le = q == 1 ? launch_pdl(group_bwd_kernel<1>, dim3(g.blocks, B), dim3(g.warps * 32), g.smem, st, gnb, gcenter, idx, cidx, N, G, k, gxyz)
+                          : launch_pdl(group_bwd_kernel<2>, dim3(g.blocks, B), dim3(g.warps * 32), g.smem, st, gnb, gcenter, idx, cidx, N, G, k, gxyz);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return launch_status();
 }

@@ -50,12 +50,14 @@ __global__ void __launch_bounds__(kGroupMaxThreads, 1)
   const int b = blockIdx.x / cs;
   const float* p = xyz + static_cast<size_t>(b) * N * 3;
 
+  pdl_trigger();  // (programmatic dependent launch, common.cuh)
   if (t == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
   }
   for (int j = t; j < G; j += blockDim.x) s_cidx[j] = j == 0 ? 0 : -1;  // FPS starts at point 0
   __syncthreads();
+  pdl_wait();     // the cloud may come from the kernel in front of this one
   unsigned parity = 0;
   stage_points(s_xyz, p, N, &s_bar, parity);
   if (cs > 1) cluster_sync_all();  // every CTA's table is initialised before the producer writes into it
@@ -214,13 +216,15 @@ static int launch_group_fused(const float* xyz, int B, int N, int G, int k, floa
   cfg.blockDim = dim3(warps * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = tuning_env_int("UPP_PDL", 0) == 1 ? 2 : 1;
   // hand-off flavour: bit 0 atomic publish / poll (else plain store + volatile load), bit 1 every lane polls,
   // bits 4.. back-off in ns while a centre is not there yet (default: atomics, 40 ns)
   const int atomic_sync = tuning_env_int("UPP_GROUP_SYNC", 1 | (40 << 4));

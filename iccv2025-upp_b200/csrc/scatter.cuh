@@ -55,6 +55,8 @@ __device__ __forceinline__ float ordered_scatter_cta(const Op& op, int N, int* s
   int2* s_q = reinterpret_cast<int2*>(wbase);
   float* s_acc = reinterpret_cast<float*>(wbase + 64 * 8);  // [32 * Q][3]: stride 3 words, conflict-free across lanes
   const unsigned lanes_below = (1u << lane) - 1u;
+  pdl_trigger();  // (programmatic dependent launch, common.cuh: the gradient chain is a run of short dependent kernels)
+  pdl_wait();     // everything read below may come from the kernel in front of this one
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     const int j = j0 + lane + 32 * q;
