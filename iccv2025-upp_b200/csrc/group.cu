@@ -197,7 +197,7 @@ static int launch_group_fused(const float* xyz, int B, int N, int G, int k, floa
   if (cs_forced > 0) {
     cs = cs_forced;
     exclusive = may_reserve && cs <= 4 && cs > 1 && max_active_clusters(kern, cs, warps * 32, kExclusiveSmemG) >= B;
-  } else if (may_reserve) {
+  } else if (may_reserve && N > 256) {  // (tiny clouds: one warp of FPS, a handful of queries -- one CTA does it all)
     for (int tryc = 4; tryc >= 2; --tryc) {
       if ((tryc - 1) * warps >= 2 * G && tryc > 2) continue;  // far more consumer warps than centres: a smaller cluster
       if (max_active_clusters(kern, tryc, warps * 32, kExclusiveSmemG) >= B) { cs = tryc; exclusive = true; break; }
