@@ -5,8 +5,10 @@
 // dependent warp-wide reductions -- bucket maximum + arg (2 REDUX), warp winner (2), block winner (2), ~60-80 cycles
 // each with the move out of the uniform register file -- and lands at 0.50 us per round whatever N and whatever the
 // warp count (4 / 8 / 16 measured: 638 / 613 / 578 us for B128 8192 -> 1024 against 555 us plain and 318 us for the
-// cluster kernel at B16).  What would make it pay: one 64-bit shared-memory atomicMax per warp in place of the block
-// stage, the bucket-level reductions taken off the chain (a stale bucket maximum is a valid, conservative skip bound).
+// cluster kernel at B16).  Also tried: lane-local candidates (bucket-level reductions off the dependent chain) + one 64-bit
+// shared-memory atomicMax per warp in place of the block stage -- 642-696 us, slower still.  The bound is not yet
+// understood (issue slots 47 %, barrier wait 33 % of the samples: the slowest warp of a round, the one with two or three
+// buckets to update); it needs a per-round timeline, not more guesses.
 //
 // Same operator as fps.cu (pointnet2_ops furthest_point_sample, reference call sites utils/misc.py:18,
 // tools/runner_module.py:310: the 8192 -> 1024 resampling of every ShapeNet55 batch), same results bit for bit.  What
