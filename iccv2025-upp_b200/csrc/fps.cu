@@ -873,6 +873,7 @@ FpsBlkConfig fps_pick_blk(int N, int B) {
   case T: return launch_fps_reg<T, 2>(xyz, B, N, M, idx, centers, st);
 
 int fps_pruned_launch(const float*, int, int, int, int32_t*, float*, cudaStream_t);  // fps_pruned.cu
+int fps_rows_launch(const float*, int, int, int, int32_t*, float*, cudaStream_t);    // fps_pruned.cu
 
 int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -880,9 +881,10 @@ int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* cente
   // the distance updates skipped, but its round is a chain of six dependent warp reductions (0.50 us at any N, against
   // 0.54 us for the plain kernel at N = 8192 and 0.30 us on clusters; profiles/r02_fps_pruned.txt).  UPP_FPS_PRUNED=1
   // (under UPP_TUNING=1) routes clouds of more than UPP_FPS_PRUNED_MIN (2048) points to it: the parity tests do.
-  if (env_int("UPP_FPS_PRUNED", 0) == 1 && N > env_int("UPP_FPS_PRUNED_MIN", 2048) && N <= kFpsMaxRegPoints && M >= 32 &&
+  const int pruned = env_int("UPP_FPS_PRUNED", 0);
+  if (pruned >= 1 && N > env_int("UPP_FPS_PRUNED_MIN", 2048) && N <= kFpsMaxRegPoints && M >= 32 &&
       env_int("UPP_FPS_CLUSTER", -1) < 1 && env_int("UPP_FPS_NW", 0) == 0 && env_int("UPP_FPS_IMPL", 2) != 1) {
-    const int rc = fps_pruned_launch(xyz, B, N, M, idx, centers, st);
+    const int rc = pruned == 2 ? fps_rows_launch(xyz, B, N, M, idx, centers, st) : fps_pruned_launch(xyz, B, N, M, idx, centers, st);
     if (rc != UPP_ERR_UNSUPPORTED) return rc;
   }
   if (const int cs = fps_pick_cluster(B, N)) {  // few large clouds: one cloud per cluster of CTAs

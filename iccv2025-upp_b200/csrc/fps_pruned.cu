@@ -34,6 +34,9 @@
 // arg-max key carries the original index above the sorted position).  Upstream semantics kept: start at index 0,
 // temp = 1e10, points with x^2+y^2+z^2 <= 1e-3 never selected, M > N allowed.
 #include <limits.h>
+#include <stdio.h>
+
+#include <type_traits>
 
 #include "bitonic.cuh"
 #include "fps_round.cuh"
@@ -282,6 +285,439 @@ static int launch_pruned(const float* xyz, int B, int N, int M, int32_t* idx, fl
   fps_pruned_kernel<NW><<<B, NW * 32, smem, st>>>(xyz, N, NP, npow2, M, idx, centers);
   count_launch();
   return launch_status();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fps_rows_kernel -- the third cut of the pruned round, built around what the two above taught: the bound is the length
+// of the DEPENDENT chain of a round AND the instructions every warp issues per round (two warps share a scheduler, and
+// the integer / compare / select pipe runs at half rate: a first version of this kernel with a 60-instruction
+// "resolve the eight posts" tail in every warp measured 0.8 us per round, 240 cycles of it that tail).
+//   * the sorted cloud lives in REGISTERS exactly as in fps_blk_kernel (packed fp32x2 coordinates, running min-distances),
+//     but ownership is by ROWS: row r of warp w is the 64 consecutive sorted points [(w * RPW + r) * 64, +64), two per lane.
+//     A row is a spatial bucket (Z-curve neighbours) with its box and its largest min-distance in lane r;
+//   * a round starts with the lane-parallel box test (one ballot -> a warp-uniform mask of rows that can change), then
+//     updates only those rows behind warp-uniform branches.  A warp with an empty mask copies its previous record and
+//     goes straight to the barrier: no distance work, no reduction;
+//   * the arg-max costs ONE REDUX per active warp: every lane keeps a max tree over its own rows (rebuilt above the
+//     touched leaves), position-independent -- ties are not ordered by position here (the sort permutes the indices) but
+//     DETECTED (two equal children on the winning lane's tree descent, two lanes in the ballot, two warps' records) and
+//     sent to a slow path that takes the lowest ORIGINAL index over all points holding the maximum.  Real clouds never
+//     take it; lattices and duplicated points take it and stay exact;
+//   * the winning lane posts {key, position | tie flag} AND the point's coordinates (its tree descent ends at a
+//     compile-time register), so after the barrier a round is: 8 lanes load the 8 keys, one REDUX, one ballot, one
+//     LDS.128 of the winner's record -> the next centre.  No second shared-memory round trip;
+//   * the row bounds are refreshed (one REDUX per touched row) after the barrier, in the shadow of that key load.
+// One barrier per round, 8 warps, 1 CTA per SM.
+template <int P2>
+struct RowTree {
+  static constexpr int N1 = (P2 + 2) / 3, N2 = (N1 + 2) / 3, N3 = (N2 + 2) / 3;
+  static_assert(N3 == 1, "RowTree covers up to 27 rows");
+  int l0[P2], l1[N1], l2[N2], l3[1];  // l0[r] = max of row r's two keys (order-preserving float bits)
+
+  template <int NI, int NO>
+  static __device__ __forceinline__ void fold(const int (&in)[NI], int (&out)[NO]) {
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+      int v = in[3 * q];
+      if (3 * q + 1 < NI) v = max(v, in[3 * q + 1]);
+      if (3 * q + 2 < NI) v = max(v, in[3 * q + 2]);
+      out[q] = v;
+    }
+  }
+  template <int Q>
+  __device__ __forceinline__ void fold1() {  // level-1 node Q from its leaves
+    int v = l0[3 * Q];
+    if constexpr (3 * Q + 1 < P2) v = max(v, l0[3 * Q + 1]);
+    if constexpr (3 * Q + 2 < P2) v = max(v, l0[3 * Q + 2]);
+    l1[Q] = v;
+  }
+  __device__ __forceinline__ int top() {  // the levels above l1
+    fold(l1, l2); fold(l2, l3);
+    return l3[0];
+  }
+  __device__ __forceinline__ int build() {
+    fold(l0, l1);
+    return top();
+  }
+  template <int LEVEL>
+  __device__ __forceinline__ int at(int q) const {
+    if constexpr (LEVEL == 0) return l0[q];
+    else if constexpr (LEVEL == 1) return l1[q];
+    else if constexpr (LEVEL == 2) return l2[q];
+    else return l3[q];
+  }
+  template <int LEVEL>
+  static __host__ __device__ constexpr int size() { return LEVEL == 0 ? P2 : LEVEL == 1 ? N1 : LEVEL == 2 ? N2 : 1; }
+  // A SLOT (2 * row + half) whose key equals `best` (the root) under node Q of LEVEL, and its coordinates (the leaf is a
+  // compile-time register).  `tie` is raised when two children of a visited node both hold `best`: any second slot
+  // holding the maximum shares such a node with the one returned.
+  template <int LEVEL, int Q>
+  __device__ __forceinline__ int descend(int best, bool& tie, const float (&md)[2 * P2], const f32x2 (&X)[P2],
+                                         const f32x2 (&Y)[P2], const f32x2 (&Z)[P2], float4& rec) const {
+    if constexpr (LEVEL == 0) {
+      const bool e0 = __float_as_int(md[2 * Q]) == best, e1 = __float_as_int(md[2 * Q + 1]) == best;
+      tie = tie || (e0 && e1);
+      float x0, x1, y0, y1, z0, z1;
+      unpack2(X[Q], x0, x1); unpack2(Y[Q], y0, y1); unpack2(Z[Q], z0, z1);
+      rec.x = e0 ? x0 : x1; rec.y = e0 ? y0 : y1; rec.z = e0 ? z0 : z1;
+      return 2 * Q + (e0 ? 0 : 1);
+    } else {
+      constexpr int n = size<LEVEL - 1>();
+      constexpr int c0 = 3 * Q;
+      if constexpr (c0 + 1 >= n) {
+        return descend<LEVEL - 1, c0>(best, tie, md, X, Y, Z, rec);
+      } else {
+        const bool e0 = at<LEVEL - 1>(c0) == best, e1 = at<LEVEL - 1>(c0 + 1) == best;
+        bool e2 = false;
+        if constexpr (c0 + 2 < n) e2 = at<LEVEL - 1>(c0 + 2) == best;
+        tie = tie || (e0 && (e1 || e2)) || (e1 && e2);
+        if (e0) return descend<LEVEL - 1, c0>(best, tie, md, X, Y, Z, rec);
+        if constexpr (c0 + 2 < n) {
+          if (e1) return descend<LEVEL - 1, c0 + 1>(best, tie, md, X, Y, Z, rec);
+          return descend<LEVEL - 1, c0 + 2>(best, tie, md, X, Y, Z, rec);
+        } else {
+          return descend<LEVEL - 1, c0 + 1>(best, tie, md, X, Y, Z, rec);
+        }
+      }
+    }
+  }
+};
+
+#ifdef UPP_ROWS_PROFILE  // debug build (make EXTRA=-DUPP_ROWS_PROFILE): per-phase cycle sums of block 0, printed per warp
+#define UPP_PROF(i_) { const long long c_ = clock64(); prof[i_] += c_ - tlast; tlast = c_; }
+#else
+#define UPP_PROF(i_)
+#endif
+
+constexpr int kRowWarps = 8, kRowThreads = kRowWarps * 32, kRowKpt = kPrMaxN / kRowThreads;  // 32 sort keys per thread
+
+// a warp's candidate of a round: 32 bytes, {key, position | tie flag << 31, -, -} {x, y, z, position | tie flag << 31}
+struct __align__(16) RowRec {
+  int key, pf, pad0, pad1;
+  float x, y, z;
+  int pf2;
+};
+
+template <int P2>
+__global__ void __launch_bounds__(kRowThreads, 1)
+    fps_rows_kernel(const float* __restrict__ xyz, int N, int RPW, int npow2, int M, int32_t* __restrict__ idx_out,
+                    float* __restrict__ centers_out) {
+  constexpr int NW = kRowWarps;
+  const int CAP = NW * RPW * 64;  // sorted slots (>= N); slot (w, r, lane, h) = (w * RPW + r) * 64 + 2 * lane + h
+  extern __shared__ __align__(16) float s_pts[];                      // 3 * CAP floats: the sorted cloud
+  unsigned* s_key = reinterpret_cast<unsigned*>(s_pts + 3 * CAP);    // npow2 sort keys
+  unsigned short* s_orig = reinterpret_cast<unsigned short*>(s_key + npow2);  // CAP original indices
+  __shared__ float s_red[6][NW];
+  __shared__ RowRec s_rec[2][NW];
+  __shared__ __align__(8) int2 s_max[3];
+  __shared__ unsigned s_tie[NW];
+
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int b = blockIdx.x;
+  const float* p = xyz + static_cast<size_t>(b) * N * 3;
+  int32_t* out = idx_out + static_cast<size_t>(b) * M;
+  float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
+
+  // ---- 1. Z-order sort of the cloud (as fps_pruned_kernel) ----
+  {
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int i = t; i < N; i += kRowThreads) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float v = __ldg(p + 3 * i + a);
+        lo[a] = fminf(lo[a], v);
+        hi[a] = fmaxf(hi[a], v);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = warp_min_f(lo[a]);
+      hi[a] = warp_max_f(hi[a]);
+      if (lane == 0) { s_red[a][warp] = lo[a]; s_red[3 + a][warp] = hi[a]; }
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float l = s_red[a][0], h = s_red[3 + a][0];
+      for (int w = 1; w < NW; ++w) { l = fminf(l, s_red[a][w]); h = fmaxf(h, s_red[3 + a][w]); }
+      lo[a] = l;
+      scale[a] = h > l ? 63.99f / (h - l) : 0.f;
+    }
+    for (int i = t; i < npow2; i += kRowThreads) {
+      unsigned key = 0xffffffffu;  // padding sorts last
+      if (i < N) {
+        unsigned q[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float f = (__ldg(p + 3 * i + a) - lo[a]) * scale[a];
+          q[a] = static_cast<unsigned>(fminf(fmaxf(f, 0.f), 63.f));
+        }
+        key = (morton18(q[0], q[1], q[2]) << 13) | static_cast<unsigned>(i);
+      }
+      s_key[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_cta<unsigned, kRowKpt>(s_key, npow2);
+    for (int pos = t; pos < CAP; pos += kRowThreads) {
+      float x = 0.f, y = 0.f, z = 0.f;
+      unsigned orig = 0;
+      if (pos < N) {
+        orig = s_key[pos] & 8191u;
+        x = __ldg(p + 3 * orig); y = __ldg(p + 3 * orig + 1); z = __ldg(p + 3 * orig + 2);
+      }
+      s_pts[3 * pos] = x; s_pts[3 * pos + 1] = y; s_pts[3 * pos + 2] = z;
+      s_orig[pos] = static_cast<unsigned short>(orig);
+    }
+    __syncthreads();
+  }
+
+  // ---- 2. registers: my two points of every row, their min-distances, the row boxes / bounds (lane r: row r) ----
+  f32x2 X[P2], Y[P2], Z[P2];
+  float md[2 * P2];
+  RowTree<P2> tr;
+  float blo[3] = {0.f, 0.f, 0.f}, bhi[3] = {0.f, 0.f, 0.f};
+  // lane r: row r's largest min-distance times (1 + 2^-17), rounded up -- the safety margin of the skip test against the
+  // rounding of the box distance; -1: nothing left to update (all selected) or nothing selectable
+  float thr = -1.0f;
+  const int slot0 = warp * RPW * 64 + 2 * lane;
+#pragma unroll
+  for (int r = 0; r < P2; ++r) {
+    float c[2][3];
+    float l3[3] = {3.4e38f, 3.4e38f, 3.4e38f}, h3[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pos = slot0 + r * 64 + h;
+      if (r < RPW && pos < N) {
+        c[h][0] = s_pts[3 * pos]; c[h][1] = s_pts[3 * pos + 1]; c[h][2] = s_pts[3 * pos + 2];
+        md[2 * r + h] = fps_initial_md(c[h][0], c[h][1], c[h][2]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { l3[a] = fminf(l3[a], c[h][a]); h3[a] = fmaxf(h3[a], c[h][a]); }
+      } else {
+        c[h][0] = c[h][1] = c[h][2] = 0.f;
+        md[2 * r + h] = kOutOfRange;
+      }
+    }
+    X[r] = pack2(c[0][0], c[1][0]);
+    Y[r] = pack2(c[0][1], c[1][1]);
+    Z[r] = pack2(c[0][2], c[1][2]);
+    tr.l0[r] = max(__float_as_int(md[2 * r]), __float_as_int(md[2 * r + 1]));
+    if (r < RPW) {  // warp-uniform
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        l3[a] = warp_min_f(l3[a]);
+        h3[a] = warp_max_f(h3[a]);
+        if (lane == r) { blo[a] = l3[a]; bhi[a] = h3[a]; }
+      }
+      const int v = redux_max_s32(tr.l0[r]);
+      if (lane == r) thr = v > 0 ? __fmul_ru(__int_as_float(v), 1.0000076294f) : -1.0f;
+    }
+  }
+
+  const unsigned lanes_below = (1u << lane) - 1u;
+  // the warp's candidate: one REDUX over the lanes' tree roots; the lowest lane holding it walks its tree down, writes
+  // the warp's record and enters the key in the round's two arg-max words (see the resolve step below)
+  auto warp_post = [&](int best, RowRec* recs, int2* mx) {
+    const int wbest = redux_max_s32(best);
+    const unsigned winners = __ballot_sync(0xffffffffu, best == wbest);
+    if (best == wbest && (winners & lanes_below) == 0u) {
+      atomicMax(&mx->x, (wbest & ~7) | warp);
+      atomicMax(&mx->y, (wbest & ~7) | (7 - warp));
+      bool tie = (winners & (winners - 1u)) != 0u;  // a second lane holds it too
+      float4 rc;
+      const int sl = tr.template descend<3, 0>(wbest, tie, md, X, Y, Z, rc);
+      int pf = slot0 + (sl >> 1) * 64 + (sl & 1);
+      if (tie) pf |= static_cast<int>(0x80000000u);
+      int4* dst = reinterpret_cast<int4*>(&recs[warp]);
+      dst[0] = make_int4(wbest, pf, 0, 0);
+      dst[1] = make_int4(__float_as_int(rc.x), __float_as_int(rc.y), __float_as_int(rc.z), pf);
+    }
+  };
+  if (t < 3) s_max[t] = make_int2(INT_MIN, INT_MIN);
+  __syncthreads();
+  warp_post(tr.build(), s_rec[0], &s_max[0]);
+
+  // first centre: original index 0 -- its coordinates straight from global memory
+  float cx = __ldg(p), cy = __ldg(p + 1), cz = __ldg(p + 2);
+  if (t == 0) out[0] = 0;
+  __syncthreads();
+
+  const bool odd1 = (lane & 1) != 0, odd2 = (lane & 2) != 0;
+  const int my_nibble = lane >> 2;
+#ifdef UPP_ROWS_PROFILE
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+  int nactive = 0, nrows = 0, nties = 0, nslow = 0;
+#endif
+  int cur = 1;  // j % 3: the round's arg-max words
+  for (int j = 1; j < M; ++j) {
+    // ---- a. which of my rows can change?  lane r tests row r (lanes >= RPW hold thr = -1: never).  A row is skipped
+    //         only when every point's distance provably exceeds the row's largest min-distance: thr carries the margin ----
+    const float ex = fmaxf(fmaxf(blo[0] - cx, cx - bhi[0]), 0.f);
+    const float ey = fmaxf(fmaxf(blo[1] - cy, cy - bhi[1]), 0.f);
+    const float ez = fmaxf(fmaxf(blo[2] - cz, cz - bhi[2]), 0.f);
+    const float dlb = __fmaf_rn(ez, ez, __fmaf_rn(ex, ex, __fmul_rn(ey, ey)));
+    const unsigned mask = __ballot_sync(0xffffffffu, !(dlb > thr));
+    RowRec* recs = s_rec[j & 1];
+    int2* mx = &s_max[cur];
+    UPP_PROF(0)
+#ifdef UPP_ROWS_PROFILE
+    nactive += mask != 0u; nrows += __popc(mask);
+#endif
+    if (mask != 0u) {  // warp-uniform
+      const f32x2 CX = pack2(cx, cx), CY = pack2(cy, cy), CZ = pack2(cz, cz);
+      // Update granularity: NIBBLES of four rows, their chains interleaved (a lone row is a 6-deep dependent chain; rows
+      // that did not need it come out unchanged).  Rows due in the same round are Z-curve neighbours: ~1.2 nibbles per
+      // active warp.  One code path per nibble keeps the loop inside the instruction cache (the per-row / per-group /
+      // all-rows variants of the first cut stalled on instruction fetch at every branch target).
+      auto update_nibble = [&](auto gc) {
+        constexpr int R0 = decltype(gc)::value, NR = (P2 - R0 < 4 ? P2 - R0 : 4);
+        f32x2 D[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) D[r] = sub2(Y[R0 + r], CY);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) D[r] = mul2(D[r], D[r]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { const f32x2 dx = sub2(X[R0 + r], CX); D[r] = fma2(dx, dx, D[r]); }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { const f32x2 dz = sub2(Z[R0 + r], CZ); D[r] = fma2(dz, dz, D[r]); }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          float d0, d1;
+          unpack2(D[r], d0, d1);
+          md[2 * (R0 + r)] = fminf(md[2 * (R0 + r)], d0);
+          md[2 * (R0 + r) + 1] = fminf(md[2 * (R0 + r) + 1], d1);
+          tr.l0[R0 + r] = max(__float_as_int(md[2 * (R0 + r)]), __float_as_int(md[2 * (R0 + r) + 1]));
+        }
+        constexpr int Q0 = R0 / 3, Q1 = (R0 + NR - 1) / 3;  // the level-1 nodes above these rows
+        tr.template fold1<Q0>();
+        if constexpr (Q1 != Q0) tr.template fold1<Q1>();
+        if constexpr (Q1 > Q0 + 1) tr.template fold1<Q0 + 1>();
+      };
+#define UPP_NIBBLE(G_) \
+  if constexpr ((G_) < P2) if ((mask >> (G_)) & 0xfu) update_nibble(std::integral_constant<int, (G_)>{});
+      UPP_NIBBLE(0) UPP_NIBBLE(4) UPP_NIBBLE(8) UPP_NIBBLE(12)
+#undef UPP_NIBBLE
+      const int best = tr.top();
+      UPP_PROF(1)
+      warp_post(best, recs, mx);
+      UPP_PROF(2)
+    } else if (lane < 8) {  // nothing of mine changed: the previous record stands (8 lanes x 4 bytes; lane 0 holds the key)
+      const int wd = reinterpret_cast<const int*>(&s_rec[(j & 1) ^ 1][warp])[lane];
+      reinterpret_cast<int*>(&recs[warp])[lane] = wd;
+      if (lane == 0) {
+        atomicMax(&mx->x, (wd & ~7) | warp);
+        atomicMax(&mx->y, (wd & ~7) | (7 - warp));
+      }
+    }
+    __syncthreads();
+    UPP_PROF(3)
+    // ---- b. block winner.  The posting lanes entered (key & ~7) | warp and (key & ~7) | (7 - warp) with two native
+    //         32-bit shared-memory atomic maxima: when both name the same warp it alone holds the largest key prefix, hence
+    //         the largest key -- one LDS.64, one LDS.128 of its record, and the next centre is known.  Two warps within
+    //         8 ulp of each other (or a flagged record) take the exact path ----
+    const int2 ab = *mx;
+    const int wa = ab.x & 7, wb = 7 - (ab.y & 7);
+    int4 win = reinterpret_cast<const int4*>(&recs[wa])[1];  // {x, y, z, position | tie flag}
+    if (t == 64) s_max[cur == 0 ? 2 : cur - 1] = make_int2(INT_MIN, INT_MIN);  // (j + 2) % 3: last read in round j - 1
+    cur = cur == 2 ? 0 : cur + 1;
+    // ---- c. refresh the bounds of the nibbles touched (in the shadow of those loads): lane r keeps row r's ----
+    if (mask != 0u) {
+#define UPP_REFRESH(G_)                                                                                    \
+  if constexpr ((G_) < P2) if ((mask >> (G_)) & 0xfu) {                                                    \
+    const int v0 = redux_max_s32(tr.l0[(G_)]);                                                             \
+    const int v1 = (G_) + 1 < P2 ? redux_max_s32(tr.l0[(G_) + 1 < P2 ? (G_) + 1 : 0]) : -1;                \
+    const int v2 = (G_) + 2 < P2 ? redux_max_s32(tr.l0[(G_) + 2 < P2 ? (G_) + 2 : 0]) : -1;                \
+    const int v3 = (G_) + 3 < P2 ? redux_max_s32(tr.l0[(G_) + 3 < P2 ? (G_) + 3 : 0]) : -1;                \
+    const int lo_ = odd1 ? v1 : v0, hi_ = odd1 ? v3 : v2;                                                  \
+    const int v = odd2 ? hi_ : lo_;                                                                        \
+    if (my_nibble == (G_) / 4) thr = v > 0 ? __fmul_ru(__int_as_float(v), 1.0000076294f) : -1.0f;          \
+  }
+      UPP_REFRESH(0) UPP_REFRESH(4) UPP_REFRESH(8) UPP_REFRESH(12)
+#undef UPP_REFRESH
+    }
+    UPP_PROF(4)
+    int kbest = 0;
+    bool tied = win.w < 0;
+    if (wa != wb || tied) {  // block-uniform, rare: resolve on the exact keys
+#ifdef UPP_ROWS_PROFILE
+      ++nslow;
+#endif
+      const int kw = lane < NW ? recs[lane].key : INT_MIN;
+      kbest = redux_max_s32(kw);
+      const unsigned holders = __ballot_sync(0xffffffffu, kw == kbest);
+      win = reinterpret_cast<const int4*>(&recs[__ffs(holders) - 1])[1];
+      tied = (holders & (holders - 1u)) != 0u || win.w < 0;
+    }
+    cx = __int_as_float(win.x);
+    cy = __int_as_float(win.y);
+    cz = __int_as_float(win.z);
+    int pos = win.w & 8191;
+    if (tied) {  // block-uniform: several points hold the maximum -> the lowest ORIGINAL index among all of them
+#ifdef UPP_ROWS_PROFILE
+      ++nties;
+#endif
+      unsigned cand = 0xffffffffu;
+#pragma unroll
+      for (int s = 0; s < 2 * P2; ++s) {
+        if (__float_as_int(md[s]) == kbest) {
+          const int ps = slot0 + (s >> 1) * 64 + (s & 1);
+          cand = min(cand, (static_cast<unsigned>(s_orig[ps]) << 13) | static_cast<unsigned>(ps));
+        }
+      }
+      cand = redux_min_u32(cand);
+      if (lane == 0) s_tie[warp] = cand;
+      __syncthreads();
+      unsigned m = s_tie[0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) m = min(m, s_tie[w]);
+      pos = static_cast<int>(m & 8191u);
+      cx = s_pts[3 * pos];
+      cy = s_pts[3 * pos + 1];
+      cz = s_pts[3 * pos + 2];
+    }
+    if (t == 0) out[j] = pos;  // sorted position for now: a store with nothing to wait for (translated after the loop)
+    UPP_PROF(5)
+  }
+#ifdef UPP_ROWS_PROFILE
+  if (b == 0 && lane == 0)
+    printf("rows prof warp %d: box %lld update %lld post %lld barrier %lld resolve+refresh %lld tail %lld | active rounds %d rows %d slow %d ties %d of %d rounds\n",
+           warp, prof[0] / (M - 1), prof[1] / (M - 1), prof[2] / (M - 1), prof[3] / (M - 1), prof[4] / (M - 1), prof[5] / (M - 1), nactive, nrows, nslow, nties, M - 1);
+#endif
+  // sorted positions -> original indices, and the centres (the fused gather of utils/misc.py:19), by the whole CTA
+  __syncthreads();  // thread 0's out[] stores are visible to the block
+  for (int j = 1 + t; j < M; j += kRowThreads) {
+    const int pos = out[j];
+    out[j] = static_cast<int32_t>(s_orig[pos]);
+    if (cen) { cen[3 * j] = s_pts[3 * pos]; cen[3 * j + 1] = s_pts[3 * pos + 1]; cen[3 * j + 2] = s_pts[3 * pos + 2]; }
+  }
+  if (cen && t == 0) { cen[0] = __ldg(p); cen[1] = __ldg(p + 1); cen[2] = __ldg(p + 2); }
+}
+
+template <int P2>
+static int launch_rows(const float* xyz, int B, int N, int M, int32_t* idx, float* centers, cudaStream_t st) {
+  const int nrows = (N + 63) / 64;
+  const int rpw = (nrows + kRowWarps - 1) / kRowWarps;
+  const int cap = kRowWarps * rpw * 64;
+  int npow2 = 32 * kRowKpt;  // one warp-sorted block at least
+  while (npow2 < N) npow2 <<= 1;
+  size_t smem = static_cast<size_t>(cap) * 12 + static_cast<size_t>(npow2) * 4 + static_cast<size_t>(cap) * 2 + 16;
+  if (B <= 148 && smem < 229376) smem = 229376;  // as every FPS chain kernel: keep throughput CTAs off this SM (fps.cu)
+  cudaError_t e = cudaFuncSetAttribute(fps_rows_kernel<P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  fps_rows_kernel<P2><<<B, kRowThreads, smem, st>>>(xyz, N, rpw, npow2, M, idx, centers);
+  count_launch();
+  return launch_status();
+}
+
+int fps_rows_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers, cudaStream_t st) {
+  if (N > kPrMaxN || N < 64) return UPP_ERR_UNSUPPORTED;
+  const int rpw = ((N + 63) / 64 + kRowWarps - 1) / kRowWarps;
+  if (rpw <= 4) return launch_rows<4>(xyz, B, N, M, idx, centers, st);
+  if (rpw <= 8) return launch_rows<8>(xyz, B, N, M, idx, centers, st);
+  if (rpw <= 12) return launch_rows<12>(xyz, B, N, M, idx, centers, st);
+  return launch_rows<16>(xyz, B, N, M, idx, centers, st);
 }
 
 // UPP_OK when the pruned kernel took the call, UPP_ERR_UNSUPPORTED when the shape is outside it.

@@ -35,6 +35,12 @@ for _ in range(4):
         ops.fps((torch.rand(32, 6144, 3, generator=g) * 2 - 1).to(dev), 1024)
     elif what == "fps_cluster8":  # C4 sharded over 8 GPUs: 16 clouds of 8192 points per GPU
         ops.fps((torch.rand(16, 8192, 3, generator=g) * 2 - 1).to(dev), 1024)
+    elif what in ("fps_rows", "fps_rows_small"):  # register-resident rows + exact pruning (fps_pruned.cu)
+        os.environ["UPP_TUNING"], os.environ["UPP_FPS_PRUNED"], os.environ["UPP_FPS_PRUNED_MIN"] = "1", "2", "63"
+        B, N = (128, 8192) if what == "fps_rows" else (32, 1228)
+        x = torch.randn(B, N, 3, generator=g) * 0.35
+        x = x - x.mean(1, keepdim=True)
+        ops.fps((x / x.norm(dim=2).max(dim=1)[0].view(-1, 1, 1)).to(dev), 1024)
     elif what == "crop":
         x = (torch.rand(32, 8192, 3, generator=g) * 2 - 1).to(dev)
         c = torch.nn.functional.normalize(torch.randn(32, 3, generator=g), dim=-1).to(dev)

@@ -45,6 +45,8 @@ FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
     "pruned_from_256": {"UPP_FPS_PRUNED": "1", "UPP_FPS_PRUNED_MIN": "255"},  # ... forced onto small clouds too
     "pruned_nw4": {"UPP_FPS_PRUNED": "1", "UPP_FPS_PRUNED_NW": "4", "UPP_FPS_PRUNED_MIN": "255"},
     "pruned_nw16": {"UPP_FPS_PRUNED": "1", "UPP_FPS_PRUNED_NW": "16"},
+    "rows": {"UPP_FPS_PRUNED": "2"},                                      # register-resident rows + exact pruning (N > 2048)
+    "rows_from_64": {"UPP_FPS_PRUNED": "2", "UPP_FPS_PRUNED_MIN": "63"},  # ... forced onto small clouds too
     "v2_nw1": {"UPP_FPS_NW": "1", "UPP_FPS_P2": "8"},                     # single warp, no barrier (N <= 512)
     "v2_nw2": {"UPP_FPS_NW": "2", "UPP_FPS_P2": "8"},                     # (N <= 1024)
     "v2_nw4_redux": {"UPP_FPS_NW": "4", "UPP_FPS_P2": "8", "UPP_FPS_S2": "1"},
