@@ -22,7 +22,11 @@ Prints ONE JSON line (rank 0).  Top level = the headline workload:
                (all cores, and the reference's own OMP_NUM_THREADS=5, main.py:2-3)
   configs      one sub-record per other BASELINE.json config -- c1 (configs[0]), c3 (configs[2]), c4 (configs[3]),
                c5 (configs[4]) -- each with value / ms_per_step / e2e / kernels / roofline (/ cpu_baseline at N=1);
-               c3 also times the reference's own chamfer.cu (oracle/_ref, compiled unmodified) on the same GPU.
+               c3 also times the reference's own chamfer.cu (oracle/_ref, compiled unmodified) on the same GPU, and
+               carries `training_shapes`: forward / backward of the three shapes the pre-training calls Chamfer on.
+  step_ms      p10 / p50 / p90 of the per-step CUDA-event times (device arm and every e2e arm)
+  e2e_dropin_launch_blocking   the headline step through the unchanged call sites, eager, with CUDA_LAUNCH_BLOCKING=1
+               as the reference ships (main.py:5) -- a child process, host wall clock
   strong       (N > 1) C4 with its GLOBAL batch of 128 clouds split over the N ranks (BASELINE.json configs[3]).
 `--workload c1|c3|c4|c5` runs that config alone as the top-level record (profiling); `--no-configs` skips the
 sub-records.  N > 1 (torchrun): batch sharded, the Chamfer-loss all-reduce fused into the kernels over NVLink peer
@@ -512,6 +516,7 @@ class Ctx:
         synchronize on both sides of every region.  Returns the median region's ms (max over ranks per region)."""
         K = self.args.steps
         out = []
+        self.last_steps_ms = []
         for _ in range(regions or self.regions):
             self.barrier()
             evs = []
@@ -523,11 +528,20 @@ class Ctx:
                 e.record()
                 evs.append((s, e))
             self.barrier()
-            out.append(sum(s.elapsed_time(e) for s, e in evs))
+            per = [s.elapsed_time(e) for s, e in evs]
+            self.last_steps_ms.extend(per)
+            out.append(sum(per))
         t = torch.tensor(out, dtype=torch.float64, device=self.dev)
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.median()), [float(x) for x in t]
+
+
+def step_percentiles(ctx):
+    """p10 / p50 / p90 of the per-step CUDA-event times of the last timed() call on this rank."""
+    xs = sorted(ctx.last_steps_ms)
+    q = lambda f: round(xs[min(len(xs) - 1, int(f * len(xs)))], 5)  # noqa: E731
+    return {"p10": q(0.10), "p50": q(0.50), "p90": q(0.90), "n": len(xs)}
 
 
 def capture(ctx, fn):
@@ -580,6 +594,107 @@ def time_gpu_reference_chamfer(W):
     return res
 
 
+def time_chamfer_training_shapes(dev, B):
+    """the three shapes the Completion-Prompter pre-training actually calls ChamferDistanceL1 on
+    (/root/reference tools/runner_pretask.py:220-223 -- 32 predicted vs 1024, 1024 vs 1024, 2048 vs 8192, B = 64),
+    forward and backward, each as its own CUDA graph; the reference's own chamfer.cu (oracle/_ref) beside it."""
+    import upp_b200
+    from oracle import ref_gpu
+    o, ref = upp_b200.ops, ref_gpu.load()
+    g = torch.Generator().manual_seed(5)
+    out = []
+
+    def graph_ms(fn, reps=20):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        ts = []
+        for it in range(8):
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(reps):
+                gr.replay()
+            e0.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(s0.elapsed_time(e0) / reps)
+        return round(statistics.median(ts), 5)
+
+    def eager_ms(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(torch.cuda.default_stream())
+            fn()
+            e0.record(torch.cuda.default_stream())
+            torch.cuda.synchronize()
+            ts.append(s0.elapsed_time(e0))
+        return round(statistics.median(ts), 5)
+
+    for n, m in ((32, 1024), (1024, 1024), (2048, 8192)):
+        a, b = torch.rand(B, n, 3, generator=g).to(dev), torch.rand(B, m, 3, generator=g).to(dev)
+        d1, d2, i1, i2 = o.chamfer_forward(a, b)
+        g1, g2 = torch.rand_like(d1), torch.rand_like(d2)
+        fwd = graph_ms(lambda: o.chamfer_forward(a, b, True))
+        bwd = graph_ms(lambda: o.chamfer_backward(a, b, i1, i2, g1, g2))
+        row = {"shape": f"B{B} {n} vs {m}", "fwd_ms": fwd, "bwd_ms": bwd,
+               "fwd_tflops_8NM": round(8.0 * n * m * B / (fwd * 1e-3) / 1e12, 3)}
+        if ref is not None:
+            r = ref.forward(a, b)
+            row["reference_fwd_ms"] = eager_ms(lambda: ref.forward(a, b))
+            row["reference_bwd_ms"] = eager_ms(lambda: ref.backward(a, b, r[2], r[3], g1, g2))
+        out.append(row)
+    return out
+
+
+def as_shipped_leg():
+    """The reference ships with CUDA_LAUNCH_BLOCKING=1 (main.py:5): every launch waits for the kernel.  One more line for
+    that setting (SURVEY.md 8d "as shipped"): the headline step through the unchanged call sites, EAGER, the variable set
+    before CUDA starts -- so it runs in a child process.  Returns the child's record or why it could not be had."""
+    import subprocess
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--as-shipped-child"], env=env, capture_output=True,
+                           text=True, timeout=240)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": (r.stderr or r.stdout)[-200:]}
+    except Exception as ex:  # noqa: BLE001
+        return {"unavailable": str(ex)[:200]}
+
+
+def as_shipped_child():
+    assert os.environ.get("CUDA_LAUNCH_BLOCKING") == "1"
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    B = DEFAULT_B[HEADLINE]
+    W = GpuWorkload(HEADLINE, make_inputs(HEADLINE, B, seed=0), dev, 1, None, "none (1 GPU)")
+    _, keys = W.h2d_bytes()
+    W.h2d = {k: W.host[k] for k in keys}
+    api = W.callsites()
+    dd = dict(W.d)
+    for _ in range(5):
+        W.run_modules(dd, api).item()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        W.run_modules(dd, api).item()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ms = statistics.median(ts)
+    print(json.dumps({"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": round(ms, 5),
+                      "what": "headline step, reference call sites unchanged over the drop-in modules + autograd, eager launches "
+                              "with CUDA_LAUNCH_BLOCKING=1 as the reference's main.py:5 sets it; H2D of the inputs and the "
+                              "loss read-back inside the step; host wall clock, median of 50 steps"}), flush=True)
+
+
 def measure(ctx, name, B, peers, collective, peaks, peak_src, want_cpu, scaling="weak", sampler=None):
     """One workload on this rank's GPU: device-resident arm, e2e arm(s), per-op roofline pass.  Collective calls inside:
     every rank must call it with the same arguments."""
@@ -604,6 +719,7 @@ def measure(ctx, name, B, peers, collective, peaks, peak_src, want_cpu, scaling=
     if sampler is not None:
         sampler.mark()
     dev_ms, dev_regions = ctx.timed(one_step)
+    dev_pct = step_percentiles(ctx)
     clocks = sampler.summary() if sampler is not None else None
 
     # ---- end-to-end arms: pinned host -> device every step (inside the captured step, on the branches that consume
@@ -642,8 +758,8 @@ def measure(ctx, name, B, peers, collective, peaks, peak_src, want_cpu, scaling=
             step()
         ms, _ = ctx.timed(step)
         out = {"value": B * world * args.steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": 4, "ms_per_step": ms / args.steps, "gpu_launches_per_step": int(nlaunch),
-               "api": f"{label}, {emode}"}
+               "d2h_bytes_per_step": 4, "ms_per_step": ms / args.steps, "step_ms": step_percentiles(ctx),
+               "gpu_launches_per_step": int(nlaunch), "api": f"{label}, {emode}"}
         if eerr:
             out["graph_error"] = eerr
         return out
@@ -693,6 +809,7 @@ def measure(ctx, name, B, peers, collective, peaks, peak_src, want_cpu, scaling=
         ctx.barrier()
 
     gpu_ref = time_gpu_reference_chamfer(W) if (name == "c3" and rank == 0) else None
+    train_shapes = time_chamfer_training_shapes(dev, B) if (name == "c3" and rank == 0 and world == 1) else None
     if rank != 0:
         return None
 
@@ -736,11 +853,13 @@ def measure(ctx, name, B, peers, collective, peaks, peak_src, want_cpu, scaling=
 
     clouds = B * world * args.steps
     rec.update({"value": clouds / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / args.steps,
-                "timed_regions": len(dev_regions), "region_ms": [round(x, 4) for x in dev_regions[:8]],
+                "timed_regions": len(dev_regions), "region_ms": [round(x, 4) for x in dev_regions[:8]], "step_ms": dev_pct,
                 "gpu_launches_per_step": int(launches_per_step), "roofline": roofline, "kernels": kernels,
                 "run_info": run_info, "clocks": clocks})
     if gpu_ref is not None:
         rec["gpu_reference"] = gpu_ref
+    if train_shapes is not None:
+        rec["training_shapes"] = train_shapes
     if want_cpu:
         rec["cpu_baseline"] = cpu_baseline_record(name, B)
     return rec
@@ -782,7 +901,11 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1/c3/c4/c5 (and strong-scaling) sub-records")
+    ap.add_argument("--as-shipped-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.as_shipped_child:
+        as_shipped_child()
+        return
     args.warmup = max(args.warmup, 3)
     args.steps = max(args.steps, 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -845,11 +968,14 @@ def main():
             "warmup": args.warmup, "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": top["config"], "run_info": top["run_info"],
             "clocks": top["clocks"], "timed_regions": top["timed_regions"], "region_ms": top["region_ms"],
+            "step_ms": top["step_ms"],
             "e2e": top["e2e"], "gpu_launches": int(top["gpu_launches_per_step"] * args.steps * top["timed_regions"]),
             "gpu_launches_per_step": top["gpu_launches_per_step"], "roofline": top["roofline"], "kernels": top["kernels"]}
     for k in ("e2e_dropin", "cpu_baseline", "gpu_reference"):
         if k in top:
             line[k] = top[k]
+    if world == 1 and args.workload == HEADLINE and not args.no_configs and not args.batch:
+        line["e2e_dropin_launch_blocking"] = as_shipped_leg()
     if subs:
         line["configs"] = {k: v for k, v in subs.items() if v is not None}
     if strong is not None:

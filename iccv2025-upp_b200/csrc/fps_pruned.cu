@@ -289,100 +289,116 @@ static int launch_pruned(const float* xyz, int B, int N, int M, int32_t* idx, fl
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// fps_rows_kernel -- the third cut of the pruned round, built around what the two above taught: the bound is the length
-// of the DEPENDENT chain of a round AND the instructions every warp issues per round (two warps share a scheduler, and
-// the integer / compare / select pipe runs at half rate: a first version of this kernel with a 60-instruction
-// "resolve the eight posts" tail in every warp measured 0.8 us per round, 240 cycles of it that tail).
+// fps_rows_kernel -- the third cut of the pruned round (UPP_FPS_PRUNED=2; an EXPERIMENT like the kernel above: exact, every
+// FPS parity test runs through it, NOT on the default path).  It was built to answer "where does a pruned round go?" with a
+// per-phase timeline (clock64 build: make EXTRA=-DUPP_ROWS_PROFILE, scripts/prof_rows.py) and ncu source counters
+// (profiles/r02_fps_rows.txt).  Design:
 //   * the sorted cloud lives in REGISTERS exactly as in fps_blk_kernel (packed fp32x2 coordinates, running min-distances),
 //     but ownership is by ROWS: row r of warp w is the 64 consecutive sorted points [(w * RPW + r) * 64, +64), two per lane.
-//     A row is a spatial bucket (Z-curve neighbours) with its box and its largest min-distance in lane r;
+//     A row is a spatial bucket (Z-curve neighbours) with its box in lane r; four rows (a NIBBLE) share one bound, the
+//     nibble's largest min-distance;
 //   * a round starts with the lane-parallel box test (one ballot -> a warp-uniform mask of rows that can change), then
-//     updates only those rows behind warp-uniform branches.  A warp with an empty mask copies its previous record and
-//     goes straight to the barrier: no distance work, no reduction;
-//   * the arg-max costs ONE REDUX per active warp: every lane keeps a max tree over its own rows (rebuilt above the
-//     touched leaves), position-independent -- ties are not ordered by position here (the sort permutes the indices) but
-//     DETECTED (two equal children on the winning lane's tree descent, two lanes in the ballot, two warps' records) and
-//     sent to a slow path that takes the lowest ORIGINAL index over all points holding the maximum.  Real clouds never
-//     take it; lattices and duplicated points take it and stay exact;
-//   * the winning lane posts {key, position | tie flag} AND the point's coordinates (its tree descent ends at a
-//     compile-time register), so after the barrier a round is: 8 lanes load the 8 keys, one REDUX, one ballot, one
-//     LDS.128 of the winner's record -> the next centre.  No second shared-memory round trip;
-//   * the row bounds are refreshed (one REDUX per touched row) after the barrier, in the shadow of that key load.
-// One barrier per round, 8 warps, 1 CTA per SM.
+//     updates the nibbles that hold such a row behind warp-uniform branches (four interleaved chains; a row that did not
+//     need it comes out unchanged).  A warp with an empty mask copies its previous record and goes straight to the barrier;
+//   * the arg-max costs ONE REDUX per active warp: every lane keeps a 4-ary max tree over its rows, position-independent --
+//     ties are not ordered by position here (the sort permutes the indices) but DETECTED (two equal children on the
+//     winning lane's tree descent, two lanes in the ballot, two warps within 8 ulp) and sent to a slow path that takes the
+//     lowest ORIGINAL index over all points holding the maximum.  Real clouds never take it; lattices and duplicates do;
+//   * the winning lane posts {key, position | tie flag} AND the point's coordinates (its descent ends at a compile-time
+//     register) and enters (key & ~7) | warp and (key & ~7) | (7 - warp) in two words with native 32-bit shared-memory
+//     atomic maxima: after the barrier one LDS.64 names the winning warp (both words agree unless two warps are within
+//     8 ulp: exact path), one LDS.128 of its record is the next centre;
+//   * the nibble bounds are reduced (one REDUX each) with the update and consumed after the barrier.
+// MEASURED (B200, profiles/r02_fps_rows.txt, scripts/gpu_quick_fps.py): the pruning works -- 2 of 16 rows per warp and
+// round are due, 45 % of the warp-rounds have nothing to do -- and the kernel is still SLOWER than the plain one:
+// 0.65 us per round at N = 8192 (plain 0.54, the cluster kernel 0.31), 0.40 us at N = 1228 where the update is free
+// (plain 0.15).  The timeline says why.  A round is not bound by distance work and not by the four or five long-latency
+// steps one counts on paper; it is bound by the NUMBER OF DEPENDENT INSTRUCTIONS on the busiest warp's path, each worth
+// 5-6 cycles (stall reason "wait", the fixed dependent-issue latency, 36 % of all samples; branch resolution another
+// 10 %): box test 25, nibble update 39 (the only part with instruction-level parallelism), tree + REDUX + vote 10, tree
+// descent with tie detection ~25, record + atomics 10, resolve 20, bounds 8, bookkeeping 25: ~160 instructions = 800
+// cycles.  fps_blk_kernel's round at N = 1228 is 109 instructions of which 75 are the 5-way interleaved update: 35
+// dependent ones, 293 cycles.  Any pruning scheme that adds more than ~30 dependent instructions to the round loses what
+// it saves, on every cloud size this library sees; the three versions of this file (six REDUX, lane candidates, rows)
+// added 60 to 120.
+// What would pay instead (simulated, not built): amortising the chain over several selections.  With per-warp (best,
+// runner-up bound) records the runner-up of a round is provably the next selection whenever it is the unique maximum of
+// the other warps' bests and the winner's bound and lies farther from the winner than its own min-distance; on the C4
+// clouds that accepts 1.82 selections per round with one look-ahead and 2.66 with three (8 Morton regions) -- but every
+// extra candidate costs another REDUX + vote + record load (~150 cycles) in the resolve, which eats the gain at today's
+// round length.
 template <int P2>
 struct RowTree {
-  static constexpr int N1 = (P2 + 2) / 3, N2 = (N1 + 2) / 3, N3 = (N2 + 2) / 3;
-  static_assert(N3 == 1, "RowTree covers up to 27 rows");
-  int l0[P2], l1[N1], l2[N2], l3[1];  // l0[r] = max of row r's two keys (order-preserving float bits)
+  static constexpr int NG = P2 / 4;  // nibbles of four rows: the update / bound granularity and the tree's inner level
+  static_assert(P2 % 4 == 0 && NG >= 1 && NG <= 4, "4, 8, 12 or 16 rows per warp");
+  int l0[P2], nib[NG];  // l0[r] = max of row r's two keys (order-preserving float bits), nib[g] = max of rows 4g .. 4g+3
 
-  template <int NI, int NO>
-  static __device__ __forceinline__ void fold(const int (&in)[NI], int (&out)[NO]) {
+  template <int G>
+  __device__ __forceinline__ void fold() { nib[G] = max(max(l0[4 * G], l0[4 * G + 1]), max(l0[4 * G + 2], l0[4 * G + 3])); }
+  __device__ __forceinline__ int top() const {
+    int v = nib[0];
 #pragma unroll
-    for (int q = 0; q < NO; ++q) {
-      int v = in[3 * q];
-      if (3 * q + 1 < NI) v = max(v, in[3 * q + 1]);
-      if (3 * q + 2 < NI) v = max(v, in[3 * q + 2]);
-      out[q] = v;
-    }
-  }
-  template <int Q>
-  __device__ __forceinline__ void fold1() {  // level-1 node Q from its leaves
-    int v = l0[3 * Q];
-    if constexpr (3 * Q + 1 < P2) v = max(v, l0[3 * Q + 1]);
-    if constexpr (3 * Q + 2 < P2) v = max(v, l0[3 * Q + 2]);
-    l1[Q] = v;
-  }
-  __device__ __forceinline__ int top() {  // the levels above l1
-    fold(l1, l2); fold(l2, l3);
-    return l3[0];
+    for (int g = 1; g < NG; ++g) v = max(v, nib[g]);
+    return v;
   }
   __device__ __forceinline__ int build() {
-    fold(l0, l1);
+    fold<0>();
+    if constexpr (NG > 1) fold<1>();
+    if constexpr (NG > 2) fold<2>();
+    if constexpr (NG > 3) fold<3>();
     return top();
   }
-  template <int LEVEL>
-  __device__ __forceinline__ int at(int q) const {
-    if constexpr (LEVEL == 0) return l0[q];
-    else if constexpr (LEVEL == 1) return l1[q];
-    else if constexpr (LEVEL == 2) return l2[q];
-    else return l3[q];
+  // A SLOT (2 * row + half) whose key equals `best` (the root) and its coordinates (every leaf is a compile-time
+  // register).  `tie` is raised when two children of a visited node both hold `best`: any second slot holding the
+  // maximum shares such a node with the one returned.
+  template <int R>
+  __device__ __forceinline__ int leaf(int best, bool& tie, const float (&md)[2 * P2], const f32x2 (&X)[P2],
+                                      const f32x2 (&Y)[P2], const f32x2 (&Z)[P2], float4& rec) const {
+    const bool e0 = __float_as_int(md[2 * R]) == best, e1 = __float_as_int(md[2 * R + 1]) == best;
+    tie = tie || (e0 && e1);
+    float x0, x1, y0, y1, z0, z1;
+    unpack2(X[R], x0, x1); unpack2(Y[R], y0, y1); unpack2(Z[R], z0, z1);
+    rec.x = e0 ? x0 : x1; rec.y = e0 ? y0 : y1; rec.z = e0 ? z0 : z1;
+    return 2 * R + (e0 ? 0 : 1);
   }
-  template <int LEVEL>
-  static __host__ __device__ constexpr int size() { return LEVEL == 0 ? P2 : LEVEL == 1 ? N1 : LEVEL == 2 ? N2 : 1; }
-  // A SLOT (2 * row + half) whose key equals `best` (the root) under node Q of LEVEL, and its coordinates (the leaf is a
-  // compile-time register).  `tie` is raised when two children of a visited node both hold `best`: any second slot
-  // holding the maximum shares such a node with the one returned.
-  template <int LEVEL, int Q>
-  __device__ __forceinline__ int descend(int best, bool& tie, const float (&md)[2 * P2], const f32x2 (&X)[P2],
-                                         const f32x2 (&Y)[P2], const f32x2 (&Z)[P2], float4& rec) const {
-    if constexpr (LEVEL == 0) {
-      const bool e0 = __float_as_int(md[2 * Q]) == best, e1 = __float_as_int(md[2 * Q + 1]) == best;
-      tie = tie || (e0 && e1);
-      float x0, x1, y0, y1, z0, z1;
-      unpack2(X[Q], x0, x1); unpack2(Y[Q], y0, y1); unpack2(Z[Q], z0, z1);
-      rec.x = e0 ? x0 : x1; rec.y = e0 ? y0 : y1; rec.z = e0 ? z0 : z1;
-      return 2 * Q + (e0 ? 0 : 1);
+  template <int G>
+  __device__ __forceinline__ int in_nibble(int best, bool& tie, const float (&md)[2 * P2], const f32x2 (&X)[P2],
+                                           const f32x2 (&Y)[P2], const f32x2 (&Z)[P2], float4& rec) const {
+    const bool e0 = l0[4 * G] == best, e1 = l0[4 * G + 1] == best, e2 = l0[4 * G + 2] == best, e3 = l0[4 * G + 3] == best;
+    tie = tie || (e0 && (e1 || e2 || e3)) || (e1 && (e2 || e3)) || (e2 && e3);
+    if (e0) return leaf<4 * G>(best, tie, md, X, Y, Z, rec);
+    if (e1) return leaf<4 * G + 1>(best, tie, md, X, Y, Z, rec);
+    if (e2) return leaf<4 * G + 2>(best, tie, md, X, Y, Z, rec);
+    return leaf<4 * G + 3>(best, tie, md, X, Y, Z, rec);
+  }
+  __device__ __forceinline__ int find(int best, bool& tie, const float (&md)[2 * P2], const f32x2 (&X)[P2],
+                                      const f32x2 (&Y)[P2], const f32x2 (&Z)[P2], float4& rec) const {
+    if constexpr (NG == 1) {
+      return in_nibble<0>(best, tie, md, X, Y, Z, rec);
     } else {
-      constexpr int n = size<LEVEL - 1>();
-      constexpr int c0 = 3 * Q;
-      if constexpr (c0 + 1 >= n) {
-        return descend<LEVEL - 1, c0>(best, tie, md, X, Y, Z, rec);
+      int holders = 0;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) holders += nib[g] == best ? 1 : 0;
+      tie = tie || holders > 1;
+      if (nib[0] == best) return in_nibble<0>(best, tie, md, X, Y, Z, rec);
+      if constexpr (NG == 2) {
+        return in_nibble<1>(best, tie, md, X, Y, Z, rec);
       } else {
-        const bool e0 = at<LEVEL - 1>(c0) == best, e1 = at<LEVEL - 1>(c0 + 1) == best;
-        bool e2 = false;
-        if constexpr (c0 + 2 < n) e2 = at<LEVEL - 1>(c0 + 2) == best;
-        tie = tie || (e0 && (e1 || e2)) || (e1 && e2);
-        if (e0) return descend<LEVEL - 1, c0>(best, tie, md, X, Y, Z, rec);
-        if constexpr (c0 + 2 < n) {
-          if (e1) return descend<LEVEL - 1, c0 + 1>(best, tie, md, X, Y, Z, rec);
-          return descend<LEVEL - 1, c0 + 2>(best, tie, md, X, Y, Z, rec);
+        if (nib[1] == best) return in_nibble<1>(best, tie, md, X, Y, Z, rec);
+        if constexpr (NG == 3) {
+          return in_nibble<2>(best, tie, md, X, Y, Z, rec);
         } else {
-          return descend<LEVEL - 1, c0 + 1>(best, tie, md, X, Y, Z, rec);
+          if (nib[2] == best) return in_nibble<2>(best, tie, md, X, Y, Z, rec);
+          return in_nibble<3>(best, tie, md, X, Y, Z, rec);
         }
       }
     }
   }
 };
+
+__device__ __forceinline__ void red_max_shared_s32(int* addr, int v) {  // one native RED, no compiler-side warp aggregation
+  asm volatile("red.relaxed.cta.shared::cta.max.s32 [%0], %1;" ::"r"(smem_u32(addr)), "r"(v) : "memory");
+}
 
 #ifdef UPP_ROWS_PROFILE  // debug build (make EXTRA=-DUPP_ROWS_PROFILE): per-phase cycle sums of block 0, printed per warp
 #define UPP_PROF(i_) { const long long c_ = clock64(); prof[i_] += c_ - tlast; tlast = c_; }
@@ -511,8 +527,19 @@ __global__ void __launch_bounds__(kRowThreads, 1)
         h3[a] = warp_max_f(h3[a]);
         if (lane == r) { blo[a] = l3[a]; bhi[a] = h3[a]; }
       }
-      const int v = redux_max_s32(tr.l0[r]);
-      if (lane == r) thr = v > 0 ? __fmul_ru(__int_as_float(v), 1.0000076294f) : -1.0f;
+    }
+  }
+  {  // a nibble's rows share one bound: the nibble's largest min-distance, with the margin of the skip test
+    const int root = tr.build();
+    (void)root;
+#pragma unroll
+    for (int g = 0; g < RowTree<P2>::NG; ++g) {
+      const int v = redux_max_s32(tr.nib[g]);
+      if ((lane >> 2) == g) thr = v > 0 ? __fmul_ru(__int_as_float(v), 1.0000076294f) : -1.0f;
+    }
+    if (lane >= RPW) {  // no such row: a box nothing is ever near
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { blo[a] = 3.0e18f; bhi[a] = -3.0e18f; }
     }
   }
 
@@ -523,11 +550,11 @@ __global__ void __launch_bounds__(kRowThreads, 1)
     const int wbest = redux_max_s32(best);
     const unsigned winners = __ballot_sync(0xffffffffu, best == wbest);
     if (best == wbest && (winners & lanes_below) == 0u) {
-      atomicMax(&mx->x, (wbest & ~7) | warp);
-      atomicMax(&mx->y, (wbest & ~7) | (7 - warp));
+      red_max_shared_s32(&mx->x, (wbest & ~7) | warp);
+      red_max_shared_s32(&mx->y, (wbest & ~7) | (7 - warp));
       bool tie = (winners & (winners - 1u)) != 0u;  // a second lane holds it too
       float4 rc;
-      const int sl = tr.template descend<3, 0>(wbest, tie, md, X, Y, Z, rc);
+      const int sl = tr.find(wbest, tie, md, X, Y, Z, rc);
       int pf = slot0 + (sl >> 1) * 64 + (sl & 1);
       if (tie) pf |= static_cast<int>(0x80000000u);
       int4* dst = reinterpret_cast<int4*>(&recs[warp]);
@@ -544,15 +571,17 @@ __global__ void __launch_bounds__(kRowThreads, 1)
   if (t == 0) out[0] = 0;
   __syncthreads();
 
-  const bool odd1 = (lane & 1) != 0, odd2 = (lane & 2) != 0;
   const int my_nibble = lane >> 2;
+  int nbound[RowTree<P2>::NG];
+#pragma unroll
+  for (int g = 0; g < RowTree<P2>::NG; ++g) nbound[g] = -1;
 #ifdef UPP_ROWS_PROFILE
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
   int nactive = 0, nrows = 0, nties = 0, nslow = 0;
 #endif
   int cur = 1;  // j % 3: the round's arg-max words
   for (int j = 1; j < M; ++j) {
-    // ---- a. which of my rows can change?  lane r tests row r (lanes >= RPW hold thr = -1: never).  A row is skipped
+    // ---- a. which of my rows can change?  lane r tests row r (lanes >= RPW hold a box at infinity: never).  A row is skipped
     //         only when every point's distance provably exceeds the row's largest min-distance: thr carries the margin ----
     const float ex = fmaxf(fmaxf(blo[0] - cx, cx - bhi[0]), 0.f);
     const float ey = fmaxf(fmaxf(blo[1] - cy, cy - bhi[1]), 0.f);
@@ -572,7 +601,7 @@ __global__ void __launch_bounds__(kRowThreads, 1)
       // active warp.  One code path per nibble keeps the loop inside the instruction cache (the per-row / per-group /
       // all-rows variants of the first cut stalled on instruction fetch at every branch target).
       auto update_nibble = [&](auto gc) {
-        constexpr int R0 = decltype(gc)::value, NR = (P2 - R0 < 4 ? P2 - R0 : 4);
+        constexpr int R0 = decltype(gc)::value, NR = 4;
         f32x2 D[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) D[r] = sub2(Y[R0 + r], CY);
@@ -590,10 +619,8 @@ __global__ void __launch_bounds__(kRowThreads, 1)
           md[2 * (R0 + r) + 1] = fminf(md[2 * (R0 + r) + 1], d1);
           tr.l0[R0 + r] = max(__float_as_int(md[2 * (R0 + r)]), __float_as_int(md[2 * (R0 + r) + 1]));
         }
-        constexpr int Q0 = R0 / 3, Q1 = (R0 + NR - 1) / 3;  // the level-1 nodes above these rows
-        tr.template fold1<Q0>();
-        if constexpr (Q1 != Q0) tr.template fold1<Q1>();
-        if constexpr (Q1 > Q0 + 1) tr.template fold1<Q0 + 1>();
+        tr.template fold<R0 / 4>();
+        nbound[R0 / 4] = redux_max_s32(tr.nib[R0 / 4]);  // the nibble's new bound: consumed after the barrier
       };
 #define UPP_NIBBLE(G_) \
   if constexpr ((G_) < P2) if ((mask >> (G_)) & 0xfu) update_nibble(std::integral_constant<int, (G_)>{});
@@ -607,8 +634,8 @@ __global__ void __launch_bounds__(kRowThreads, 1)
       const int wd = reinterpret_cast<const int*>(&s_rec[(j & 1) ^ 1][warp])[lane];
       reinterpret_cast<int*>(&recs[warp])[lane] = wd;
       if (lane == 0) {
-        atomicMax(&mx->x, (wd & ~7) | warp);
-        atomicMax(&mx->y, (wd & ~7) | (7 - warp));
+        red_max_shared_s32(&mx->x, (wd & ~7) | warp);
+        red_max_shared_s32(&mx->y, (wd & ~7) | (7 - warp));
       }
     }
     __syncthreads();
@@ -622,18 +649,12 @@ __global__ void __launch_bounds__(kRowThreads, 1)
     int4 win = reinterpret_cast<const int4*>(&recs[wa])[1];  // {x, y, z, position | tie flag}
     if (t == 64) s_max[cur == 0 ? 2 : cur - 1] = make_int2(INT_MIN, INT_MIN);  // (j + 2) % 3: last read in round j - 1
     cur = cur == 2 ? 0 : cur + 1;
-    // ---- c. refresh the bounds of the nibbles touched (in the shadow of those loads): lane r keeps row r's ----
+    // ---- c. the bounds of the nibbles touched: their reductions were issued with the update, the results land here.
+    //         A nibble's four rows share one bound (its largest min-distance) but keep their own boxes ----
     if (mask != 0u) {
-#define UPP_REFRESH(G_)                                                                                    \
-  if constexpr ((G_) < P2) if ((mask >> (G_)) & 0xfu) {                                                    \
-    const int v0 = redux_max_s32(tr.l0[(G_)]);                                                             \
-    const int v1 = (G_) + 1 < P2 ? redux_max_s32(tr.l0[(G_) + 1 < P2 ? (G_) + 1 : 0]) : -1;                \
-    const int v2 = (G_) + 2 < P2 ? redux_max_s32(tr.l0[(G_) + 2 < P2 ? (G_) + 2 : 0]) : -1;                \
-    const int v3 = (G_) + 3 < P2 ? redux_max_s32(tr.l0[(G_) + 3 < P2 ? (G_) + 3 : 0]) : -1;                \
-    const int lo_ = odd1 ? v1 : v0, hi_ = odd1 ? v3 : v2;                                                  \
-    const int v = odd2 ? hi_ : lo_;                                                                        \
-    if (my_nibble == (G_) / 4) thr = v > 0 ? __fmul_ru(__int_as_float(v), 1.0000076294f) : -1.0f;          \
-  }
+#define UPP_REFRESH(G_)                                                                              \
+  if constexpr ((G_) < P2) if (((mask >> (G_)) & 0xfu) && my_nibble == (G_) / 4)                      \
+    thr = nbound[(G_) / 4] > 0 ? __fmul_ru(__int_as_float(nbound[(G_) / 4]), 1.0000076294f) : -1.0f;
       UPP_REFRESH(0) UPP_REFRESH(4) UPP_REFRESH(8) UPP_REFRESH(12)
 #undef UPP_REFRESH
     }
