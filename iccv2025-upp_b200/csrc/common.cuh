@@ -200,6 +200,11 @@ __device__ __forceinline__ void st_async_b64(uint32_t remote_addr, int lo, int h
                "r"(lo), "r"(hi), "r"(remote_bar)
                : "memory");
 }
+__device__ __forceinline__ void st_async_b128(uint32_t remote_addr, int a, int b, int c, int d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
+}
 __device__ __forceinline__ unsigned cluster_nctarank() {
   unsigned r;
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));

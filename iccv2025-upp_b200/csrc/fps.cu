@@ -17,6 +17,8 @@
 // x^2+y^2+z^2 <= 1e-3 (double compare) never selected, d = fma(dz,dz,fma(dx,dx,dy*dy)).
 #include <limits.h>
 
+#include <stdio.h>
+
 #include "fps_round.cuh"
 
 namespace upp {
@@ -552,6 +554,196 @@ __global__ void __launch_bounds__(NW * 32, 1)
   }
 }
 
+// Cluster FPS with ONE LOOK-AHEAD (fps_cluster2_kernel): the same exchange, but a round may yield TWO selections.
+// A cluster round is ~600 cycles of which ~290 are the DSMEM flight and the mbarrier wake-up, whatever the payload; so
+// every warp also sends an upper bound of everything else it holds (its runner-up: one more REDUX, issued beside the
+// index REDUX), and after the exchange every thread checks whether the round's runner-up is already decided:
+//   * p1 = the arg-max as before (largest key, lowest index);
+//   * candidates for the next selection: every other entry's key, and for p1's warp its runner-up bound.  If their
+//     maximum M2 > 0 is held by exactly ONE entry, that entry is not p1's warp's bound, and the point p2 it names is not
+//     reached by p1 -- fma(dz,dz,fma(dx,dx,dy*dy)) of (p2 - p1), the very value the update would compute, is >= M2 -- then
+//     after the update with p1 every point is still <= its old min-distance < M2 (or == M2 at a higher index inside p2's
+//     warp), p2 keeps M2, p1 drops to 0: the next round's arg-max IS p2.  It is selected now, and the next round updates
+//     with both centres (min3).  Any doubt (a tie between entries, the bound of p1's own warp, p2 inside p1's reach,
+//     M2 <= 0, the last selection) ends the round with one selection, as before.
+// Same selections bit for bit as every other FPS kernel here (the parity tests force it on the cluster shapes it is built
+// for).  MEASURED (B200, round 2), NOT ADOPTED: the look-ahead is accepted in 88 % of the rounds -- 1023 selections in 545
+// exchange rounds on C4's clouds (B16 x 8192), 557 at B32 x 6144 -- and the launch is no faster: 297-315 us against
+// 308-324 us (B16 x 8192), 296-306 against 291 (B32 x 6144), 62-68 against 53 (M = 128: few acceptances early on).  A
+// round with the second resolve costs ~1100 cycles against 620: one more REDUX before the exchange, REDUX + two votes +
+// shuffle + three LDS + the distance test + the second centre's update after it -- ~50 more DEPENDENT instructions at 5-6
+// cycles each plus two more 60-70-cycle REDUX round trips, which is what a second 600-cycle round would have cost.
+// UPP_FPS_CLUSTER_AHEAD=1 (under UPP_TUNING=1) selects it.
+constexpr int kAheadFrom = 48;
+
+template <int CS, int NW, int P2>
+__global__ void __launch_bounds__(NW * 32, 1)
+    fps_cluster2_kernel(const float* __restrict__ xyz, int N, int M, int Nc, int32_t* __restrict__ idx_out,
+                        float* __restrict__ centers_out) {
+  static_assert(CS * NW <= 32, "one entry per lane in the cluster stage");
+  constexpr int P = 2 * P2;
+  extern __shared__ __align__(16) float s_xyz[];  // 3*N floats: the whole cloud (AoS, as in global memory)
+  __shared__ __align__(16) int4 s_x[2][32];       // {key, index, runner-up bound, -} of every warp of the cluster, by round parity
+  __shared__ __align__(8) uint64_t s_bar, s_xbar[2];
+
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x / CS;
+  const float* p = xyz + static_cast<size_t>(b) * N * 3;
+  int32_t* out = idx_out + static_cast<size_t>(b) * M;
+  float* cen = centers_out ? centers_out + static_cast<size_t>(b) * M * 3 : nullptr;
+
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_init(&s_xbar[0], 1);
+    mbar_init(&s_xbar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers exist before anyone sends to them
+  unsigned parity = 0;
+  stage_points(s_xyz, p, N, &s_bar, parity);
+
+  const int lo = static_cast<int>(rank) * Nc;
+  const int hi = min(N, lo + Nc);
+  const int base = lo + t * P;
+  f32x2 X[P2], Y[P2], Z[P2];
+  float md[P];
+#pragma unroll
+  for (int r = 0; r < P2; ++r) {
+    float c[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = base + 2 * r + h;
+      if (i < hi) {
+        c[h][0] = s_xyz[3 * i];
+        c[h][1] = s_xyz[3 * i + 1];
+        c[h][2] = s_xyz[3 * i + 2];
+        md[2 * r + h] = fps_initial_md(c[h][0], c[h][1], c[h][2]);
+      } else {
+        c[h][0] = c[h][1] = c[h][2] = 0.f;
+        md[2 * r + h] = kOutOfRange;
+      }
+    }
+    X[r] = pack2(c[0][0], c[1][0]);
+    Y[r] = pack2(c[0][1], c[1][1]);
+    Z[r] = pack2(c[0][2], c[1][2]);
+  }
+  const unsigned dst = lane < CS ? lane : 0;
+  const int my_entry = static_cast<int>(rank) * NW + warp;
+  const uint32_t r_entry0 = map_to_cta(smem_u32(&s_x[0][my_entry]), dst);
+  const uint32_t r_entry1 = map_to_cta(smem_u32(&s_x[1][my_entry]), dst);
+  const uint32_t r_bar0 = map_to_cta(smem_u32(&s_xbar[0]), dst);
+  const uint32_t r_bar1 = map_to_cta(smem_u32(&s_xbar[1]), dst);
+  const unsigned lanes_below = (1u << lane) - 1u;
+
+  float cx = s_xyz[0], cy = s_xyz[1], cz = s_xyz[2];
+  float ex = cx, ey = cy, ez = cz;  // the second centre of a round (when `two`)
+  bool two = false;
+  if (t == 0 && rank == 0) out[0] = 0;
+  int rnd = 0;
+  for (int j = 1; j < M;) {
+    ++rnd;
+    const int h = rnd & 1;
+    if (t == 0) mbar_expect_tx(&s_xbar[h], CS * NW * 16u);  // this round's CS * NW entries of 16 bytes
+    // distances to the round's centre(s), running-min update, in-thread arg-max: the tuned span of every FPS kernel here
+    int best, ls = 0;
+    if (two) {  // cluster-uniform: the second centre of the previous round first (its maximum is recomputed below)
+      const f32x2 EX = pack2(ex, ex), EY = pack2(ey, ey), EZ = pack2(ez, ez);
+      f32x2 D[P2];
+#pragma unroll
+      for (int r = 0; r < P2; ++r) D[r] = sub2(Y[r], EY);
+#pragma unroll
+      for (int r = 0; r < P2; ++r) D[r] = mul2(D[r], D[r]);
+#pragma unroll
+      for (int r = 0; r < P2; ++r) { const f32x2 dx = sub2(X[r], EX); D[r] = fma2(dx, dx, D[r]); }
+#pragma unroll
+      for (int r = 0; r < P2; ++r) { const f32x2 dz = sub2(Z[r], EZ); D[r] = fma2(dz, dz, D[r]); }
+#pragma unroll
+      for (int r = 0; r < P2; ++r) {
+        float d0, d1;
+        unpack2(D[r], d0, d1);
+        md[2 * r] = fminf(md[2 * r], d0);
+        md[2 * r + 1] = fminf(md[2 * r + 1], d1);
+      }
+    }
+    {
+      const f32x2 CX = pack2(cx, cx), CY = pack2(cy, cy), CZ = pack2(cz, cz);
+      fps_span<P2, 0, P2, true>(X, Y, Z, md, CX, CY, CZ, best, ls);
+    }
+    const int wbest = redux_max_s32(best);
+    // (in the shadow of the REDUX) the largest of the thread's other slots: independent selects + a max tree
+    int second;
+    {
+      int o[P];
+#pragma unroll
+      for (int s = 0; s < P; ++s) o[s] = s == ls ? INT_MIN : __float_as_int(md[s]);
+#pragma unroll
+      for (int n = P; n > 1; n = (n + 2) / 3) {
+#pragma unroll
+        for (int q = 0; q < (n + 2) / 3; ++q) {
+          int v = o[3 * q];
+          if (3 * q + 1 < n) v = max(v, o[3 * q + 1]);
+          if (3 * q + 2 < n) v = max(v, o[3 * q + 2]);
+          o[q] = v;
+        }
+      }
+      second = o[0];
+    }
+    const unsigned winners = __ballot_sync(0xffffffffu, best == wbest);
+    const bool poster = best == wbest && (winners & lanes_below) == 0u;  // lower lane == lower point indices
+    const unsigned widx = redux_min_u32(best == wbest ? static_cast<unsigned>(base + ls) : 0xffffffffu);
+    const int wsec = redux_max_s32(poster ? second : best);  // everything this warp holds besides the point it names
+    if (lane < CS) st_async_b128(h ? r_entry1 : r_entry0, wbest, static_cast<int>(widx), wsec, 0, h ? r_bar1 : r_bar0);
+    mbar_wait(&s_xbar[h], static_cast<unsigned>((rnd - 1) >> 1) & 1u);  // buffer h is on its ((rnd - 1) / 2)-th use
+    const int4 e = lane < CS * NW ? s_x[h][lane] : make_int4(INT_MIN, INT_MAX, INT_MIN, 0);
+    const int k1 = redux_max_s32(e.x);
+    const int sel = static_cast<int>(redux_min_u32(e.x == k1 ? static_cast<unsigned>(e.y) : 0xffffffffu));
+    cx = s_xyz[3 * sel];
+    cy = s_xyz[3 * sel + 1];
+    cz = s_xyz[3 * sel + 2];
+    // the look-ahead: is the runner-up already decided?  (Not tried during the first selections: the min-distances are
+    // still so large that p1 reaches nearly everything.)
+    bool ok2 = false;
+    int sel2 = 0;
+    if (j >= kAheadFrom && j + 1 < M) {  // cluster-uniform
+      const bool is_top = e.x == k1 && e.y == sel;  // the entry naming p1
+      const int cand = is_top ? e.z : e.x;
+      const int m2c = redux_max_s32(cand);
+      const unsigned h2 = __ballot_sync(0xffffffffu, cand == m2c && !is_top);
+      const unsigned hall = __ballot_sync(0xffffffffu, cand == m2c);
+      if (m2c > 0 && h2 == hall && (h2 & (h2 - 1u)) == 0u) {
+        sel2 = __shfl_sync(0xffffffffu, e.y, __ffs(h2) - 1);
+        ex = s_xyz[3 * sel2];
+        ey = s_xyz[3 * sel2 + 1];
+        ez = s_xyz[3 * sel2 + 2];
+        ok2 = !(dist_yxz(ex - cx, ey - cy, ez - cz) < __int_as_float(m2c));  // p1 does not reach p2
+      }
+    }
+    if (t == 0 && rank == 0) {
+      out[j] = sel;
+      if (ok2) out[j + 1] = sel2;
+    }
+    two = ok2;
+    j += ok2 ? 2 : 1;
+  }
+#ifdef UPP_CLUSTER_STATS
+  if (blockIdx.x == 0 && t == 0) printf("cluster look-ahead: %d selections in %d rounds\n", M - 1, rnd);
+#endif
+  cluster_sync_all();  // nobody leaves while a peer may still be sending to it
+  if (cen && rank == 0) {
+    __syncthreads();  // thread 0's out[] stores are visible to the block
+    for (int j = t; j < M; j += NW * 32) {
+      const int sel = out[j];
+      cen[3 * j] = s_xyz[3 * sel];
+      cen[3 * j + 1] = s_xyz[3 * sel + 1];
+      cen[3 * j + 2] = s_xyz[3 * sel + 2];
+    }
+  }
+}
+
 // Any-N fallback: min-distance array in a global workspace (L2-resident), xyz re-read from
 // global memory every iteration.  Same selection rule, same two-stage arg-max.
 template <int THREADS>
@@ -768,13 +960,13 @@ static int dispatch_fps_blk_big(FpsBlkConfig c, const float* xyz, int B, int N, 
   return UPP_ERR_UNSUPPORTED;
 }
 
-template <int CS, int NW, int P2>
+template <int CS, int NW, int P2, bool AHEAD = false>
 static int launch_fps_cluster(const float* xyz, int B, int N, int M, int Nc, int32_t* idx, float* centers,
                               cudaStream_t st) {
   // as for one CTA per cloud: while every CTA can have an SM of its own, keep throughput kernels off that SM --
   // up to 4 CTAs per cluster (measured: a cluster of 8 CTAs asking for the whole 227 KB each is not placed at all)
   const size_t need = static_cast<size_t>(N) * 3 * sizeof(float);
-  auto kern = fps_cluster_kernel<CS, NW, P2>;
+  auto kern = AHEAD ? fps_cluster2_kernel<CS, NW, P2> : fps_cluster_kernel<CS, NW, P2>;
   size_t smem = CS <= 4 ? fps_smem_request(need, B * CS) : need;
   // ... but only if ALL B whole-SM clusters fit at once on this very GPU (GPC sizes differ from chip to chip): a cluster
   // left over runs as a second wave and doubles the launch
@@ -830,6 +1022,14 @@ static int dispatch_fps_cluster(int cs, const float* xyz, int B, int N, int M, i
   const int want = (nc + nw * 64 - 1) / (nw * 64);
   const int p2 = want <= 4 ? want : (want <= 6 ? 6 : (want <= 8 ? 8 : (want <= 12 ? 12 : 16)));
   if (p2 > 16 || static_cast<long>(p2) * nw * 64 < nc) return UPP_ERR_UNSUPPORTED;
+  // one look-ahead per round (fps_cluster2_kernel): MEASURED, NOT FASTER (see its header) -- off unless UPP_FPS_CLUSTER_AHEAD=1,
+  // and instantiated only for the shapes the heuristic itself picks (8 x 4 warps: 2-4 pairs, 4 x 4 warps: 4-8 pairs)
+  if (env_int("UPP_FPS_CLUSTER_AHEAD", 0) == 1 && M > 2 && nw == 4) {
+#define UPP_CLA(CS_, P2_) \
+  if (cs == CS_ && p2 == P2_) return launch_fps_cluster<CS_, 4, P2_, true>(xyz, B, N, M, nc, idx, centers, st);
+    UPP_CLA(8, 2) UPP_CLA(8, 3) UPP_CLA(8, 4) UPP_CLA(4, 4) UPP_CLA(4, 6) UPP_CLA(4, 8)
+#undef UPP_CLA
+  }
 #define UPP_CL(CS_, NW_, P2_) \
   if (cs == CS_ && nw == NW_ && p2 == P2_) return launch_fps_cluster<CS_, NW_, P2_>(xyz, B, N, M, nc, idx, centers, st);
 #define UPP_CL_ROW(CS_, NW_) UPP_CL(CS_, NW_, 1) UPP_CL(CS_, NW_, 2) UPP_CL(CS_, NW_, 3) UPP_CL(CS_, NW_, 4) \

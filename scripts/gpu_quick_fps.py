@@ -43,7 +43,7 @@ def env(**kw):
             os.environ[k] = str(v)
 
 
-VARIANTS = (("default", {}), ("one CTA per cloud", dict(UPP_FPS_CLUSTER=0)), ("buckets", dict(UPP_FPS_PRUNED=1)),
+VARIANTS = (("default", {}), ("clusters + look-ahead", dict(UPP_FPS_CLUSTER_AHEAD=1)), ("one CTA per cloud", dict(UPP_FPS_CLUSTER=0)), ("buckets", dict(UPP_FPS_PRUNED=1)),
             ("rows", dict(UPP_FPS_PRUNED=2, UPP_FPS_PRUNED_MIN=63)))
 SHAPES = ((128, 8192, 1024), (16, 8192, 1024), (32, 6144, 1024), (64, 6144, 1024), (32, 4096, 1024), (32, 2048, 1024),
           (32, 2500, 300), (64, 8192, 128), (32, 1228, 1024))

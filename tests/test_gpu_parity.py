@@ -68,6 +68,9 @@ FPS_KERNELS = {  # name -> tuning environment (read per launch by fps_launch)
     "cluster2_nw8": {"UPP_FPS_CLUSTER": "2", "UPP_FPS_CLUSTER_NW": "8"},  # 4 / 8 warps per CTA (8: clusters of <= 4 CTAs)
     "cluster4_nw8": {"UPP_FPS_CLUSTER": "4", "UPP_FPS_CLUSTER_NW": "8"},
     "cluster4_nw4": {"UPP_FPS_CLUSTER": "4", "UPP_FPS_CLUSTER_NW": "4"},
+    # up to two selections per exchange round (one look-ahead; measured experiment, off by default)
+    "cluster4_ahead": {"UPP_FPS_CLUSTER": "4", "UPP_FPS_CLUSTER_AHEAD": "1"},
+    "cluster8_ahead": {"UPP_FPS_CLUSTER": "8", "UPP_FPS_CLUSTER_AHEAD": "1"},
     "v1": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "0"},                       # round-1a strided kernels
     "v1_w4": {"UPP_FPS_IMPL": "1", "UPP_FPS_W4": "1"},
 }
