@@ -1077,10 +1077,11 @@ int fps_rows_launch(const float*, int, int, int, int32_t*, float*, cudaStream_t)
 
 int fps_launch(const float* xyz, int B, int N, int M, int32_t* idx, float* centers,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  // Morton buckets + exact pruning (fps_pruned.cu): an EXPERIMENT, off by default -- bit-identical selections with 85 % of
-  // the distance updates skipped, but its round is a chain of six dependent warp reductions (0.50 us at any N, against
-  // 0.54 us for the plain kernel at N = 8192 and 0.30 us on clusters; profiles/r02_fps_pruned.txt).  UPP_FPS_PRUNED=1
-  // (under UPP_TUNING=1) routes clouds of more than UPP_FPS_PRUNED_MIN (2048) points to it: the parity tests do.
+  // Exact spatial pruning on a Z-order-sorted copy of the cloud (fps_pruned.cu): EXPERIMENTS, off by default -- bit-identical
+  // selections with 85 % of the distance updates skipped, and not faster: the pruned round trades distance work for dependent
+  // instructions (0.50-0.65 us per round at N = 8192 against 0.54 for the plain kernel and 0.31 on clusters).
+  // UPP_FPS_PRUNED=1 (shared-memory buckets) / 2 (register-resident rows), under UPP_TUNING=1, route clouds of more than
+  // UPP_FPS_PRUNED_MIN (2048) points to them: the parity tests do.
   const int pruned = env_int("UPP_FPS_PRUNED", 0);
   if (pruned >= 1 && N > env_int("UPP_FPS_PRUNED_MIN", 2048) && N <= kFpsMaxRegPoints && M >= 32 &&
       env_int("UPP_FPS_CLUSTER", -1) < 1 && env_int("UPP_FPS_NW", 0) == 0 && env_int("UPP_FPS_IMPL", 2) != 1) {
