@@ -747,12 +747,19 @@ def measure(ctx, name, B, peers, collective, peaks, peak_src, want_cpu, scaling=
                 W.run_modules(dd, api)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        rp, loss, emode, nlaunch, eerr = capture(ctx, lambda: W.run_modules(dd, api))
+        host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def graph_fn():  # the step AND the read-back of its result: one pinned 4-byte D2H copy, a node of the same graph
+            out = W.run_modules(dd, api)
+            host_loss.copy_(out.reshape(1), non_blocking=True)
+            return out
+        rp, loss, emode, nlaunch, eerr = capture(ctx, graph_fn)
 
         def step():
             if rp is not None:
                 rp()
-                return loss.item()                          # D2H of the step's result
+                torch.cuda.current_stream().synchronize()   # the host needs the value: it waits for the copy
+                return float(host_loss[0])                   # D2H of the step's result
             return W.run_modules(dd, api).item()
         for _ in range(args.warmup):
             step()

@@ -29,10 +29,13 @@ class _FpsGather(Function):
         ctx.save_for_backward(idx)
         ctx.n = data.size(1)
         ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)  # no zero-fill launches for the index output's (undefined) gradient
         return centers, idx
 
     @staticmethod
     def backward(ctx, grad_centers, _grad_idx):
+        if grad_centers is None:
+            return None, None
         (idx,) = ctx.saved_tensors
         # (B,M,3) -> scatter-add -> (B,N,3), row-major: no transposes (the reference pays two, utils/misc.py:19)
         return ops.rows_scatter_add(grad_centers.contiguous(), idx, ctx.n), None
@@ -50,11 +53,18 @@ class _FusedGroup(Function):
         ctx.save_for_backward(idx, cidx)
         ctx.n = xyz.size(1)
         ctx.mark_non_differentiable(idx, cidx)
+        # undefined gradients arrive as None instead of zero tensors: autograd otherwise launches one fill kernel per
+        # output (neighbourhoods, centres and both index tensors) in front of every backward
+        ctx.set_materialize_grads(False)
         return nb, center, idx, cidx
 
     @staticmethod
     def backward(ctx, g_nb, g_center, _gi, _gc):
+        if g_nb is None and g_center is None:
+            return None, None, None
         idx, cidx = ctx.saved_tensors
+        if g_nb is None:  # only the centres were used downstream
+            g_nb = g_center.new_zeros(idx.shape + (3,))
         g_center = g_center.contiguous() if g_center is not None else None
         return ops.group_backward(g_nb.contiguous(), g_center, idx, cidx, ctx.n), None, None
 
@@ -103,11 +113,18 @@ class ChamferFunction(Function):
     def forward(ctx, xyz1, xyz2):
         dist1, dist2, idx1, idx2 = ops.chamfer_forward(xyz1, xyz2)
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        ctx.set_materialize_grads(False)
         return dist1, dist2
 
     @staticmethod
     def backward(ctx, grad_dist1, grad_dist2):
         xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        if grad_dist1 is None and grad_dist2 is None:
+            return None, None
+        if grad_dist1 is None:  # only one direction was used downstream (ChamferDistanceL2_split callers)
+            grad_dist1 = xyz1.new_zeros(xyz1.shape[:2])
+        if grad_dist2 is None:
+            grad_dist2 = xyz2.new_zeros(xyz2.shape[:2])
         grad_xyz1, grad_xyz2 = ops.chamfer_backward(xyz1, xyz2, idx1, idx2, grad_dist1, grad_dist2)
         return grad_xyz1, grad_xyz2
 
@@ -252,10 +269,13 @@ class _KnnPoints(Function):
         d, i, _ = ops.knn_points(p1, p2, K)
         ctx.save_for_backward(p1, p2, i)
         ctx.mark_non_differentiable(i)
+        ctx.set_materialize_grads(False)
         return d, i
 
     @staticmethod
     def backward(ctx, grad_d, _grad_i):
+        if grad_d is None:
+            return None, None, None
         p1, p2, i = ctx.saved_tensors
         B, N1, K = i.shape
         flat = i.reshape(B, N1 * K, 1).expand(-1, -1, 3)
