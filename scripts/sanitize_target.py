@@ -48,6 +48,18 @@ for tag, kw in (("cluster4", dict(UPP_FPS_CLUSTER=4)), ("cluster8", dict(UPP_FPS
     env(**kw)
     check("fps " + tag, np.array_equal(o.fps(xb.to(dev), 24).cpu().numpy(), wantb))
     env(**{k: None for k in kw})
+# the measured experiments (off by default): exact pruning on a Z-order-sorted copy (shared-memory buckets / register rows),
+# clusters with one look-ahead selection per exchange round (M > 48: the look-ahead is not tried before)
+wantc = O.fps(xb.numpy(), 80)
+for tag, kw in (("pruned_buckets", dict(UPP_FPS_PRUNED=1, UPP_FPS_PRUNED_MIN=255)), ("pruned_rows", dict(UPP_FPS_PRUNED=2, UPP_FPS_PRUNED_MIN=63)),
+                ("cluster8_ahead", dict(UPP_FPS_CLUSTER=8, UPP_FPS_CLUSTER_AHEAD=1))):
+    env(**kw)
+    check("fps " + tag, np.array_equal(o.fps(xb.to(dev), 80).cpu().numpy(), wantc))
+    env(**{k: None for k in kw})
+xc = (torch.rand(2, 4100, 3, generator=g) * 2 - 1)
+env(UPP_FPS_CLUSTER=4, UPP_FPS_CLUSTER_AHEAD=1)
+check("fps cluster4_ahead", np.array_equal(o.fps(xc.to(dev), 70).cpu().numpy(), O.fps(xc.numpy(), 70)))
+env(UPP_FPS_CLUSTER=None, UPP_FPS_CLUSTER_AHEAD=None)
 # Group: single launch in every cluster shape (producer / consumer warps, DSMEM centre table), two launches
 xg = (torch.rand(3, 600, 3, generator=g) * 2 - 1)
 wg = O.group(xg.numpy(), 20, 16)
