@@ -134,6 +134,10 @@ __device__ __forceinline__ void warp_topk_tile(const float* s_ref, int tile, int
     //  distance with >= k elements strictly below it, REDUX.ADD per probe -- cuts the insertions per 1024-reference
     //  query from ~100 to ~13 but costs as many instructions as it saves: 15.4 us either way, 29.2 -> 31.7 us at
     //  B = 128.  The per-query instruction budget (2400) is spread over control flow, not concentrated in insertions.)
+    // (Seeding with the 32 smallest of the 64 per-lane TWO smallest -- one more row sort + one bitonic merge, ~12 insertions
+    //  per 1024 references instead of ~100 -- measured in round 2: Group(64,32) 20.6 -> 20.8 us, Group(32,16) on 1096
+    //  points 18.6 -> 20.5 us, interpolation forward 63.9 -> 66.8 us; only C4's throughput-bound Group(64,32) at B = 128
+    //  gained, 37.0 -> 34.9 us.  With k = 16 the 16th of the 32 lane minima is tight already.  Left out.)
     if (!st.seeded) {
       st.seeded = true;
       st.ld = lmin;
