@@ -1,5 +1,7 @@
+"""Device activities (kernels, copies) of ONE headline step through the module API and through the unchanged call sites,
+in start order (torch profiler): what sits on the end-to-end critical path besides our kernels."""
 import os, sys, json
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "iccv2025-upp_b200"), os.path.join(ROOT, "iccv2025-upp_b200", "dropin"), ROOT):
     sys.path.insert(0, p)
 import torch
